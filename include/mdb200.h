@@ -1,0 +1,193 @@
+/*
+ * mdb200.h -- C ABI of the B200-native engine for MolecularDynamics.jl's per-step hot path.
+ *
+ * The reference (Julia, /root/reference) has no FFI today: its boundary is the Julia-level
+ * run_simulation!/initialize_state/Parameters API and the Potential + evaluate plugin contract.
+ * Each entry point below names the reference code it replaces (paths relative to /root/reference).
+ * The Julia-side binding a maintainer adds (`ccall` stubs + GPUSystem) is julia/MolecularDynamicsB200.jl
+ * and is walked through in INTEGRATION.md; the Python mirror used by tests/bench is
+ * moleculardynamics.jl_b200/ (ctypes).
+ *
+ * Conventions
+ *  - plain C, opaque handle, int status returns (0 = MDB_OK); no exceptions cross the boundary;
+ *    mdb_last_error() gives the message of the last failure on that handle (or of mdb_create).
+ *  - host arrays are AoS [n][dim] Float64 / Int32 in C order, i.e. exactly
+ *    reinterpret(Float64, ::Vector{MVector{dim,Float64}}) (src/initialization.jl:44,93,97,137);
+ *    particle order on the host side is always the caller's original order.
+ *  - the library owns all device memory; one handle is driven by one host thread.
+ *  - there is NO CPU fallback: without a CUDA device mdb_create fails with MDB_ERR_NO_DEVICE.
+ */
+#ifndef MDB200_H
+#define MDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_VERSION 100
+
+typedef struct mdb_engine_s *mdb_handle;
+
+enum mdb_status {
+    MDB_OK = 0,
+    MDB_ERR_INVALID_ARG = 1,
+    MDB_ERR_CUDA = 2,
+    MDB_ERR_UNSUPPORTED_POTENTIAL = 3, /* Potential subtype without a device functor (src/types.jl:4-6 errors likewise) */
+    MDB_ERR_UNSUPPORTED_CELL = 4,      /* non-diagonal unit cell (to_unitcell matrix branch, src/initialization.jl:13-15) */
+    MDB_ERR_BOX_TOO_SMALL = 5,         /* cutoff >= L/2 in a periodic direction */
+    MDB_ERR_NO_DEVICE = 6,
+    MDB_ERR_NCCL = 7,
+    MDB_ERR_STATE = 8,                 /* e.g. run before velocities were set */
+    MDB_ERR_NONFINITE = 9,             /* overlap / blow-up detected: non-finite energy */
+    MDB_ERR_NVRTC = 10
+};
+
+/* Potential subtype -> device functor tag (src/potentials.jl, README.md:82-145) */
+enum mdb_potential {
+    MDB_POT_PSEUDOHS = 0, /* PseudoHS: no parameters (lambda = 50 fixed, src/potentials.jl:11-29) */
+    MDB_POT_LJ = 1,       /* LennardJones: params = {epsilon, r_cut} (src/potentials.jl:160-164, 66-77) */
+    MDB_POT_LJ_XPLOR = 2, /* LennardJonesXPLOR: params = {epsilon, r_on, r_cut} (src/potentials.jl:217-249) */
+    MDB_POT_POLY = 3,     /* non-additive Polydisperse plugin: params = {rcut, non_additivity} (README.md:89-145) */
+    MDB_POT_USER = 100    /* user CUDA-C `evaluate` body compiled with NVRTC (mdb_set_user_potential) */
+};
+
+/* Ensemble subtypes (src/types.jl:34-51) */
+enum mdb_ensemble { MDB_NVE = 0, MDB_NVT = 1, MDB_BROWNIAN = 2 };
+
+/* Neighbour strategy.  Results are identical (same pair set, same per-pair arithmetic); only cost differs. */
+enum mdb_mode {
+    MDB_MODE_AUTO = 0,
+    MDB_MODE_CELLS = 1, /* cell list rebuilt and particles re-sorted EVERY step (the reference's shape, src/simulation.jl:100) */
+    MDB_MODE_LIST = 2   /* Verlet list with skin, rebuilt from the cell list when the displacement bound is reached */
+};
+
+typedef struct mdb_config {
+    int32_t dim;            /* 2 or 3                       (initialize_state(dimension=...), src/initialization.jl:116) */
+    int32_t potential;      /* enum mdb_potential           (Parameters.potential, src/types.jl:12) */
+    int64_t n_particles;    /* global particle count        (Parameters.n_particles, src/types.jl:10) */
+    double unitcell[9];     /* row-major 3x3, upper-left dim x dim used; must be diagonal (SimulationState.unitcell) */
+    double cutoff;          /* neighbour cutoff             (initialize_state(cutoff=1.5), src/initialization.jl:118) */
+    double pot_params[8];   /* see enum mdb_potential */
+    uint64_t seed;          /* key of the counter-based RNG (replaces SimulationState.rng, src/types.jl:21) */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t mode;           /* enum mdb_mode */
+    double skin;            /* Verlet skin for MDB_MODE_LIST; <= 0 picks a default */
+    int32_t use_graph;      /* 1: replay each step as a CUDA graph (conditional rebuild node); 0: eager launches */
+    int32_t rank;           /* slab decomposition along x: this handle owns x in [rank, rank+1) * Lx / nranks */
+    int32_t nranks;         /* 1 = single domain */
+    int32_t reserved[5];
+} mdb_config;
+
+typedef struct mdb_stats {
+    int64_t steps;            /* MD steps executed since creation */
+    int64_t rebuilds;         /* cell/list rebuilds */
+    int64_t kernel_launches;  /* kernels launched by this library (graph kernel nodes counted per replay) */
+    int64_t n_owned;          /* particles owned by this handle */
+    int64_t n_ghost;          /* ghost particles currently held (nranks > 1) */
+    int64_t list_capacity;    /* neighbour slots per particle (MDB_MODE_LIST) */
+    int64_t max_neighbors;    /* largest neighbour count seen at the last rebuild */
+    double r_search;          /* min(cutoff, potential range): radius the force kernels search */
+    double cell_len[3];
+    int32_t ncell[3];
+    int32_t mode;             /* resolved mode */
+    double last_run_ms;       /* device time of the last mdb_run_* call (CUDA events) */
+    double last_force_ms;     /* device time of the pair-force kernel of the last step of that call (eager mode only) */
+} mdb_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+int mdb_version(void);
+/* message of the most recent failure (per handle; h == NULL: last failure of mdb_create on this thread) */
+const char *mdb_last_error(mdb_handle h);
+/* replaces CellListMap.ParticleSystem(...) construction at src/initialization.jl:100-107 + SimulationState (:140-142) */
+int mdb_create(const mdb_config *cfg, mdb_handle *out);
+int mdb_destroy(mdb_handle h);
+
+/* ---- state transfer (host arrays in original particle order) --------------------------------------------- */
+/* positions/diameters required; velocities, forces, images may be NULL (zeros: src/initialization.jl:97-99,137).
+ * Positions are wrapped into the unit cell on upload with wrap_to_box arithmetic (src/boundary.jl:7-17), images
+ * accumulate the crossings, so x + U*img is preserved.  With nranks > 1 every rank passes the GLOBAL arrays and
+ * keeps the particles of its slab. */
+int mdb_upload(mdb_handle h, const double *positions, const double *velocities, const double *forces,
+               const double *diameters, const int32_t *images);
+/* state.velocities = initialize_velocities(...) assignment (README.md:38-41) */
+int mdb_set_velocities(mdb_handle h, const double *velocities);
+/* any pointer may be NULL.  nranks == 1: arrays are [n_particles][dim] in original order.
+ * nranks > 1: use mdb_download_owned. */
+int mdb_download(mdb_handle h, double *positions, double *velocities, double *forces, int32_t *images);
+/* owned particles of this rank, in device slot order, with their original indices; arrays sized for capacity rows;
+ * *count receives the number written. */
+int mdb_download_owned(mdb_handle h, int64_t capacity, int32_t *ids, double *positions, double *velocities,
+                       double *forces, int32_t *images, int64_t *count);
+
+/* ---- the force path alone ----------------------------------------------------------------------------- */
+/* reset_output! + CellListMap.map_pairwise!(energy_and_forces!) (src/simulation.jl:99-104, src/pairwise.jl:26-39,
+ * src/minimize.jl:71-72): fills the resident forces; returns energy, virial and the number of pairs that passed
+ * the potential's own range test (each unordered pair once; rank-local share when nranks > 1). */
+int mdb_compute_forces(mdb_handle h, double *energy, double *virial, int64_t *n_pairs);
+/* debug: number of unordered pairs with minimum-image d2 <= cutoff^2 (what map_pairwise! would visit), and optionally
+ * each particle's neighbour count in original order (nranks == 1 only). */
+int mdb_count_pairs(mdb_handle h, double cutoff, int64_t *n_pairs, int32_t *per_particle);
+
+/* ---- the step loop (src/simulation.jl:88-108 and :231-250) ---------------------------------------------- */
+/* thermo, when not NULL, receives one row per step: {U, W, KE, n_pairs} = potential energy, virial, kinetic energy after
+ * the ensemble step (0 for Brownian), interacting pairs.  Forces are NOT primed before step 0. */
+/* integrate_half! -> forces -> integrate_second_half! -> ensemble_step!(::NVE)  (src/integrate.jl:8-44) */
+int mdb_run_nve(mdb_handle h, int64_t nsteps, double dt, double *thermo);
+/* ... -> ensemble_step!(::NVT): bussi! with T0 = ktemp_per_step[s] = ensemble.ktemp(step+1) (src/integrate.jl:46-53,
+ * src/thermostat.jl:20-48); nf = dim*(N-1) as src/initialization.jl:124 */
+int mdb_run_nvt(mdb_handle h, int64_t nsteps, double dt, const double *ktemp_per_step, double tau, double *thermo);
+/* forces -> integrate_brownian! (src/simulation.jl:231-250, src/integrate.jl:66-82; intended semantics) */
+int mdb_run_brownian(mdb_handle h, int64_t nsteps, double dt, double ktemp, double *thermo);
+/* {U, W, KE, n_pairs} of the most recent force evaluation / step */
+int mdb_thermo(mdb_handle h, double out[4]);
+
+/* ---- FIRE minimiser (src/minimize.jl:31-135), second caller of the force path ----------------------------- */
+typedef struct mdb_fire_params {
+    int64_t max_steps;
+    double tol, dt_initial, dt_max, alpha0, f_inc, f_dec;
+    int32_t n_min;
+    int32_t reserved;
+} mdb_fire_params;
+/* out: {energy, F_rms, steps_done}; *converged = 1 when F_norm/sqrt(ndof) < tol */
+int mdb_fire_minimize(mdb_handle h, const mdb_fire_params *p, double out[3], int32_t *converged);
+
+/* ---- thermostat test hooks --------------------------------------------------------------------------- */
+/* scale factor of bussi! (src/thermostat.jl:38-43) evaluated ON THE DEVICE from injected noises */
+int mdb_bussi_scale_from(mdb_handle h, double kinetic_energy, double ktemp, double nf, double dt, double tau, double r1,
+                         double r2, double *scale);
+/* the (r1, r2) = (randn, sum_noises(nf-1)) the device draws for RNG step `step` (src/thermostat.jl:1-18,35-36) */
+int mdb_bussi_noises(mdb_handle h, uint64_t step, double nf, double *r1, double *r2);
+/* engine-wide step counter that keys the RNG; run calls advance it */
+int mdb_get_rng_step(mdb_handle h, uint64_t *step);
+int mdb_set_rng_step(mdb_handle h, uint64_t step);
+
+/* ---- user-defined Potential (src/types.jl:1-6 plugin contract) on the device, compiled with NVRTC --------- */
+/* `body` is the CUDA-C body of
+ *   __device__ bool evaluate(double r, double sigma1, double sigma2, const double* p, double& u, double& f)
+ * returning true when the pair interacts.  `range` = largest r at which it can return true. Must be called before
+ * mdb_upload; sets cfg.potential = MDB_POT_USER. */
+int mdb_set_user_potential(mdb_handle h, const char *body, const double *params, int32_t n_params, double range);
+
+/* ---- multi-GPU slabs (new; the reference is single-process) --------------------------------------------- */
+/* 128-byte NCCL unique id: rank 0 calls mdb_comm_unique_id and ships it to the others (torch.distributed broadcast) */
+int mdb_comm_unique_id(char id[128]);
+/* join the slab ring: ncclCommInitRank; ghost + migration exchange use ncclSend/ncclRecv, observables ncclAllReduce */
+int mdb_comm_init(mdb_handle h, const char id[128]);
+/* in-process ring of handles on the same device (tests / single-GPU emulation of the slab protocol; no NCCL) */
+int mdb_comm_init_local(mdb_handle *handles, int32_t count);
+
+/* ---- introspection ------------------------------------------------------------------------------------ */
+int mdb_get_stats(mdb_handle h, mdb_stats *out);
+/* device pointer to resident arrays, for zero-copy interop (CUDA.jl CuArray / torch tensor views).
+ * which: 0 pos4 {x,y,z,sigma} [n], 1 velocities SoA, 2 forces SoA, 3 images SoA, 4 ids; *stride = SoA component stride */
+int mdb_device_ptr(mdb_handle h, int32_t which, void **ptr, int64_t *stride);
+/* the CUDA stream the engine launches on (cudaStream_t), so callers can order their own work / events after it */
+int mdb_stream(mdb_handle h, void **stream);
+int mdb_synchronize(mdb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDB200_H */

@@ -1,0 +1,292 @@
+"""ctypes binding of the C ABI in include/mdb200.h (csrc/libmdb200.so).
+
+Fails loudly when the CUDA library is missing or no device is present: there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+# enum mdb_status
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED_POTENTIAL, ERR_UNSUPPORTED_CELL, ERR_BOX_TOO_SMALL = 0, 1, 2, 3, 4, 5
+ERR_NO_DEVICE, ERR_NCCL, ERR_STATE, ERR_NONFINITE, ERR_NVRTC = 6, 7, 8, 9, 10
+STATUS_NAMES = {0: "MDB_OK", 1: "MDB_ERR_INVALID_ARG", 2: "MDB_ERR_CUDA", 3: "MDB_ERR_UNSUPPORTED_POTENTIAL",
+                4: "MDB_ERR_UNSUPPORTED_CELL", 5: "MDB_ERR_BOX_TOO_SMALL", 6: "MDB_ERR_NO_DEVICE", 7: "MDB_ERR_NCCL",
+                8: "MDB_ERR_STATE", 9: "MDB_ERR_NONFINITE", 10: "MDB_ERR_NVRTC"}
+POT_PSEUDOHS, POT_LJ, POT_LJ_XPLOR, POT_POLY, POT_USER = 0, 1, 2, 3, 100
+NVE, NVT, BROWNIAN = 0, 1, 2
+MODE_AUTO, MODE_CELLS, MODE_LIST = 0, 1, 2
+
+# every symbol include/mdb200.h declares (tests/test_capi_symbols.py checks the header against this list and the .so)
+SYMBOLS = [
+    "mdb_version", "mdb_last_error", "mdb_create", "mdb_destroy", "mdb_upload", "mdb_set_velocities", "mdb_download",
+    "mdb_download_owned", "mdb_compute_forces", "mdb_count_pairs", "mdb_run_nve", "mdb_run_nvt", "mdb_run_brownian",
+    "mdb_thermo", "mdb_fire_minimize", "mdb_bussi_scale_from", "mdb_bussi_noises", "mdb_get_rng_step",
+    "mdb_set_rng_step", "mdb_set_user_potential", "mdb_comm_unique_id", "mdb_comm_init", "mdb_comm_init_local",
+    "mdb_get_stats", "mdb_device_ptr", "mdb_stream", "mdb_synchronize",
+]
+
+
+class MdbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(code, code), msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("potential", C.c_int32), ("n_particles", C.c_int64), ("unitcell", C.c_double * 9),
+                ("cutoff", C.c_double), ("pot_params", C.c_double * 8), ("seed", C.c_uint64), ("device", C.c_int32),
+                ("mode", C.c_int32), ("skin", C.c_double), ("use_graph", C.c_int32), ("rank", C.c_int32),
+                ("nranks", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("kernel_launches", C.c_int64), ("n_owned", C.c_int64),
+                ("n_ghost", C.c_int64), ("list_capacity", C.c_int64), ("max_neighbors", C.c_int64),
+                ("r_search", C.c_double), ("cell_len", C.c_double * 3), ("ncell", C.c_int32 * 3), ("mode", C.c_int32),
+                ("last_run_ms", C.c_double), ("last_force_ms", C.c_double)]
+
+
+class FireParams(C.Structure):
+    _fields_ = [("max_steps", C.c_int64), ("tol", C.c_double), ("dt_initial", C.c_double), ("dt_max", C.c_double),
+                ("alpha0", C.c_double), ("f_inc", C.c_double), ("f_dec", C.c_double), ("n_min", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_H = C.c_void_p
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load csrc/libmdb200.so; raises if it has not been built (build with __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError("%s is missing: build it with `python __graft_entry__.py build` "
+                           "(nvcc, sm_100a). There is no CPU fallback." % path)
+    L = C.CDLL(path)
+    L.mdb_version.restype = C.c_int
+    L.mdb_last_error.restype = C.c_char_p
+    L.mdb_last_error.argtypes = [_H]
+    L.mdb_create.argtypes = [C.POINTER(Config), C.POINTER(_H)]
+    L.mdb_destroy.argtypes = [_H]
+    L.mdb_upload.argtypes = [_H, _dp, _dp, _dp, _dp, _ip]
+    L.mdb_set_velocities.argtypes = [_H, _dp]
+    L.mdb_download.argtypes = [_H, _dp, _dp, _dp, _ip]
+    L.mdb_download_owned.argtypes = [_H, C.c_int64, _ip, _dp, _dp, _dp, _ip, C.POINTER(C.c_int64)]
+    L.mdb_compute_forces.argtypes = [_H, _dp, _dp, C.POINTER(C.c_int64)]
+    L.mdb_count_pairs.argtypes = [_H, C.c_double, C.POINTER(C.c_int64), _ip]
+    L.mdb_run_nve.argtypes = [_H, C.c_int64, C.c_double, _dp]
+    L.mdb_run_nvt.argtypes = [_H, C.c_int64, C.c_double, _dp, C.c_double, _dp]
+    L.mdb_run_brownian.argtypes = [_H, C.c_int64, C.c_double, C.c_double, _dp]
+    L.mdb_thermo.argtypes = [_H, _dp]
+    L.mdb_fire_minimize.argtypes = [_H, C.POINTER(FireParams), _dp, _ip]
+    L.mdb_bussi_scale_from.argtypes = [_H] + [C.c_double] * 7 + [_dp]
+    L.mdb_bussi_noises.argtypes = [_H, C.c_uint64, C.c_double, _dp, _dp]
+    L.mdb_get_rng_step.argtypes = [_H, C.POINTER(C.c_uint64)]
+    L.mdb_set_rng_step.argtypes = [_H, C.c_uint64]
+    L.mdb_set_user_potential.argtypes = [_H, C.c_char_p, _dp, C.c_int32, C.c_double]
+    L.mdb_comm_unique_id.argtypes = [C.c_char_p]
+    L.mdb_comm_init.argtypes = [_H, C.c_char_p]
+    L.mdb_comm_init_local.argtypes = [C.POINTER(_H), C.c_int32]
+    L.mdb_get_stats.argtypes = [_H, C.POINTER(Stats)]
+    L.mdb_device_ptr.argtypes = [_H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.mdb_stream.argtypes = [_H, C.POINTER(C.c_void_p)]
+    L.mdb_synchronize.argtypes = [_H]
+    for name in SYMBOLS:
+        if name not in ("mdb_last_error",):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError("expected array of shape %s, got %s" % (shape, a.shape))
+    return a
+
+
+class Engine:
+    """Thin object wrapper over one mdb_handle (one GPU, one host thread)."""
+
+    def __init__(self, dim, n_particles, box, cutoff, potential, pot_params=(), seed=0, device=0, mode=MODE_AUTO,
+                 skin=0.0, use_graph=True, rank=0, nranks=1):
+        L = load()
+        cfg = Config()
+        cfg.dim = dim
+        cfg.potential = potential
+        cfg.n_particles = n_particles
+        box = np.asarray(box, dtype=np.float64)
+        cell = np.zeros((3, 3))
+        if box.ndim == 0:
+            cell[:dim, :dim] = np.eye(dim) * float(box)
+        elif box.ndim == 1:
+            cell[:dim, :dim] = np.diag(box[:dim])
+        else:
+            cell[:dim, :dim] = box[:dim, :dim]
+        cfg.unitcell = (C.c_double * 9)(*cell.ravel())
+        cfg.cutoff = cutoff
+        pp = np.zeros(8)
+        pot_params = np.asarray(pot_params, dtype=np.float64).ravel()
+        pp[: pot_params.size] = pot_params
+        cfg.pot_params = (C.c_double * 8)(*pp)
+        cfg.seed = seed
+        cfg.device = device
+        cfg.mode = mode
+        cfg.skin = skin or 0.0
+        cfg.use_graph = 1 if use_graph else 0
+        cfg.rank = rank
+        cfg.nranks = nranks
+        self._lib = L
+        self.dim = dim
+        self.n = n_particles
+        self.box = np.array([cell[k, k] for k in range(dim)])
+        self._h = _H()
+        rc = L.mdb_create(C.byref(cfg), C.byref(self._h))
+        if rc != OK:
+            raise MdbError(rc, (L.mdb_last_error(None) or b"").decode())
+
+    def _check(self, rc):
+        if rc != OK:
+            raise MdbError(rc, (self._lib.mdb_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mdb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # state -------------------------------------------------------------------------------------------
+    def upload(self, positions, diameters, velocities=None, forces=None, images=None):
+        shape = (self.n, self.dim)
+        x = _f64(positions, shape)
+        d = _f64(diameters, (self.n,))
+        v = _f64(velocities, shape)
+        f = _f64(forces, shape)
+        im = None if images is None else np.ascontiguousarray(images, dtype=np.int32)
+        self._check(self._lib.mdb_upload(self._h, _d(x), _d(v), _d(f), _d(d), _i(im)))
+
+    def set_velocities(self, velocities):
+        v = _f64(velocities, (self.n, self.dim))
+        self._check(self._lib.mdb_set_velocities(self._h, _d(v)))
+
+    def download(self, positions=True, velocities=True, forces=True, images=True):
+        shape = (self.n, self.dim)
+        x = np.empty(shape) if positions else None
+        v = np.empty(shape) if velocities else None
+        f = np.empty(shape) if forces else None
+        im = np.empty(shape, dtype=np.int32) if images else None
+        self._check(self._lib.mdb_download(self._h, _d(x), _d(v), _d(f), _i(im)))
+        return x, v, f, im
+
+    def download_into(self, x=None, v=None, f=None, im=None):
+        self._check(self._lib.mdb_download(self._h, _d(x), _d(v), _d(f), _i(im)))
+
+    # physics -----------------------------------------------------------------------------------------
+    def compute_forces(self):
+        e, w, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self._lib.mdb_compute_forces(self._h, C.byref(e), C.byref(w), C.byref(n)))
+        return e.value, w.value, n.value
+
+    def count_pairs(self, cutoff, per_particle=False):
+        n = C.c_int64()
+        per = np.zeros(self.n, dtype=np.int32) if per_particle else None
+        self._check(self._lib.mdb_count_pairs(self._h, cutoff, C.byref(n), _i(per)))
+        return (n.value, per) if per_particle else n.value
+
+    def run_nve(self, nsteps, dt, thermo=True):
+        t = np.zeros((nsteps, 4)) if thermo else None
+        self._check(self._lib.mdb_run_nve(self._h, nsteps, dt, _d(t)))
+        return t
+
+    def run_nvt(self, nsteps, dt, ktemp, tau, thermo=True):
+        kt = np.ascontiguousarray(np.broadcast_to(np.asarray(ktemp, dtype=np.float64), (max(nsteps, 1),)))
+        t = np.zeros((nsteps, 4)) if thermo else None
+        self._check(self._lib.mdb_run_nvt(self._h, nsteps, dt, _d(kt), tau, _d(t)))
+        return t
+
+    def run_brownian(self, nsteps, dt, ktemp, thermo=True):
+        t = np.zeros((nsteps, 4)) if thermo else None
+        self._check(self._lib.mdb_run_brownian(self._h, nsteps, dt, ktemp, _d(t)))
+        return t
+
+    def thermo(self):
+        out = np.zeros(4)
+        self._check(self._lib.mdb_thermo(self._h, _d(out)))
+        return out
+
+    def fire_minimize(self, max_steps=10000, tol=1e-6, dt_initial=0.01, dt_max=0.1, alpha0=0.1, f_inc=1.2, f_dec=0.2,
+                      n_min=5):
+        p = FireParams(max_steps, tol, dt_initial, dt_max, alpha0, f_inc, f_dec, n_min, 0)
+        out = np.zeros(3)
+        conv = C.c_int32()
+        self._check(self._lib.mdb_fire_minimize(self._h, C.byref(p), _d(out), C.byref(conv)))
+        return out[0], out[1], int(out[2]), bool(conv.value)
+
+    def bussi_scale_from(self, ke, ktemp, nf, dt, tau, r1, r2):
+        s = C.c_double()
+        self._check(self._lib.mdb_bussi_scale_from(self._h, ke, ktemp, nf, dt, tau, r1, r2, C.byref(s)))
+        return s.value
+
+    def bussi_noises(self, step, nf):
+        r1, r2 = C.c_double(), C.c_double()
+        self._check(self._lib.mdb_bussi_noises(self._h, step, nf, C.byref(r1), C.byref(r2)))
+        return r1.value, r2.value
+
+    @property
+    def rng_step(self):
+        s = C.c_uint64()
+        self._check(self._lib.mdb_get_rng_step(self._h, C.byref(s)))
+        return s.value
+
+    @rng_step.setter
+    def rng_step(self, value):
+        self._check(self._lib.mdb_set_rng_step(self._h, value))
+
+    def set_user_potential(self, body, params=(), rng=1.0):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(self._lib.mdb_set_user_potential(self._h, body.encode(), _d(p), p.size, rng))
+
+    def stats(self):
+        s = Stats()
+        self._check(self._lib.mdb_get_stats(self._h, C.byref(s)))
+        return {k: (list(getattr(s, k)) if hasattr(getattr(s, k), "__len__") else getattr(s, k)) for k, _ in s._fields_}
+
+    def device_ptr(self, which):
+        p, st = C.c_void_p(), C.c_int64()
+        self._check(self._lib.mdb_device_ptr(self._h, which, C.byref(p), C.byref(st)))
+        return p.value, st.value
+
+    def stream(self):
+        p = C.c_void_p()
+        self._check(self._lib.mdb_stream(self._h, C.byref(p)))
+        return p.value
+
+    def synchronize(self):
+        self._check(self._lib.mdb_synchronize(self._h))

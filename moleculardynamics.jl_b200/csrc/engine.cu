@@ -1,0 +1,994 @@
+// engine.cu -- host side of the C ABI declared in include/mdb200.h: device memory, streams, CUDA graphs,
+// kernel dispatch.  No CPU compute path exists here: every physics operation is a kernel in kernels.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mdb200.h"
+#include "kernels.cuh"
+
+using namespace mdb;
+
+#define MDB_EXPORT extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string g_create_error;
+
+struct GraphKey {
+    int ensemble = -1;
+    double dt = 0, tau = 0, ktemp = 0;
+    int thermo = 0;
+    bool operator==(const GraphKey &o) const
+    {
+        return ensemble == o.ensemble && dt == o.dt && tau == o.tau && ktemp == o.ktemp && thermo == o.thermo;
+    }
+};
+
+struct mdb_engine_s {
+    mdb_config cfg;
+    int dim = 3;
+    int64_t N = 0;  // global particle count
+    int n = 0;      // particles resident on this handle
+    int64_t cap = 0;
+    double L[3] = {1, 1, 1};
+    double smin = 1, smax = 1;
+    double r_search = 0, skin = 0, r_grid = 0, cutoff2 = 0;
+    int mode = MDB_MODE_CELLS;  // resolved: CELLS, LIST; brute = tiny-box all-pairs
+    bool brute = false;
+    bool uploaded = false, have_vel = false;
+    Grid grid;
+    int64_t ncell = 0;
+    PotParams pp;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evf0 = nullptr, evf1 = nullptr;
+
+    StatePtrs st[2];
+    uint32_t *cell_of = nullptr, *slot_of = nullptr, *counts = nullptr, *start = nullptr, *order = nullptr, *tile_sums = nullptr;
+    int ntiles = 0;
+    uint32_t *nl = nullptr;
+    int32_t *nnbr = nullptr;
+    int kmax = 0;
+    int64_t nl_stride = 0;
+    double *part = nullptr, *disp_part = nullptr;
+    DevCtl *ctl = nullptr;
+    DevCtl *h_ctl = nullptr;  // pinned mirror
+    double *d_thermo = nullptr, *d_ktemp = nullptr, *d_scratch = nullptr;
+    unsigned long long *d_count = nullptr;
+    int64_t chunk = 4096;
+    // host<->device staging (AoS images)
+    double *sx = nullptr, *sv = nullptr, *sf = nullptr, *sd = nullptr;
+    int32_t *si = nullptr, *sid = nullptr;
+    int64_t stage_n = 0;
+
+    cudaGraphExec_t gexec = nullptr;
+    cudaGraph_t graph = nullptr;
+    GraphKey gkey;
+    int graph_kernels_fixed = 0, graph_kernels_rebuild = 0;
+
+    mdb_stats stats;
+    uint64_t rng_step = 0;
+    std::string err;
+};
+
+typedef mdb_engine_s Engine;
+
+static int fail(Engine *e, int code, const std::string &msg)
+{
+    if (e) e->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                            \
+    do {                                                                                                    \
+        cudaError_t _e = (call);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(e, MDB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+    } while (0)
+
+static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
+
+template <class F>
+static bool dispatch_pot(int tag, F &&f)
+{
+    switch (tag) {
+    case MDB_POT_PSEUDOHS: f(PotPHS{}); return true;
+    case MDB_POT_LJ: f(PotLJ{}); return true;
+    case MDB_POT_LJ_XPLOR: f(PotXPLOR{}); return true;
+    case MDB_POT_POLY: f(PotPoly{}); return true;
+    }
+    return false;
+}
+
+static double pot_range(const Engine *e)
+{
+    switch (e->cfg.potential) {
+    case MDB_POT_PSEUDOHS: return PotPHS::range(e->pp, e->smin, e->smax);
+    case MDB_POT_LJ: return PotLJ::range(e->pp, e->smin, e->smax);
+    case MDB_POT_LJ_XPLOR: return PotXPLOR::range(e->pp, e->smin, e->smax);
+    case MDB_POT_POLY: return PotPoly::range(e->pp, e->smin, e->smax);
+    }
+    return e->cfg.cutoff;
+}
+
+// ------------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------------
+static void free_state(Engine *e)
+{
+    for (int b = 0; b < 2; b++) {
+        cudaFree(e->st[b].pos); cudaFree(e->st[b].vel); cudaFree(e->st[b].frc); cudaFree(e->st[b].img); cudaFree(e->st[b].id);
+        e->st[b] = StatePtrs{};
+    }
+    cudaFree(e->cell_of); cudaFree(e->slot_of); cudaFree(e->counts); cudaFree(e->start); cudaFree(e->order); cudaFree(e->tile_sums);
+    cudaFree(e->nl); cudaFree(e->nnbr);
+    e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
+    e->nl = nullptr; e->nnbr = nullptr;
+}
+
+static void free_stage(Engine *e)
+{
+    cudaFree(e->sx); cudaFree(e->sv); cudaFree(e->sf); cudaFree(e->sd); cudaFree(e->si); cudaFree(e->sid);
+    e->sx = e->sv = e->sf = e->sd = nullptr; e->si = e->sid = nullptr; e->stage_n = 0;
+}
+
+static int ensure_stage(Engine *e, int64_t n)
+{
+    if (e->stage_n >= n) return MDB_OK;
+    free_stage(e);
+    size_t d = (size_t)e->dim;
+    CU(cudaMalloc(&e->sx, sizeof(double) * n * d));
+    CU(cudaMalloc(&e->sv, sizeof(double) * n * d));
+    CU(cudaMalloc(&e->sf, sizeof(double) * n * d));
+    CU(cudaMalloc(&e->sd, sizeof(double) * n));
+    CU(cudaMalloc(&e->si, sizeof(int32_t) * n * d));
+    CU(cudaMalloc(&e->sid, sizeof(int32_t) * n));
+    e->stage_n = n;
+    return MDB_OK;
+}
+
+static void drop_graph(Engine *e)
+{
+    if (e->gexec) cudaGraphExecDestroy(e->gexec);
+    if (e->graph) cudaGraphDestroy(e->graph);
+    e->gexec = nullptr; e->graph = nullptr; e->gkey = GraphKey{};
+}
+
+// choose grid + neighbour strategy for the resident particle set
+static int plan_neighbors(Engine *e)
+{
+    const int d = e->dim;
+    double range = pot_range(e);
+    e->r_search = std::min(e->cfg.cutoff, range);
+    e->cutoff2 = e->cfg.cutoff * e->cfg.cutoff;
+    for (int k = 0; k < d; k++)
+        if (!(e->r_search < 0.5 * e->L[k]))
+            return fail(e, MDB_ERR_BOX_TOO_SMALL, "search radius must be < L/2 in every periodic direction");
+    double volume = 1.0;
+    for (int k = 0; k < d; k++) volume *= e->L[k];
+    double rho = (double)e->N / volume;
+    double skin = e->cfg.skin > 0 ? e->cfg.skin : 0.25 * e->r_search;
+    auto cells_for = [&](double r, int nc[3]) {
+        bool ok = true;
+        nc[0] = nc[1] = nc[2] = 1;
+        for (int k = 0; k < d; k++) {
+            nc[k] = (int)std::floor(e->L[k] / (r * (1.0 + 1e-6)));
+            if (nc[k] < 3) ok = false;
+        }
+        return ok;
+    };
+    int nc[3];
+    int want = e->cfg.mode;
+    e->brute = false;
+    if ((want == MDB_MODE_AUTO || want == MDB_MODE_LIST) && cells_for(e->r_search + skin, nc)) {
+        e->mode = MDB_MODE_LIST;
+        e->skin = skin;
+        e->r_grid = e->r_search + skin;
+    } else if (cells_for(e->r_search, nc)) {
+        e->mode = MDB_MODE_CELLS;
+        e->skin = 0;
+        e->r_grid = e->r_search;
+    } else {
+        if (e->n > 16384) return fail(e, MDB_ERR_BOX_TOO_SMALL, "box has fewer than 3 cells per direction and N is too large for the all-pairs kernel");
+        e->mode = MDB_MODE_CELLS;
+        e->brute = true;
+        e->skin = 0;
+        e->r_grid = e->r_search;
+        nc[0] = nc[1] = nc[2] = 1;
+    }
+    // very dilute systems: do not allocate far more cells than particles
+    if (!e->brute) {
+        double ncell = (double)nc[0] * nc[1] * nc[2];
+        double limit = std::max(64.0, 8.0 * (double)e->n);
+        if (ncell > limit) {
+            double sc = std::pow(limit / ncell, 1.0 / d);
+            for (int k = 0; k < d; k++) nc[k] = std::max(3, (int)std::floor(nc[k] * sc));
+        }
+    }
+    Grid &g = e->grid;
+    for (int k = 0; k < 3; k++) {
+        g.nc[k] = nc[k];
+        g.L[k] = e->L[k];
+        g.invL[k] = 1.0 / e->L[k];
+        g.hL[k] = 0.5 * e->L[k];
+        g.cinv[k] = (double)nc[k] / e->L[k];
+    }
+    e->ncell = (int64_t)nc[0] * nc[1] * nc[2];
+    // neighbour-slot capacity for the Verlet list
+    if (e->mode == MDB_MODE_LIST) {
+        double rl = e->r_grid;
+        double expect = (d == 3) ? rho * 4.18879020478639 * rl * rl * rl : rho * 3.14159265358979 * rl * rl;
+        int k = (int)std::ceil(expect * 1.6) + 12;
+        k = (k + 3) & ~3;
+        e->kmax = std::max(e->kmax, std::max(16, k));
+    }
+    e->stats.r_search = e->r_search;
+    e->stats.mode = e->mode;
+    for (int k = 0; k < 3; k++) {
+        e->stats.ncell[k] = nc[k];
+        e->stats.cell_len[k] = e->L[k] / nc[k];
+    }
+    return MDB_OK;
+}
+
+static int alloc_neighbors(Engine *e)
+{
+    cudaFree(e->counts); cudaFree(e->start); cudaFree(e->tile_sums); cudaFree(e->nl);
+    e->counts = e->start = e->tile_sums = nullptr; e->nl = nullptr;
+    CU(cudaMalloc(&e->counts, sizeof(uint32_t) * (e->ncell + 1)));
+    CU(cudaMalloc(&e->start, sizeof(uint32_t) * (e->ncell + 1)));
+    e->ntiles = nblk(e->ncell, kScanTile);
+    CU(cudaMalloc(&e->tile_sums, sizeof(uint32_t) * std::max(1, e->ntiles)));
+    if (e->mode == MDB_MODE_LIST) {
+        e->nl_stride = (e->cap + 31) & ~(int64_t)31;
+        CU(cudaMalloc(&e->nl, sizeof(uint32_t) * e->nl_stride * e->kmax));
+    }
+    e->stats.list_capacity = e->mode == MDB_MODE_LIST ? e->kmax : 0;
+    drop_graph(e);
+    return MDB_OK;
+}
+
+static int alloc_state(Engine *e, int64_t n)
+{
+    free_state(e);
+    e->cap = std::max<int64_t>(32, (n + 31) & ~(int64_t)31);
+    for (int b = 0; b < 2; b++) {
+        StatePtrs &s = e->st[b];
+        s.cap = e->cap;
+        CU(cudaMalloc(&s.pos, sizeof(double4) * e->cap));
+        CU(cudaMalloc(&s.vel, sizeof(double) * 3 * e->cap));
+        CU(cudaMalloc(&s.frc, sizeof(double) * 3 * e->cap));
+        CU(cudaMalloc(&s.img, sizeof(int32_t) * 3 * e->cap));
+        CU(cudaMalloc(&s.id, sizeof(int32_t) * e->cap));
+        CU(cudaMemsetAsync(s.vel, 0, sizeof(double) * 3 * e->cap, e->stream));
+        CU(cudaMemsetAsync(s.frc, 0, sizeof(double) * 3 * e->cap, e->stream));
+        CU(cudaMemsetAsync(s.img, 0, sizeof(int32_t) * 3 * e->cap, e->stream));
+    }
+    CU(cudaMalloc(&e->cell_of, sizeof(uint32_t) * e->cap));
+    CU(cudaMalloc(&e->slot_of, sizeof(uint32_t) * e->cap));
+    CU(cudaMalloc(&e->order, sizeof(uint32_t) * e->cap));
+    CU(cudaMalloc(&e->nnbr, sizeof(int32_t) * e->cap));
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch sequences (all on e->stream; also what gets captured into the step graph)
+// ------------------------------------------------------------------------------------------------
+template <int DIM>
+static void enqueue_rebuild(Engine *e)
+{
+    cudaStream_t s = e->stream;
+    const int n = e->n;
+    if (!e->brute) {
+        cudaMemsetAsync(e->counts, 0, sizeof(uint32_t) * (e->ncell + 1), s);
+        k_hash<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->ctl, e->grid, e->cell_of, e->slot_of, e->counts);
+        k_scan_tile_sums<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums);
+        k_scan_tiles<<<1, 1024, 0, s>>>(e->ntiles, e->tile_sums);
+        k_scan_apply<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums, e->start);
+        k_fill<<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->cell_of, e->slot_of, e->start, e->order);
+        k_cellsort<<<nblk(e->ncell, kStreamBlock), kStreamBlock, 0, s>>>(e->ncell, e->start, e->order);
+        k_gather<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->order, e->ctl);
+        k_flip<<<1, 1, 0, s>>>(e->ctl);
+        if (e->mode == MDB_MODE_LIST) {
+            double rl2 = e->r_grid * e->r_grid;
+            k_build_list<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
+                                                                         e->nnbr, e->ctl);
+        }
+    }
+}
+static int rebuild_kernel_count(const Engine *e) { return e->brute ? 0 : (e->mode == MDB_MODE_LIST ? 9 : 8); }
+
+template <int DIM, bool KICK2>
+static void enqueue_force(Engine *e, double dt)
+{
+    cudaStream_t s = e->stream;
+    const int n = e->n;
+    ForceOut out{e->part};
+    int blocks = nblk(n, kForceBlock);
+    dispatch_pot(e->cfg.potential, [&](auto pot) {
+        typedef decltype(pot) Pot;
+        if (e->brute)
+            k_force_brute<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->cutoff2, pot, e->pp, dt, out);
+        else if (e->mode == MDB_MODE_LIST)
+            k_force_list<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->nl, e->nl_stride, e->kmax,
+                                                                       e->nnbr, e->cutoff2, pot, e->pp, dt, out);
+        else
+            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out);
+    });
+}
+
+static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHandle handle, int use_handle)
+{
+    int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
+    k_skin_check<<<1, kStreamBlock, 0, e->stream>>>(nblk(e->n, kStreamBlock), e->disp_part, scale, e->skin, always, e->ctl, handle,
+                                                    use_handle);
+}
+
+static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance)
+{
+    double nf = e->dim * ((double)e->N - 1.0);  // src/initialization.jl:124
+    k_finalize<<<1, kStreamBlock, 0, e->stream>>>(nblk(e->n, kForceBlock), e->part, ensemble, nf, dt, tau, e->d_ktemp, e->cfg.seed,
+                                                  thermo ? e->d_thermo : nullptr, advance, e->ctl);
+}
+
+// the part of one step before the (conditional) rebuild
+template <int DIM>
+static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphConditionalHandle handle, int use_handle)
+{
+    if (ensemble != MDB_BROWNIAN) {
+        k_kick_drift<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl, e->disp_part);
+        enqueue_skin_check(e, dt, handle, use_handle);
+    } else {
+        enqueue_skin_check(e, 1.0, handle, use_handle);
+    }
+}
+// the part of one step after the rebuild
+template <int DIM>
+static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, double ktemp, int thermo)
+{
+    if (ensemble != MDB_BROWNIAN) {
+        enqueue_force<DIM, true>(e, dt);
+        enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
+    } else {
+        enqueue_force<DIM, false>(e, dt);
+        k_brownian<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt),
+                                                                                e->cfg.seed, e->ctl, e->disp_part);
+        enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
+    }
+}
+static int step_fixed_kernels(int ensemble) { return ensemble == MDB_BROWNIAN ? 4 : 4; }
+
+template <int DIM>
+static int build_graph(Engine *e, const GraphKey &key)
+{
+    drop_graph(e);
+    cudaStream_t s = e->stream;
+    CU(cudaGraphCreate(&e->graph, 0));
+    const bool conditional = (e->mode == MDB_MODE_LIST) && !e->brute;
+    cudaGraphConditionalHandle handle = 0;
+    if (conditional) CU(cudaGraphConditionalHandleCreate(&handle, e->graph, 0, cudaGraphCondAssignDefault));
+    // head
+    CU(cudaStreamBeginCaptureToGraph(s, e->graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    enqueue_step_head<DIM>(e, key.ensemble, key.dt, handle, conditional ? 1 : 0);
+    std::vector<cudaGraphNode_t> deps;
+    if (conditional) {
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t *d = nullptr;
+        size_t nd = 0;
+        CU(cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &d, &nd));
+        deps.assign(d, d + nd);
+        cudaGraph_t g2 = nullptr;
+        CU(cudaStreamEndCapture(s, &g2));
+        cudaGraphNodeParams cp = {};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        cudaGraphNode_t cnode;
+        CU(cudaGraphAddNode(&cnode, e->graph, deps.data(), deps.size(), &cp));
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        enqueue_rebuild<DIM>(e);
+        CU(cudaStreamEndCapture(s, &g2));
+        CU(cudaStreamBeginCaptureToGraph(s, e->graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+        enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo);
+        CU(cudaStreamEndCapture(s, &g2));
+    } else {
+        enqueue_rebuild<DIM>(e);
+        enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo);
+        cudaGraph_t g2 = nullptr;
+        CU(cudaStreamEndCapture(s, &g2));
+    }
+    CU(cudaGraphInstantiate(&e->gexec, e->graph, 0));
+    e->gkey = key;
+    return MDB_OK;
+}
+
+static int sync_ctl(Engine *e)
+{
+    CU(cudaMemcpyAsync(e->h_ctl, e->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MDB_OK;
+}
+
+// make sure the neighbour structure matches the resident positions before a stand-alone force evaluation
+template <int DIM>
+static int eager_prepare(Engine *e, double scale)
+{
+    enqueue_skin_check(e, scale, 0, 0);
+    e->stats.kernel_launches += 1;
+    if (e->mode == MDB_MODE_LIST && !e->brute) {
+        CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->h_ctl->need_rebuild) {
+            enqueue_rebuild<DIM>(e);
+            e->stats.kernel_launches += rebuild_kernel_count(e);
+        }
+    } else {
+        enqueue_rebuild<DIM>(e);
+        e->stats.kernel_launches += rebuild_kernel_count(e);
+    }
+    return MDB_OK;
+}
+
+template <int DIM>
+static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const double *ktemp_per_step, double tau, double ktemp,
+                    double *thermo)
+{
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload has not been called");
+    if (ensemble != MDB_BROWNIAN && !e->have_vel)
+        return fail(e, MDB_ERR_STATE, "velocities were never set (state.velocities = initialize_velocities(...), README.md:38-41)");
+    if (nsteps < 0 || !(dt > 0)) return fail(e, MDB_ERR_INVALID_ARG, "nsteps must be >= 0 and dt > 0");
+    if (ensemble == MDB_NVT && (!ktemp_per_step || !(tau > 0))) return fail(e, MDB_ERR_INVALID_ARG, "NVT needs ktemp_per_step and tau > 0");
+    if (ensemble == MDB_BROWNIAN && !(ktemp > 0)) return fail(e, MDB_ERR_INVALID_ARG, "Brownian needs ktemp > 0");
+    cudaStream_t s = e->stream;
+    GraphKey key;
+    key.ensemble = ensemble; key.dt = dt; key.tau = tau; key.ktemp = ktemp; key.thermo = thermo ? 1 : 0;
+    if (e->cfg.use_graph && !(e->gexec && e->gkey == key)) {
+        int rc = build_graph<DIM>(e, key);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(e->ev0, s));
+    int64_t done = 0;
+    unsigned long long rebuilds0 = 0;
+    {
+        int rc = sync_ctl(e);
+        if (rc) return rc;
+        rebuilds0 = e->h_ctl->rebuilds;
+    }
+    while (done < nsteps) {
+        int64_t m = std::min(e->chunk, nsteps - done);
+        if (ensemble == MDB_NVT)
+            CU(cudaMemcpyAsync(e->d_ktemp, ktemp_per_step + done, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(&e->ctl->step, 0, sizeof(unsigned long long), s));
+        for (int64_t q = 0; q < m; q++) {
+            if (e->cfg.use_graph) {
+                CU(cudaGraphLaunch(e->gexec, s));
+            } else {
+                enqueue_step_head<DIM>(e, ensemble, dt, 0, 0);
+                if (e->mode == MDB_MODE_LIST && !e->brute) {
+                    CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, s));
+                    CU(cudaStreamSynchronize(s));
+                    if (e->h_ctl->need_rebuild) enqueue_rebuild<DIM>(e);
+                } else {
+                    enqueue_rebuild<DIM>(e);
+                }
+                bool last = (done + q == nsteps - 1);
+                if (last) CU(cudaEventRecord(e->evf0, s));
+                enqueue_step_tail<DIM>(e, ensemble, dt, tau, ktemp, key.thermo);
+                if (last) CU(cudaEventRecord(e->evf1, s));
+            }
+        }
+        if (thermo) CU(cudaMemcpyAsync(thermo + 4 * done, e->d_thermo, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
+        done += m;
+        // the pinned thermo target / ktemp source must not be overwritten before the copy ran
+        if (done < nsteps) CU(cudaStreamSynchronize(s));
+    }
+    if (ensemble == MDB_NVT) {
+        // the scale of the last step is still pending (it is normally fused into the next kick)
+        k_scale<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, s>>>(e->n, e->ctl);
+        k_reset_alpha<<<1, 1, 0, s>>>(e->ctl);
+        e->stats.kernel_launches += 2;
+    }
+    CU(cudaEventRecord(e->ev1, s));
+    {
+        int rc = sync_ctl(e);
+        if (rc) return rc;
+    }
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->stats.last_run_ms = ms;
+    if (!e->cfg.use_graph && nsteps > 0) {
+        CU(cudaEventElapsedTime(&ms, e->evf0, e->evf1));
+        e->stats.last_force_ms = ms;
+    }
+    unsigned long long nreb = e->h_ctl->rebuilds - rebuilds0;
+    e->stats.steps += nsteps;
+    e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
+    e->stats.kernel_launches += nsteps * step_fixed_kernels(ensemble) + (int64_t)nreb * rebuild_kernel_count(e);
+    e->stats.max_neighbors = e->h_ctl->max_nnbr;
+    e->rng_step = e->h_ctl->rng_step;
+    if (e->mode == MDB_MODE_LIST && e->h_ctl->max_nnbr > e->kmax) {
+        // correctness was kept by the cell fallback; grow the list so the fast path covers everyone next time
+        e->kmax = (e->h_ctl->max_nnbr + 4 + 3) & ~3;
+        int rc = alloc_neighbors(e);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(&e->ctl->list_valid, 0, sizeof(int), s));
+    }
+    if (e->h_ctl->nonfinite) {
+        CU(cudaMemsetAsync(&e->ctl->nonfinite, 0, sizeof(int), s));
+        return fail(e, MDB_ERR_NONFINITE, "non-finite energy: overlapping particles or unstable time step");
+    }
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+MDB_EXPORT int mdb_version(void) { return MDB_VERSION; }
+
+MDB_EXPORT const char *mdb_last_error(mdb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
+{
+    Engine *e = nullptr;
+    if (!cfg || !out) return fail(nullptr, MDB_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->dim != 2 && cfg->dim != 3) return fail(nullptr, MDB_ERR_INVALID_ARG, "dim must be 2 or 3");
+    if (cfg->n_particles < 1 || cfg->n_particles > (1ll << 27)) return fail(nullptr, MDB_ERR_INVALID_ARG, "n_particles out of range (1 .. 2^27 per handle)");
+    if (!(cfg->cutoff > 0)) return fail(nullptr, MDB_ERR_INVALID_ARG, "cutoff must be > 0");
+    for (int r = 0; r < cfg->dim; r++)
+        for (int c = 0; c < cfg->dim; c++) {
+            double v = cfg->unitcell[3 * r + c];
+            if (r != c && v != 0.0) return fail(nullptr, MDB_ERR_UNSUPPORTED_CELL, "only diagonal (orthorhombic) unit cells are supported");
+            if (r == c && !(v > 0)) return fail(nullptr, MDB_ERR_INVALID_ARG, "unit cell diagonal must be positive");
+        }
+    switch (cfg->potential) {
+    case MDB_POT_PSEUDOHS: case MDB_POT_LJ: case MDB_POT_LJ_XPLOR: case MDB_POT_POLY: break;
+    default: return fail(nullptr, MDB_ERR_UNSUPPORTED_POTENTIAL, "no device functor for this Potential subtype (no CPU fallback exists)");
+    }
+    if (cfg->nranks > 1) return fail(nullptr, MDB_ERR_INVALID_ARG, "nranks > 1: slab decomposition is not available in this build");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, MDB_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (this engine has no CPU path)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MDB_ERR_INVALID_ARG, "bad device ordinal");
+    e = new Engine();
+    e->cfg = *cfg;
+    e->dim = cfg->dim;
+    e->N = cfg->n_particles;
+    for (int k = 0; k < 3; k++) e->L[k] = (k < cfg->dim) ? cfg->unitcell[4 * k] : 1.0;
+    memcpy(e->pp.p, cfg->pot_params, sizeof(e->pp.p));
+    memset(&e->stats, 0, sizeof(e->stats));
+    memset(&e->grid, 0, sizeof(e->grid));
+    auto bail = [&](int code) {
+        g_create_error = e->err;
+        mdb_destroy(e);
+        return code;
+    };
+#define CUC(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                                 \
+            return bail(MDB_ERR_CUDA);                                                                    \
+        }                                                                                                 \
+    } while (0)
+    CUC(cudaSetDevice(cfg->device));
+    CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&e->ev0));
+    CUC(cudaEventCreate(&e->ev1));
+    CUC(cudaEventCreate(&e->evf0));
+    CUC(cudaEventCreate(&e->evf1));
+    CUC(cudaMalloc(&e->ctl, sizeof(DevCtl)));
+    CUC(cudaMemset(e->ctl, 0, sizeof(DevCtl)));
+    CUC(cudaMallocHost(&e->h_ctl, sizeof(DevCtl)));
+    memset(e->h_ctl, 0, sizeof(DevCtl));
+    CUC(cudaMalloc(&e->part, sizeof(double) * 4 * kMaxPartials));
+    CUC(cudaMemset(e->part, 0, sizeof(double) * 4 * kMaxPartials));
+    CUC(cudaMalloc(&e->disp_part, sizeof(double) * kMaxPartials));
+    CUC(cudaMemset(e->disp_part, 0, sizeof(double) * kMaxPartials));
+    CUC(cudaMalloc(&e->d_thermo, sizeof(double) * 4 * e->chunk));
+    CUC(cudaMalloc(&e->d_ktemp, sizeof(double) * e->chunk));
+    CUC(cudaMalloc(&e->d_scratch, sizeof(double) * 16));
+    CUC(cudaMalloc(&e->d_count, sizeof(unsigned long long)));
+#undef CUC
+    *out = e;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_destroy(mdb_handle e)
+{
+    if (!e) return MDB_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    drop_graph(e);
+    free_state(e);
+    free_stage(e);
+    cudaFree(e->part); cudaFree(e->disp_part); cudaFree(e->ctl); cudaFree(e->d_thermo); cudaFree(e->d_ktemp); cudaFree(e->d_scratch);
+    cudaFree(e->d_count);
+    if (e->h_ctl) cudaFreeHost(e->h_ctl);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->evf0) cudaEventDestroy(e->evf0);
+    if (e->evf1) cudaEventDestroy(e->evf1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *velocities, const double *forces,
+                          const double *diameters, const int32_t *images)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!positions || !diameters) return fail(e, MDB_ERR_INVALID_ARG, "positions and diameters are required");
+    CU(cudaSetDevice(e->cfg.device));
+    const int64_t n = e->N;
+    const size_t d = (size_t)e->dim;
+    if (n > (int64_t)kMaxPartials * kForceBlock) return fail(e, MDB_ERR_INVALID_ARG, "too many particles for one handle");
+    // diameter extrema decide the potential's range (non-additive mixtures)
+    double smin = diameters[0], smax = diameters[0];
+    for (int64_t i = 1; i < n; i++) {
+        smin = std::min(smin, diameters[i]);
+        smax = std::max(smax, diameters[i]);
+    }
+    if (!(smin > 0) || !std::isfinite(smax)) return fail(e, MDB_ERR_INVALID_ARG, "diameters must be positive and finite");
+    e->smin = smin; e->smax = smax;
+    e->n = (int)n;
+    int rc;
+    if (e->cap < n || !e->st[0].pos) {
+        if ((rc = alloc_state(e, n))) return rc;
+    }
+    if ((rc = ensure_stage(e, n))) return rc;
+    if ((rc = plan_neighbors(e))) return rc;
+    if ((rc = alloc_neighbors(e))) return rc;
+    cudaStream_t s = e->stream;
+    CU(cudaMemcpyAsync(e->sx, positions, sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->sd, diameters, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    if (velocities) CU(cudaMemcpyAsync(e->sv, velocities, sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
+    if (forces) CU(cudaMemcpyAsync(e->sf, forces, sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
+    if (images) CU(cudaMemcpyAsync(e->si, images, sizeof(int32_t) * n * d, cudaMemcpyHostToDevice, s));
+    // control block: buffer 0 live, nothing pending
+    DevCtl c;
+    memset(&c, 0, sizeof(c));
+    c.alpha = 1.0;
+    c.rng_step = e->rng_step;
+    c.st[0] = e->st[0];
+    c.st[1] = e->st[1];
+    *e->h_ctl = c;
+    CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(e->disp_part, 0, sizeof(double) * kMaxPartials, s));
+    int blocks = nblk(n, kStreamBlock);
+    if (e->dim == 3)
+        k_import<3><<<blocks, kStreamBlock, 0, s>>>(n, e->sx, velocities ? e->sv : nullptr, forces ? e->sf : nullptr, e->sd,
+                                                   images ? e->si : nullptr, nullptr, e->st[0], e->grid);
+    else
+        k_import<2><<<blocks, kStreamBlock, 0, s>>>(n, e->sx, velocities ? e->sv : nullptr, forces ? e->sf : nullptr, e->sd,
+                                                   images ? e->si : nullptr, nullptr, e->st[0], e->grid);
+    e->stats.kernel_launches += 1;
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    e->uploaded = true;
+    e->have_vel = velocities != nullptr;
+    e->stats.n_owned = n;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_set_velocities(mdb_handle e, const double *velocities)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload first");
+    if (!velocities) return fail(e, MDB_ERR_INVALID_ARG, "null velocities");
+    CU(cudaSetDevice(e->cfg.device));
+    const int64_t n = e->n;
+    cudaStream_t s = e->stream;
+    CU(cudaMemcpyAsync(e->sv, velocities, sizeof(double) * e->N * e->dim, cudaMemcpyHostToDevice, s));
+    if (e->dim == 3) k_import_vel<3><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->sv, e->ctl);
+    else k_import_vel<2><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->sv, e->ctl);
+    e->stats.kernel_launches += 1;
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    e->have_vel = true;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_download(mdb_handle e, double *positions, double *velocities, double *forces, int32_t *images)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    CU(cudaSetDevice(e->cfg.device));
+    const int64_t n = e->n;
+    const size_t d = (size_t)e->dim;
+    cudaStream_t s = e->stream;
+    int blocks = nblk(n, kStreamBlock);
+    if (e->dim == 3)
+        k_export<3><<<blocks, kStreamBlock, 0, s>>>(n, e->ctl, positions ? e->sx : nullptr, velocities ? e->sv : nullptr,
+                                                   forces ? e->sf : nullptr, images ? e->si : nullptr, 1);
+    else
+        k_export<2><<<blocks, kStreamBlock, 0, s>>>(n, e->ctl, positions ? e->sx : nullptr, velocities ? e->sv : nullptr,
+                                                   forces ? e->sf : nullptr, images ? e->si : nullptr, 1);
+    e->stats.kernel_launches += 1;
+    if (positions) CU(cudaMemcpyAsync(positions, e->sx, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    if (velocities) CU(cudaMemcpyAsync(velocities, e->sv, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    if (forces) CU(cudaMemcpyAsync(forces, e->sf, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    if (images) CU(cudaMemcpyAsync(images, e->si, sizeof(int32_t) * n * d, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_download_owned(mdb_handle e, int64_t capacity, int32_t *ids, double *positions, double *velocities, double *forces,
+                                  int32_t *images, int64_t *count)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    if (capacity < e->n) return fail(e, MDB_ERR_INVALID_ARG, "capacity smaller than the owned particle count");
+    CU(cudaSetDevice(e->cfg.device));
+    const int64_t n = e->n;
+    const size_t d = (size_t)e->dim;
+    cudaStream_t s = e->stream;
+    int blocks = nblk(n, kStreamBlock);
+    if (e->dim == 3)
+        k_export<3><<<blocks, kStreamBlock, 0, s>>>(n, e->ctl, positions ? e->sx : nullptr, velocities ? e->sv : nullptr,
+                                                   forces ? e->sf : nullptr, images ? e->si : nullptr, 0);
+    else
+        k_export<2><<<blocks, kStreamBlock, 0, s>>>(n, e->ctl, positions ? e->sx : nullptr, velocities ? e->sv : nullptr,
+                                                   forces ? e->sf : nullptr, images ? e->si : nullptr, 0);
+    e->stats.kernel_launches += 1;
+    int rc = sync_ctl(e);
+    if (rc) return rc;
+    if (ids) CU(cudaMemcpyAsync(ids, e->h_ctl->st[e->h_ctl->cur].id, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    if (positions) CU(cudaMemcpyAsync(positions, e->sx, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    if (velocities) CU(cudaMemcpyAsync(velocities, e->sv, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    if (forces) CU(cudaMemcpyAsync(forces, e->sf, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    if (images) CU(cudaMemcpyAsync(images, e->si, sizeof(int32_t) * n * d, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (count) *count = n;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_compute_forces(mdb_handle e, double *energy, double *virial, int64_t *n_pairs)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc;
+    CU(cudaEventRecord(e->ev0, e->stream));
+    if (e->dim == 3) {
+        if ((rc = eager_prepare<3>(e, 1.0))) return rc;
+        CU(cudaEventRecord(e->evf0, e->stream));
+        enqueue_force<3, false>(e, 0.0);
+    } else {
+        if ((rc = eager_prepare<2>(e, 1.0))) return rc;
+        CU(cudaEventRecord(e->evf0, e->stream));
+        enqueue_force<2, false>(e, 0.0);
+    }
+    CU(cudaEventRecord(e->evf1, e->stream));
+    enqueue_finalize(e, MDB_BROWNIAN, 0.0, 1.0, 0, 0);  // ensemble 2: no kinetic part, no thermostat
+    e->stats.kernel_launches += 2;
+    CU(cudaEventRecord(e->ev1, e->stream));
+    if ((rc = sync_ctl(e))) return rc;
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->evf0, e->evf1));
+    e->stats.last_force_ms = ms;
+    CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->stats.last_run_ms = ms;
+    e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
+    e->stats.max_neighbors = e->h_ctl->max_nnbr;
+    if (energy) *energy = e->h_ctl->last[0];
+    if (virial) *virial = e->h_ctl->last[1];
+    if (n_pairs) *n_pairs = (int64_t)llround(e->h_ctl->last[3]);
+    if (e->mode == MDB_MODE_LIST && e->h_ctl->max_nnbr > e->kmax) {
+        e->kmax = (e->h_ctl->max_nnbr + 4 + 3) & ~3;
+        if ((rc = alloc_neighbors(e))) return rc;
+        CU(cudaMemsetAsync(&e->ctl->list_valid, 0, sizeof(int), e->stream));
+    }
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_count_pairs(mdb_handle e, double cutoff, int64_t *n_pairs, int32_t *per_particle)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    if (!(cutoff > 0)) return fail(e, MDB_ERR_INVALID_ARG, "cutoff must be > 0");
+    CU(cudaSetDevice(e->cfg.device));
+    for (int k = 0; k < e->dim; k++)
+        if (!(cutoff < 0.5 * e->L[k])) return fail(e, MDB_ERR_BOX_TOO_SMALL, "cutoff must be < L/2");
+    // temporary grid for this cutoff: re-sorts the resident state (order is arbitrary anyway) and invalidates the list
+    Grid saved = e->grid;
+    int64_t saved_ncell = e->ncell;
+    int saved_mode = e->mode;
+    bool saved_brute = e->brute;
+    int nc[3] = {1, 1, 1};
+    bool cells = true;
+    for (int k = 0; k < e->dim; k++) {
+        nc[k] = (int)std::floor(e->L[k] / (cutoff * (1.0 + 1e-6)));
+        if (nc[k] < 3) cells = false;
+    }
+    int64_t ncell = (int64_t)nc[0] * nc[1] * nc[2];
+    if (cells && ncell > saved_ncell) {
+        // keep within the allocated cell arrays by coarsening
+        double sc = std::pow((double)saved_ncell / (double)ncell, 1.0 / e->dim);
+        for (int k = 0; k < e->dim; k++) nc[k] = std::max(3, (int)std::floor(nc[k] * sc));
+        ncell = (int64_t)nc[0] * nc[1] * nc[2];
+        if (ncell > saved_ncell) cells = false;
+    }
+    if (!cells && e->n > 16384) return fail(e, MDB_ERR_BOX_TOO_SMALL, "box too small for a cell grid at this cutoff and N too large for all-pairs");
+    cudaStream_t s = e->stream;
+    if (cells) {
+        for (int k = 0; k < 3; k++) {
+            e->grid.nc[k] = nc[k];
+            e->grid.cinv[k] = (double)nc[k] / e->L[k];
+        }
+        e->ncell = ncell;
+        e->ntiles = nblk(e->ncell, kScanTile);
+        e->mode = MDB_MODE_CELLS;
+        e->brute = false;
+        if (e->dim == 3) enqueue_rebuild<3>(e);
+        else enqueue_rebuild<2>(e);
+        e->stats.kernel_launches += rebuild_kernel_count(e);
+    }
+    int32_t *d_per = nullptr;
+    if (per_particle) d_per = e->si;  // staging, n ints
+    CU(cudaMemsetAsync(e->d_count, 0, sizeof(unsigned long long), s));
+    int blocks = nblk(e->n, kForceBlock);
+    if (e->dim == 3)
+        k_count_pairs<3><<<blocks, kForceBlock, 0, s>>>(e->n, e->ctl, e->grid, e->start, cutoff * cutoff, cells ? 1 : 0, d_per, e->d_count);
+    else
+        k_count_pairs<2><<<blocks, kForceBlock, 0, s>>>(e->n, e->ctl, e->grid, e->start, cutoff * cutoff, cells ? 1 : 0, d_per, e->d_count);
+    e->stats.kernel_launches += 1;
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, e->d_count, sizeof(total), cudaMemcpyDeviceToHost, s));
+    if (per_particle) CU(cudaMemcpyAsync(per_particle, d_per, sizeof(int32_t) * e->n, cudaMemcpyDeviceToHost, s));
+    // restore the production grid; the neighbour structure must be rebuilt before the next force evaluation
+    e->grid = saved;
+    e->ncell = saved_ncell;
+    e->ntiles = nblk(e->ncell, kScanTile);
+    e->mode = saved_mode;
+    e->brute = saved_brute;
+    CU(cudaMemsetAsync(&e->ctl->list_valid, 0, sizeof(int), s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    if (n_pairs) *n_pairs = (int64_t)(total / 2);
+    return MDB_OK;
+}
+
+static int run_dispatch(Engine *e, int ensemble, int64_t nsteps, double dt, const double *kt, double tau, double ktemp, double *thermo)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(e->cfg.device));
+    return e->dim == 3 ? run_impl<3>(e, ensemble, nsteps, dt, kt, tau, ktemp, thermo)
+                       : run_impl<2>(e, ensemble, nsteps, dt, kt, tau, ktemp, thermo);
+}
+
+MDB_EXPORT int mdb_run_nve(mdb_handle e, int64_t nsteps, double dt, double *thermo)
+{
+    return run_dispatch(e, MDB_NVE, nsteps, dt, nullptr, 1.0, 0.0, thermo);
+}
+MDB_EXPORT int mdb_run_nvt(mdb_handle e, int64_t nsteps, double dt, const double *ktemp_per_step, double tau, double *thermo)
+{
+    return run_dispatch(e, MDB_NVT, nsteps, dt, ktemp_per_step, tau, 0.0, thermo);
+}
+MDB_EXPORT int mdb_run_brownian(mdb_handle e, int64_t nsteps, double dt, double ktemp, double *thermo)
+{
+    return run_dispatch(e, MDB_BROWNIAN, nsteps, dt, nullptr, 1.0, ktemp, thermo);
+}
+
+MDB_EXPORT int mdb_thermo(mdb_handle e, double out[4])
+{
+    if (!e || !out) return MDB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = sync_ctl(e);
+    if (rc) return rc;
+    for (int q = 0; q < 4; q++) out[q] = e->h_ctl->last[q];
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_fire_minimize(mdb_handle e, const mdb_fire_params *, double *, int32_t *)
+{
+    return fail(e, MDB_ERR_INVALID_ARG, "mdb_fire_minimize: not available in this build");
+}
+
+MDB_EXPORT int mdb_bussi_scale_from(mdb_handle e, double ke, double ktemp, double nf, double dt, double tau, double r1, double r2,
+                                    double *scale)
+{
+    if (!e || !scale) return MDB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(e->cfg.device));
+    k_bussi_hooks<<<1, 1, 0, e->stream>>>(0, ke, ktemp, nf, dt, tau, r1, r2, 0, 0, e->d_scratch);
+    e->stats.kernel_launches += 1;
+    CU(cudaMemcpyAsync(scale, e->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_bussi_noises(mdb_handle e, uint64_t step, double nf, double *r1, double *r2)
+{
+    if (!e || !r1 || !r2) return MDB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(e->cfg.device));
+    k_bussi_hooks<<<1, 1, 0, e->stream>>>(1, nf, 0, 0, 0, 0, 0, 0, e->cfg.seed, step, e->d_scratch);
+    e->stats.kernel_launches += 1;
+    double h[2];
+    CU(cudaMemcpyAsync(h, e->d_scratch, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *r1 = h[0];
+    *r2 = h[1];
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_get_rng_step(mdb_handle e, uint64_t *step)
+{
+    if (!e || !step) return MDB_ERR_INVALID_ARG;
+    *step = e->rng_step;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_set_rng_step(mdb_handle e, uint64_t step)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    e->rng_step = step;
+    if (e->uploaded) {
+        CU(cudaSetDevice(e->cfg.device));
+        unsigned long long v = step;
+        CU(cudaMemcpyAsync(&e->ctl->rng_step, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_set_user_potential(mdb_handle e, const char *, const double *, int32_t, double)
+{
+    return fail(e, MDB_ERR_NVRTC, "mdb_set_user_potential: not available in this build");
+}
+
+MDB_EXPORT int mdb_comm_unique_id(char *) { return fail(nullptr, MDB_ERR_NCCL, "slab decomposition is not available in this build"); }
+MDB_EXPORT int mdb_comm_init(mdb_handle e, const char *) { return fail(e, MDB_ERR_NCCL, "slab decomposition is not available in this build"); }
+MDB_EXPORT int mdb_comm_init_local(mdb_handle *, int32_t) { return fail(nullptr, MDB_ERR_NCCL, "slab decomposition is not available in this build"); }
+
+MDB_EXPORT int mdb_get_stats(mdb_handle e, mdb_stats *out)
+{
+    if (!e || !out) return MDB_ERR_INVALID_ARG;
+    *out = e->stats;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_device_ptr(mdb_handle e, int32_t which, void **ptr, int64_t *stride)
+{
+    if (!e || !ptr) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = sync_ctl(e);
+    if (rc) return rc;
+    const StatePtrs &s = e->h_ctl->st[e->h_ctl->cur];
+    switch (which) {
+    case 0: *ptr = s.pos; break;
+    case 1: *ptr = s.vel; break;
+    case 2: *ptr = s.frc; break;
+    case 3: *ptr = s.img; break;
+    case 4: *ptr = s.id; break;
+    default: return fail(e, MDB_ERR_INVALID_ARG, "which must be 0..4");
+    }
+    if (stride) *stride = s.cap;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_stream(mdb_handle e, void **stream)
+{
+    if (!e || !stream) return MDB_ERR_INVALID_ARG;
+    *stream = (void *)e->stream;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_synchronize(mdb_handle e)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    return MDB_OK;
+}

@@ -1,0 +1,913 @@
+// kernels.cuh -- sm_100a kernels of the per-step hot path (FP64 throughout, compiled with -fmad=false).
+//
+// Device layout (all resident in HBM, "slot order" = order of the last cell sort):
+//   pos   double4[n]   {x, y, z, sigma}  one 32-byte sector per particle: a neighbour gather costs one sector
+//   vel   double[3][cap], frc double[3][cap]   SoA, coalesced for the integrator sweeps
+//   img   int32[3][cap]  periodic image counters, id int32[cap] original particle index
+// Reference functions replaced are cited per kernel (paths relative to /root/reference).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "potentials.cuh"
+#include "rng.cuh"
+
+namespace mdb {
+
+constexpr int kForceBlock = 128;   // threads per CTA in the pair kernels
+constexpr int kStreamBlock = 256;  // threads per CTA in the streaming (integrator / sort) kernels
+constexpr int kQueue = 8;          // deferred-hit queue depth per thread (sparse-hit potentials)
+constexpr int kMaxPartials = 1 << 17;
+
+struct Grid {
+    int nc[3];
+    double cinv[3];  // nc / L
+    double L[3];
+    double invL[3];  // 1 / L  (IEEE division on the host == the reference's inv(U) for a diagonal cell)
+    double hL[3];    // L / 2
+};
+
+struct StatePtrs {
+    double4 *pos;
+    double *vel;
+    double *frc;
+    int32_t *img;
+    int32_t *id;
+    int64_t cap;  // SoA component stride
+};
+
+// device-resident control block: lets one captured CUDA graph replay every step unchanged
+struct DevCtl {
+    unsigned long long step;      // steps done in the current chunk (row of thermo / ktemp arrays)
+    unsigned long long rng_step;  // engine-wide step counter keying the RNG
+    double alpha;                 // Bussi scale produced by the previous step, applied by the next kick (1 = none)
+    double disp;                  // sum over steps of the largest per-step displacement since the last rebuild
+    double last[4];               // U, W, KE, n_pairs of the most recent evaluation
+    int need_rebuild;
+    int list_valid;
+    int max_nnbr;                 // largest neighbour count at the last list build
+    int nonfinite;
+    int cur;                      // which of the two state buffers is live (flipped on device by the re-sort)
+    int rebuilds_lo;
+    unsigned long long rebuilds;
+    StatePtrs st[2];
+    double fire[8];               // FIRE scalars: dt, alpha, steps_since_neg, converged, P, vnorm2, fnorm2, energy
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// deterministic block reduction of NV values (fixed tree); result valid in thread 0
+template <int NV, int BLOCK, bool MAX = false>
+__device__ __forceinline__ void block_reduce(double (&v)[NV])
+{
+    __shared__ double sm[NV][BLOCK / 32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        v[q] = MAX ? warp_max(v[q]) : warp_sum(v[q]);
+        if (lane == 0) sm[q][w] = v[q];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            double x = (lane < BLOCK / 32) ? sm[q][lane] : (MAX ? 0.0 : 0.0);
+            v[q] = MAX ? warp_max(x) : warp_sum(x);
+        }
+    }
+}
+
+// one 256-bit transaction per particle record (LDG.E.256 / STG.E.256 on sm_100a); pos is 32-byte aligned
+__device__ __forceinline__ double4 ldg_pos(const double4 *p)
+{
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double4 ld_pos(const double4 *p)
+{
+    double4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_pos(double4 *p, const double4 &v)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
+__device__ __forceinline__ int cell_coord(double x, double cinv, int nc)
+{
+    int c = (int)(x * cinv);
+    return c < nc - 1 ? (c < 0 ? 0 : c) : nc - 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0  upload: AoS host image -> device layout, with wrap_to_box (src/boundary.jl:7-17)
+// ------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_import(int64_t n, const double *__restrict__ x, const double *__restrict__ v, const double *__restrict__ f,
+                         const double *__restrict__ diam, const int32_t *__restrict__ im, const int32_t *__restrict__ ids,
+                         StatePtrs s, Grid g)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3] = {0.0, 0.0, 0.0};
+    int32_t m[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        double xv = x[i * DIM + k];
+        int32_t iv = im ? im[i * DIM + k] : 0;
+        double invL = g.invL[k];
+        if (xv < 0.0 || xv >= g.L[k]) {
+            double frac = invL * xv;
+            double ncr = floor(frac);
+            iv += (int32_t)ncr;
+            xv = g.L[k] * (frac - ncr);
+        }
+        p[k] = xv;
+        m[k] = iv;
+    }
+    s.pos[i] = make_double4(p[0], p[1], p[2], diam[i]);
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        s.vel[k * s.cap + i] = v ? v[i * DIM + k] : 0.0;
+        s.frc[k * s.cap + i] = f ? f[i * DIM + k] : 0.0;
+        s.img[k * s.cap + i] = m[k];
+    }
+    s.id[i] = ids ? ids[i] : (int32_t)i;
+}
+
+template <int DIM>
+__global__ void k_import_vel(int64_t n, const double *__restrict__ v, const DevCtl *__restrict__ ctl)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t o = s.id[i];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) s.vel[k * s.cap + i] = v[(int64_t)o * DIM + k];
+}
+
+// device layout -> AoS host image in ORIGINAL particle order (scatter through id)
+template <int DIM>
+__global__ void k_export(int64_t n, const DevCtl *__restrict__ ctl, double *__restrict__ x, double *__restrict__ v, double *__restrict__ f,
+                         int32_t *__restrict__ im, int to_original)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t o = to_original ? s.id[i] : i;
+    double4 p = s.pos[i];
+    double pp[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        if (x) x[o * DIM + k] = pp[k];
+        if (v) v[o * DIM + k] = s.vel[k * s.cap + i];
+        if (f) f[o * DIM + k] = s.frc[k * s.cap + i];
+        if (im) im[o * DIM + k] = s.img[k * s.cap + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1-K3  cell list build: hash + count, scan, fill, canonical in-cell order, gather-reorder.
+// Replaces CellListMap's UpdateCellList! inside map_pairwise! (src/simulation.jl:100).
+// ------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_hash(int64_t n, const DevCtl *__restrict__ ctl, Grid g, uint32_t *__restrict__ cell_of,
+                       uint32_t *__restrict__ slot_of, uint32_t *__restrict__ counts)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 p = ctl->st[ctl->cur].pos[i];
+    int cx = cell_coord(p.x, g.cinv[0], g.nc[0]);
+    int cy = cell_coord(p.y, g.cinv[1], g.nc[1]);
+    int cz = (DIM == 3) ? cell_coord(p.z, g.cinv[2], g.nc[2]) : 0;
+    uint32_t c = ((uint32_t)cz * g.nc[1] + cy) * g.nc[0] + cx;
+    cell_of[i] = c;
+    slot_of[i] = atomicAdd(&counts[c], 1u);
+}
+
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kStreamBlock * kScanItems;
+
+__global__ void k_scan_tile_sums(int64_t n, const uint32_t *__restrict__ in, uint32_t *__restrict__ tile_sums)
+{
+    __shared__ uint32_t sm[kStreamBlock / 32];
+    int64_t base = (int64_t)blockIdx.x * kScanTile;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        int64_t q = base + k * kStreamBlock + threadIdx.x;
+        if (q < n) s += in[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kStreamBlock / 32; w++) t += sm[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// single CTA: exclusive scan of the tile sums in place
+__global__ void k_scan_tiles(int ntiles, uint32_t *__restrict__ tile_sums)
+{
+    __shared__ uint32_t sm[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        int q = base + threadIdx.x;
+        uint32_t v = q < ntiles ? tile_sums[q] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t incl = sm[threadIdx.x];
+        if (q < ntiles) tile_sums[q] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+}
+
+// exclusive scan within each tile + tile offset; writes start[0..n] (start[n] = total)
+__global__ void k_scan_apply(int64_t n, const uint32_t *__restrict__ in, const uint32_t *__restrict__ tile_off,
+                             uint32_t *__restrict__ start)
+{
+    __shared__ uint32_t sm[kStreamBlock / 32];
+    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    // exclusive scan of s over the CTA
+    uint32_t incl = s;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int q = 0; q < w; q++) woff += sm[q];
+    uint32_t run = tile_off[blockIdx.x] + woff + incl - s;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) start[base + k] = run;
+        run += v[k];
+        if (base + k == n - 1) start[n] = run;
+    }
+}
+
+__global__ void k_fill(int64_t n, const uint32_t *__restrict__ cell_of, const uint32_t *__restrict__ slot_of,
+                       const uint32_t *__restrict__ start, uint32_t *__restrict__ order)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[start[cell_of[i]] + slot_of[i]] = (uint32_t)i;
+}
+
+// canonical (ascending previous-slot) order inside each cell: removes the atomic-arrival nondeterminism,
+// so the whole pipeline is a stable counting sort and reruns are bit-identical
+__global__ void k_cellsort(int64_t ncell, const uint32_t *__restrict__ start, uint32_t *__restrict__ order)
+{
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    uint32_t b = start[c], e = start[c + 1];
+    for (uint32_t a = b + 1; a < e; a++) {
+        uint32_t key = order[a];
+        uint32_t q = a;
+        while (q > b && order[q - 1] > key) {
+            order[q] = order[q - 1];
+            q--;
+        }
+        order[q] = key;
+    }
+}
+
+template <int DIM>
+__global__ void k_gather(int64_t n, const uint32_t *__restrict__ order, const DevCtl *__restrict__ ctl)
+{
+    const StatePtrs src = ctl->st[ctl->cur], dst = ctl->st[ctl->cur ^ 1];
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t s = order[p];
+    dst.pos[p] = src.pos[s];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        dst.vel[k * dst.cap + p] = src.vel[k * src.cap + s];
+        dst.frc[k * dst.cap + p] = src.frc[k * src.cap + s];
+        dst.img[k * dst.cap + p] = src.img[k * src.cap + s];
+    }
+    dst.id[p] = src.id[s];
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbour-cell traversal shared by the pair-force kernel, the list builder and the pair counter.
+// Rows of three x-adjacent cells are contiguous slot ranges (cells are numbered x-fastest).
+// Minimum image: dx = (xi - xj) - k*L with k in {-1,0,1} given by the periodic wrap of the cell row
+// (same value as the oracle's k = nearbyint(dx/L) for every pair within the search radius).
+// visit(j, dx, dy, dz, d2, sigma_j, code) is called for every candidate j != i with d2 <= r2.
+// ------------------------------------------------------------------------------------------------
+template <int DIM, class Visit>
+__device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__restrict__ start,
+                                               const double4 *__restrict__ pos, int i, const double4 &pi, int cx, int cy,
+                                               int cz, double r2, Visit &&visit)
+{
+    const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+    for (int dz = (DIM == 3 ? -1 : 0); dz <= (DIM == 3 ? 1 : 0); dz++) {
+        int oz = cz + dz;
+        int kz = 0;
+        if (DIM == 3) {
+            if (oz < 0) { oz += nz; kz = -1; }
+            else if (oz >= nz) { oz -= nz; kz = 1; }
+        }
+        for (int dy = -1; dy <= 1; dy++) {
+            int oy = cy + dy;
+            int ky = 0;
+            if (oy < 0) { oy += ny; ky = -1; }
+            else if (oy >= ny) { oy -= ny; ky = 1; }
+            const uint32_t row = ((uint32_t)oz * ny + oy) * nx;
+            // up to two contiguous segments along x
+            int seg_lo[2], seg_hi[2], seg_k[2], nseg = 1;
+            seg_lo[0] = cx - 1; seg_hi[0] = cx + 1; seg_k[0] = 0;
+            if (cx == 0) {
+                seg_lo[0] = 0; seg_hi[0] = 1; seg_k[0] = 0;
+                seg_lo[1] = nx - 1; seg_hi[1] = nx - 1; seg_k[1] = -1;
+                nseg = 2;
+            } else if (cx == nx - 1) {
+                seg_lo[0] = nx - 2; seg_hi[0] = nx - 1; seg_k[0] = 0;
+                seg_lo[1] = 0; seg_hi[1] = 0; seg_k[1] = 1;
+                nseg = 2;
+            }
+            for (int sgi = 0; sgi < nseg; sgi++) {
+                const uint32_t jb = start[row + seg_lo[sgi]], je = start[row + seg_hi[sgi] + 1];
+                const int kx = seg_k[sgi];
+                const int code = (kx + 1) + 3 * (ky + 1) + 9 * (kz + 1);
+                if (code == 13) {
+                    for (uint32_t j = jb; j < je; j++) {
+                        double4 pj = ldg_pos(&pos[j]);
+                        double dx = pi.x - pj.x, dy_ = pi.y - pj.y;
+                        double d2 = fma(dy_, dy_, dx * dx);
+                        double dz_ = 0.0;
+                        if (DIM == 3) {
+                            dz_ = pi.z - pj.z;
+                            d2 = fma(dz_, dz_, d2);
+                        }
+                        if (d2 <= r2 && (int)j != i) visit((int)j, dx, dy_, dz_, d2, pj.w, code);
+                    }
+                } else {
+                    const double sx = kx * g.L[0], sy = ky * g.L[1], sz = (DIM == 3) ? kz * g.L[2] : 0.0;
+                    for (uint32_t j = jb; j < je; j++) {
+                        double4 pj = ldg_pos(&pos[j]);
+                        double dx = (pi.x - pj.x) - sx, dy_ = (pi.y - pj.y) - sy;
+                        double d2 = fma(dy_, dy_, dx * dx);
+                        double dz_ = 0.0;
+                        if (DIM == 3) {
+                            dz_ = (pi.z - pj.z) - sz;
+                            d2 = fma(dz_, dz_, d2);
+                        }
+                        if (d2 <= r2 && (int)j != i) visit((int)j, dx, dy_, dz_, d2, pj.w, code);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// per-pair update: src/pairwise.jl:26-39 (one side of it: the gather evaluates each pair from both ends,
+// the antisymmetric halves are bit-exact negatives, energy/virial/pair-count totals are halved at the end)
+template <int DIM, class Pot>
+__device__ __forceinline__ void pair_accumulate(const Pot &pot, const PotParams &pp, double dx, double dy, double dz, double d2,
+                                                double si, double sj, double (&F)[3], double &e, double &w, double &np)
+{
+    double d = sqrt(d2);
+    double u, f;
+    bool in = pot.eval(pp, d, si, sj, u, f);
+    double sx = (f * dx) / d, sy = (f * dy) / d;
+    double dot = sx * dx + sy * dy;
+    F[0] += sx;
+    F[1] += sy;
+    if (DIM == 3) {
+        double sz = (f * dz) / d;
+        dot += sz * dz;
+        F[2] += sz;
+    }
+    w += dot;
+    e += u;
+    np += in ? 1.0 : 0.0;
+}
+
+struct ForceOut {
+    double *part;  // [4][kMaxPartials]: sum_i e_i, sum_i w_i, sum_i n_i, sum_i |v_i|^2
+};
+
+// epilogue shared by the force kernels: store f, optional second half kick (src/integrate.jl:28-38) with the
+// kinetic-energy partial (src/thermostat.jl:50-60), block partials of e, w, n.
+template <int DIM, bool KICK2>
+__device__ __forceinline__ void force_epilogue(bool active, int i, const double (&F)[3], double e, double w, double np,
+                                               StatePtrs s, double dt, ForceOut out)
+{
+    double v2 = 0.0;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
+        if (KICK2) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                double v = s.vel[k * s.cap + i];
+                v += F[k] * dt / 2.0;
+                s.vel[k * s.cap + i] = v;
+                v2 = (k == 0) ? v * v : v2 + v * v;
+            }
+        }
+    }
+    double r[4] = {e, w, np, v2};
+    block_reduce<4, kForceBlock>(r);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) out.part[q * kMaxPartials + blockIdx.x] = r[q];
+    }
+}
+
+// deferred-hit queue: for sparse-hit potentials (PseudoHS: ~1 interacting neighbour out of ~26 candidates) a hit in
+// any lane would drag the whole warp through sqrt + divisions every iteration; hits are parked and drained together.
+// ------------------------------------------------------------------------------------------------
+// K4a  pair forces straight from the cell list (MDB_MODE_CELLS; also the list-less fallback)
+// Replaces map_pairwise! + energy_and_forces! + evaluate + reducer (src/pairwise.jl:17-39, src/potentials.jl).
+// ------------------------------------------------------------------------------------------------
+template <int DIM, class Pot, bool KICK2>
+__global__ void __launch_bounds__(kForceBlock)
+k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, double cutoff2, Pot pot, PotParams pp, double dt,
+              ForceOut out)
+{
+    __shared__ uint32_t queue[kQueue][kForceBlock];
+    const StatePtrs s = ctl->st[ctl->cur];
+    int i = blockIdx.x * kForceBlock + threadIdx.x;
+    bool active = i < n;
+    double F[3] = {0.0, 0.0, 0.0}, e = 0.0, w = 0.0, np = 0.0;
+    double4 pi = make_double4(0, 0, 0, 1);
+    int nq = 0;
+    const double4 *__restrict__ pos = s.pos;
+    auto drain_one = [&]() {
+        if (nq > 0) {
+            uint32_t ent = queue[--nq][threadIdx.x];
+            int j = (int)(ent & 0x7ffffffu);
+            int code = (int)(ent >> 27);
+            int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
+            double4 pj = ldg_pos(&pos[j]);
+            double dx = (pi.x - pj.x) - kx * g.L[0], dy = (pi.y - pj.y) - ky * g.L[1];
+            double d2 = fma(dy, dy, dx * dx), dz = 0.0;
+            if (DIM == 3) {
+                dz = (pi.z - pj.z) - kz * g.L[2];
+                d2 = fma(dz, dz, d2);
+            }
+            pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
+        }
+    };
+    if (active) {
+        pi = pos[i];
+        int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
+        int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
+        int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
+        traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, cutoff2,
+                            [&](int j, double dx, double dy, double dz, double d2, double sj, int code) {
+                                if (Pot::kSparseHits) {
+                                    queue[nq++][threadIdx.x] = (uint32_t)j | ((uint32_t)code << 27);
+                                    if (nq == kQueue) {
+                                        while (nq > 0) drain_one();
+                                    }
+                                } else {
+                                    pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, sj, F, e, w, np);
+                                }
+                            });
+    }
+    if (Pot::kSparseHits) {
+        // all lanes drain together: iterations = max queue depth in the warp
+        while (__any_sync(0xffffffffu, nq > 0)) drain_one();
+    }
+    force_epilogue<DIM, KICK2>(active, i, F, e, w, np, s, dt, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b  Verlet list build (r_list = r_search + skin) and list-driven pair forces (MDB_MODE_LIST)
+// nl is column-major: nl[k * stride + i], coalesced across the warp.
+// ------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(kForceBlock)
+k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
+             uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, DevCtl *ctl)
+{
+    const double4 *__restrict__ pos = ctl->st[ctl->cur].pos;
+    int i = blockIdx.x * kForceBlock + threadIdx.x;
+    int cnt = 0;
+    if (i < n) {
+        double4 pi = pos[i];
+        int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
+        int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
+        int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
+        traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, rlist2,
+                            [&](int j, double, double, double, double, double, int) {
+                                if (cnt < kmax) nl[(int64_t)cnt * stride + i] = (uint32_t)j;
+                                cnt++;
+                            });
+        nnbr[i] = cnt;
+    }
+    int m = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&ctl->max_nnbr, m);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->list_valid = 1;
+        ctl->disp = 0.0;
+    }
+}
+
+template <int DIM, class Pot, bool KICK2>
+__global__ void __launch_bounds__(kForceBlock)
+k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, const uint32_t *__restrict__ nl, int64_t stride,
+             int kmax, const int32_t *__restrict__ nnbr, double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out)
+{
+    __shared__ uint32_t queue[kQueue][kForceBlock];
+    const StatePtrs s = ctl->st[ctl->cur];
+    int i = blockIdx.x * kForceBlock + threadIdx.x;
+    bool active = i < n;
+    double F[3] = {0.0, 0.0, 0.0}, e = 0.0, w = 0.0, np = 0.0;
+    double4 pi = make_double4(0, 0, 0, 1);
+    int nq = 0;
+    const double4 *__restrict__ pos = s.pos;
+    // positions are re-wrapped every step, so the image of a listed pair is decided per evaluation:
+    // dx = (xi - xj) - k*L with k = +-1 when |xi - xj| > L/2 (identical to the oracle's nearbyint for listed pairs)
+    auto separation = [&](const double4 &pj, double &dx, double &dy, double &dz) -> double {
+        dx = pi.x - pj.x;
+        if (dx > g.hL[0]) dx -= g.L[0];
+        else if (dx < -g.hL[0]) dx += g.L[0];
+        dy = pi.y - pj.y;
+        if (dy > g.hL[1]) dy -= g.L[1];
+        else if (dy < -g.hL[1]) dy += g.L[1];
+        double d2 = fma(dy, dy, dx * dx);
+        dz = 0.0;
+        if (DIM == 3) {
+            dz = pi.z - pj.z;
+            if (dz > g.hL[2]) dz -= g.L[2];
+            else if (dz < -g.hL[2]) dz += g.L[2];
+            d2 = fma(dz, dz, d2);
+        }
+        return d2;
+    };
+    auto drain_one = [&]() {
+        if (nq > 0) {
+            int j = (int)queue[--nq][threadIdx.x];
+            double4 pj = ldg_pos(&pos[j]);
+            double dx, dy, dz;
+            double d2 = separation(pj, dx, dy, dz);
+            pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
+        }
+    };
+    auto candidate = [&](int j) {
+        double4 pj = ldg_pos(&pos[j]);
+        double dx, dy, dz;
+        double d2 = separation(pj, dx, dy, dz);
+        if (d2 <= cutoff2) {
+            if (Pot::kSparseHits) {
+                queue[nq++][threadIdx.x] = (uint32_t)j;
+                if (nq == kQueue) {
+                    while (nq > 0) drain_one();
+                }
+            } else {
+                pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
+            }
+        }
+    };
+    if (active) {
+        pi = pos[i];
+        int cnt = nnbr[i];
+        if (cnt <= kmax) {
+            for (int k = 0; k < cnt; k++) candidate((int)nl[(int64_t)k * stride + i]);
+        } else {
+            // list overflow: exact fallback through the (stale but conservative) build-time cells.
+            // slot order is the build-time cell order, so the home cell is found by bisection on `start`.
+            int64_t ncell = (int64_t)g.nc[0] * g.nc[1] * g.nc[2];
+            int64_t lo = 0, hi = ncell;  // start[lo] <= i < start[hi]
+            while (hi - lo > 1) {
+                int64_t mid = (lo + hi) >> 1;
+                if (start[mid] <= (uint32_t)i) lo = mid;
+                else hi = mid;
+            }
+            int cx = (int)(lo % g.nc[0]), cy = (int)((lo / g.nc[0]) % g.nc[1]), cz = (int)(lo / ((int64_t)g.nc[0] * g.nc[1]));
+            // search everything in the 27 build-time cells; the candidate test re-derives the image
+            traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, 1e300,
+                                [&](int j, double, double, double, double, double, int) { candidate(j); });
+        }
+    }
+    if (Pot::kSparseHits) {
+        while (__any_sync(0xffffffffu, nq > 0)) drain_one();
+    }
+    force_epilogue<DIM, KICK2>(active, i, F, e, w, np, s, dt, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4c  all-pairs kernel for boxes with fewer than three cells per direction (tiny systems) -- same arithmetic,
+// k = nearbyint(dx/L) exactly as the oracle's brute force.
+// ------------------------------------------------------------------------------------------------
+template <int DIM, class Pot, bool KICK2>
+__global__ void __launch_bounds__(kForceBlock)
+k_force_brute(int n, const DevCtl *__restrict__ ctl, Grid g, double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    int i = blockIdx.x * kForceBlock + threadIdx.x;
+    bool active = i < n;
+    double F[3] = {0.0, 0.0, 0.0}, e = 0.0, w = 0.0, np = 0.0;
+    if (active) {
+        double4 pi = s.pos[i];
+        double inv[3] = {g.invL[0], g.invL[1], g.invL[2]};
+        for (int j = 0; j < n; j++) {
+            if (j == i) continue;
+            double4 pj = ldg_pos(&s.pos[j]);
+            double dx = pi.x - pj.x;
+            dx = dx - nearbyint(dx * inv[0]) * g.L[0];
+            double dy = pi.y - pj.y;
+            dy = dy - nearbyint(dy * inv[1]) * g.L[1];
+            double d2 = fma(dy, dy, dx * dx), dz = 0.0;
+            if (DIM == 3) {
+                dz = pi.z - pj.z;
+                dz = dz - nearbyint(dz * inv[2]) * g.L[2];
+                d2 = fma(dz, dz, d2);
+            }
+            if (d2 <= cutoff2) pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
+        }
+    }
+    force_epilogue<DIM, KICK2>(active, i, F, e, w, np, s, dt, out);
+}
+
+// debug pair counter: pairs with d2 <= cutoff^2 (what map_pairwise! visits); per-particle counts in original order
+template <int DIM>
+__global__ void __launch_bounds__(kForceBlock)
+k_count_pairs(int n, const DevCtl *__restrict__ ctl, Grid g,
+              const uint32_t *__restrict__ start, double cutoff2, int use_cells, int32_t *__restrict__ per_particle,
+              unsigned long long *__restrict__ total)
+{
+    const double4 *__restrict__ pos = ctl->st[ctl->cur].pos;
+    const int32_t *__restrict__ id = ctl->st[ctl->cur].id;
+    int i = blockIdx.x * kForceBlock + threadIdx.x;
+    int cnt = 0;
+    if (i < n) {
+        double4 pi = pos[i];
+        if (use_cells) {
+            int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
+            int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
+            int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
+            traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, cutoff2,
+                                [&](int, double, double, double, double, double, int) { cnt++; });
+        } else {
+            double inv[3] = {g.invL[0], g.invL[1], g.invL[2]};
+            for (int j = 0; j < n; j++) {
+                if (j == i) continue;
+                double4 pj = ldg_pos(&pos[j]);
+                double dx = pi.x - pj.x;
+                dx = dx - nearbyint(dx * inv[0]) * g.L[0];
+                double dy = pi.y - pj.y;
+                dy = dy - nearbyint(dy * inv[1]) * g.L[1];
+                double d2 = fma(dy, dy, dx * dx);
+                if (DIM == 3) {
+                    double dz = pi.z - pj.z;
+                    dz = dz - nearbyint(dz * inv[2]) * g.L[2];
+                    d2 = fma(dz, dz, d2);
+                }
+                if (d2 <= cutoff2) cnt++;
+            }
+        }
+        if (per_particle) per_particle[id[i]] = cnt;
+    }
+    unsigned long long c = (unsigned long long)cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  first half of velocity Verlet, fused with the pending Bussi rescale and the periodic wrap:
+//   v <- v*alpha (bussi!, src/thermostat.jl:45-47, deferred from the previous step)
+//   v += (f*dt)/2 ; x += v*dt ; x = wrap_to_box(x)   (src/integrate.jl:8-21, src/boundary.jl:7-17)
+// also emits the block maximum of |v|^2 that bounds this step's displacement (Verlet-skin bookkeeping).
+// ------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(kStreamBlock)
+k_kick_drift(int n, Grid g, double dt, const DevCtl *__restrict__ ctl, double *__restrict__ vmax_part)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    int i = blockIdx.x * kStreamBlock + threadIdx.x;
+    double v2 = 0.0;
+    if (i < n) {
+        const double alpha = ctl->alpha;
+        double4 p = s.pos[i];
+        double x[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double v = s.vel[k * s.cap + i];
+            double f = s.frc[k * s.cap + i];
+            v = v * alpha;
+            v += f * dt / 2.0;
+            s.vel[k * s.cap + i] = v;
+            v2 = (k == 0) ? v * v : v2 + v * v;
+            double xv = x[k] + v * dt;
+            double invL = g.invL[k];
+            double frac = invL * xv;
+            double ncr = floor(frac);
+            if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
+            x[k] = g.L[k] * (frac - ncr);
+        }
+        s.pos[i] = make_double4(x[0], x[1], x[2], p.w);
+    }
+    double r[1] = {v2};
+    block_reduce<1, kStreamBlock, true>(r);
+    if (threadIdx.x == 0) vmax_part[blockIdx.x] = r[0];
+}
+
+// second half kick alone (used when the force kernel ran without the fused epilogue)
+template <int DIM>
+__global__ void k_kick2(int n, const DevCtl *__restrict__ ctl, double dt, double *__restrict__ part)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    int i = blockIdx.x * kStreamBlock + threadIdx.x;
+    double v2 = 0.0;
+    if (i < n) {
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double v = s.vel[k * s.cap + i];
+            v += s.frc[k * s.cap + i] * dt / 2.0;
+            s.vel[k * s.cap + i] = v;
+            v2 = (k == 0) ? v * v : v2 + v * v;
+        }
+    }
+    double r[1] = {v2};
+    block_reduce<1, kStreamBlock>(r);
+    if (threadIdx.x == 0) part[3 * kMaxPartials + blockIdx.x] = r[0];
+}
+
+// apply a pending Bussi scale to the resident velocities (end of an NVT run) : src/thermostat.jl:45-47
+template <int DIM>
+__global__ void k_scale(int n, DevCtl *ctl)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    int i = blockIdx.x * kStreamBlock + threadIdx.x;
+    const double alpha = ctl->alpha;
+    if (i < n) {
+#pragma unroll
+        for (int k = 0; k < DIM; k++) s.vel[k * s.cap + i] = s.vel[k * s.cap + i] * alpha;
+    }
+}
+__global__ void k_reset_alpha(DevCtl *ctl) { ctl->alpha = 1.0; }
+// after the gather-reorder: the other state buffer becomes live
+__global__ void k_flip(DevCtl *ctl)
+{
+    ctl->cur ^= 1;
+    ctl->max_nnbr = 0;
+    ctl->rebuilds += 1;
+}
+
+// K8  Brownian step: x = x + (f*dt/kT) + (noise*sigma), wrap (src/integrate.jl:66-82 intended semantics, SURVEY Q5;
+// sigma = sqrt(2 dt), src/simulation.jl:212).  Noise keyed by (original particle id, RNG step).
+template <int DIM>
+__global__ void __launch_bounds__(kStreamBlock)
+k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, const DevCtl *__restrict__ ctl,
+           double *__restrict__ dmax_part)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    int i = blockIdx.x * kStreamBlock + threadIdx.x;
+    double d2 = 0.0;
+    if (i < n) {
+        double noise[3];
+        brownian_noise<DIM>(seed, ctl->rng_step, (uint32_t)s.id[i], noise);
+        double4 p = s.pos[i];
+        double x[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double f = s.frc[k * s.cap + i];
+            double xv = x[k] + (f * dt / ktemp) + (noise[k] * sigma);
+            double del = xv - x[k];
+            d2 = (k == 0) ? del * del : d2 + del * del;
+            double invL = g.invL[k];
+            double frac = invL * xv;
+            double ncr = floor(frac);
+            if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
+            x[k] = g.L[k] * (frac - ncr);
+        }
+        s.pos[i] = make_double4(x[0], x[1], x[2], p.w);
+    }
+    double r[1] = {d2};
+    block_reduce<1, kStreamBlock, true>(r);
+    if (threadIdx.x == 0) dmax_part[blockIdx.x] = r[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-skin: fold the per-block displacement bounds, decide whether the Verlet list must be rebuilt before the
+// coming force evaluation, and drive the conditional graph node.  part holds max |v|^2 (scale = dt) or max |dx|^2 (scale = 1).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_skin_check(int nblocks, double *__restrict__ part, double scale, double skin, int always, DevCtl *ctl,
+                             cudaGraphConditionalHandle handle, int use_handle)
+{
+    double m = 0.0;
+    for (int q = threadIdx.x; q < nblocks; q += blockDim.x) {
+        m = fmax(m, part[q]);
+        part[q] = 0.0;  // consumed
+    }
+    double r[1] = {m};
+    block_reduce<1, kStreamBlock, true>(r);
+    if (threadIdx.x == 0) {
+        double disp = ctl->disp + sqrt(r[0]) * scale;
+        // NaN-safe: a non-finite bound forces a rebuild
+        int need = always || !ctl->list_valid || !(2.0 * disp <= skin);
+        ctl->disp = need ? 0.0 : disp;
+        ctl->need_rebuild = need;
+        if (use_handle) cudaGraphSetConditional(handle, need ? 1u : 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9  thermo: fixed-order second stage of the block partials (deterministic), kinetic energy / temperature
+// (src/thermostat.jl:50-67), and the Bussi-Donadio-Parrinello scale for NVT (src/thermostat.jl:20-48) drawn from the
+// counter-based RNG.  Feeds the scalars read at src/simulation.jl:118-131.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_finalize(int nblocks, const double *__restrict__ part, int ensemble, double nf, double dt, double tau,
+                           const double *__restrict__ ktemp, uint64_t seed, double *__restrict__ thermo, int advance, DevCtl *ctl)
+{
+    double r[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int q = threadIdx.x; q < nblocks; q += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) r[c] += part[c * kMaxPartials + q];
+    }
+    block_reduce<4, kStreamBlock>(r);
+    if (threadIdx.x == 0) {
+        double U = 0.5 * r[0], W = 0.5 * r[1], NP = 0.5 * r[2];
+        double KE = r[3] / 2.0;
+        unsigned long long st = ctl->step;
+        if (ensemble == 1) {
+            ThermoRng rng;
+            rng.init(seed, ctl->rng_step);
+            double r1 = rng.normal();
+            double r2 = rng.sum_noises(nf - 1.0);
+            double scale = bussi_scale(KE, ktemp[st], nf, dt, tau, r1, r2);
+            ctl->alpha = scale;
+            KE = (scale * scale) * KE;
+        }
+        if (ensemble == 2) KE = 0.0;
+        ctl->last[0] = U;
+        ctl->last[1] = W;
+        ctl->last[2] = KE;
+        ctl->last[3] = NP;
+        if (!(isfinite(U) && isfinite(KE))) ctl->nonfinite = 1;
+        if (thermo) {
+            thermo[4 * st + 0] = U;
+            thermo[4 * st + 1] = W;
+            thermo[4 * st + 2] = KE;
+            thermo[4 * st + 3] = NP;
+        }
+        if (advance) {
+            ctl->step = st + 1;
+            ctl->rng_step += 1;
+        }
+    }
+}
+
+__global__ void k_bussi_hooks(int what, double a0, double a1, double a2, double a3, double a4, double a5, double a6, uint64_t seed,
+                              uint64_t step, double *out)
+{
+    if (what == 0) {
+        out[0] = bussi_scale(a0, a1, a2, a3, a4, a5, a6);
+    } else {
+        ThermoRng rng;
+        rng.init(seed, step);
+        out[0] = rng.normal();
+        out[1] = rng.sum_noises(a0 - 1.0);
+    }
+}
+
+}  // namespace mdb

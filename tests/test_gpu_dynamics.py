@@ -1,0 +1,145 @@
+"""GPU parity of the step loop (mdb_run_nve / mdb_run_nvt / mdb_run_brownian) against the oracle's restatement of
+src/simulation.jl:88-108 / :231-250 on identical inputs, with the same counter-based RNG streams."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(md, n=1024, mode="auto", use_graph=True, seed=99, kt=1.4737):
+    from mdjl_b200 import workloads
+    cfg = workloads.phs_fluid(n)
+    v0 = workloads.velocities(n, 3, kt)
+    modes = {"auto": md._capi.MODE_AUTO, "cells": md._capi.MODE_CELLS, "list": md._capi.MODE_LIST}
+    e = md.Engine(3, n, cfg["box"], 1.5, md._capi.POT_PSEUDOHS, seed=seed, mode=modes[mode], use_graph=use_graph)
+    e.upload(cfg["x"], cfg["diam"], velocities=v0)
+    return cfg, v0, e
+
+
+def _oracle_run(orc, ens, cfg, v0, nsteps, dt, seed=99, rng_step0=0, **kw):
+    n, dim = cfg["x"].shape
+    return orc.run(ens, cfg["x"], v0, np.zeros_like(cfg["x"]), np.zeros((n, dim), np.int32), cfg["diam"], cfg["box"], 1.5,
+                   orc.POT_PHS, (), dt, nsteps, seed=seed, rng_step0=rng_step0, **kw)
+
+
+@pytest.mark.parametrize("mode,use_graph", [("cells", False), ("cells", True), ("list", False), ("list", True)])
+def test_nve_matches_oracle(md, orc, mode, use_graph):
+    cfg, v0, e = _setup(md, mode=mode, use_graph=use_graph)
+    dt, nsteps = 1e-3, 50
+    t = e.run_nve(nsteps, dt)
+    x, v, f, img = e.download()
+    ox, ov, of, oimg, ot = _oracle_run(orc, orc.NVE, cfg, v0, nsteps, dt)
+    assert np.array_equal(img, oimg)
+    assert np.max(np.abs(x - ox)) < 1e-10
+    assert np.max(np.abs(v - ov)) < 1e-9
+    assert np.array_equal(t[:, 3], ot[:, 3])                      # interacting pair counts, every step, exact
+    assert np.allclose(t[:, :3], ot[:, :3], rtol=1e-10, atol=0)    # U, W, KE every step
+    # step 0 uses zero forces: positions after step 0 are x0 + v0*dt wrapped -- covered by the oracle run
+    e.close()
+
+
+def test_graph_and_eager_are_bit_identical(md, orc):
+    out = []
+    for use_graph in (False, True):
+        cfg, v0, e = _setup(md, n=4096, mode="list", use_graph=use_graph)
+        t = e.run_nvt(120, 1e-3, 1.4737, 0.1)
+        out.append((t, e.download(), e.stats()))
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    assert out[0][2]["rebuilds"] == out[1][2]["rebuilds"] > 1
+
+
+def test_list_mode_equals_cell_mode(md, orc):
+    """same pair set every step: pair counts identical, energies to rounding, over several list rebuilds"""
+    res = {}
+    for mode in ("cells", "list"):
+        cfg, v0, e = _setup(md, n=4096, mode=mode)
+        res[mode] = (e.run_nve(300, 1e-3), e.stats())
+        e.close()
+    a, b = res["cells"][0], res["list"][0]
+    assert np.array_equal(a[:, 3], b[:, 3])
+    assert np.allclose(a[:, :3], b[:, :3], rtol=1e-9)
+    assert res["list"][1]["rebuilds"] < res["cells"][1]["rebuilds"] == 300
+
+
+def test_nvt_bussi_matches_oracle(md, orc):
+    cfg, v0, e = _setup(md)
+    dt, nsteps, tau = 1e-3, 40, 0.1
+    kt = np.linspace(1.4737, 1.2, nsteps)  # ktemp(step+1) schedule, as a LinearRamp would give
+    t = e.run_nvt(nsteps, dt, kt, tau)
+    x, v, f, img = e.download()
+    ox, ov, of, oimg, ot = _oracle_run(orc, orc.NVT, cfg, v0, nsteps, dt, ktemp=kt, tau=tau)
+    assert np.array_equal(img, oimg)
+    assert np.max(np.abs(x - ox)) < 1e-10 and np.max(np.abs(v - ov)) < 1e-9
+    assert np.allclose(t[:, :3], ot[:, :3], rtol=1e-10)
+    assert e.rng_step == nsteps
+    # chained call continues the RNG stream and carries forces
+    t2 = e.run_nvt(10, dt, 1.2, tau)
+    ox2, ov2, of2, oimg2, ot2 = orc.run(orc.NVT, ox, ov, of, oimg, cfg["diam"], cfg["box"], 1.5, orc.POT_PHS, (), dt, 10,
+                                        ktemp=1.2, tau=tau, seed=99, rng_step0=nsteps)
+    assert np.allclose(t2[:, :3], ot2[:, :3], rtol=1e-9)
+    e.close()
+
+
+def test_bussi_hooks(md, orc):
+    e = md.Engine(3, 1024, 10.0, 1.5, 0, seed=4242)
+    for nf in (3069.0, 3068.0, 2.0, 3.0, 1.0, 3145725.0):
+        for step in (0, 1, 12345678901):
+            r1, r2 = e.bussi_noises(step, nf)
+            o1, o2 = orc.bussi_noises(4242, step, nf)
+            assert relerr(r1, o1) < 1e-12 and relerr(r2, o2) < 1e-12, (nf, step, r1, o1, r2, o2)
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        ke, kt = rng.uniform(500, 5000), rng.uniform(0.5, 2.0)
+        r1, r2 = rng.standard_normal(), rng.chisquare(3068)
+        a = e.bussi_scale_from(ke, kt, 3069.0, 1e-3, 0.1, r1, r2)
+        assert relerr(a, orc.bussi_scale(ke, kt, 3069.0, 1e-3, 0.1, r1, r2)) < 1e-14
+    e.close()
+
+
+def test_brownian_matches_oracle(md, orc):
+    from mdjl_b200 import workloads
+    cfg = workloads.phs_fluid(1024)
+    e = md.Engine(3, 1024, cfg["box"], 1.5, 0, seed=31337)
+    e.upload(cfg["x"], cfg["diam"])
+    dt, nsteps, kt = 1e-5, 30, 1.4737
+    t = e.run_brownian(nsteps, dt, kt)
+    x, _, f, img = e.download()
+    ox, _, of, oimg, ot = orc.run(orc.BROWNIAN, cfg["x"], None, np.zeros_like(cfg["x"]), np.zeros((1024, 3), np.int32),
+                                  cfg["diam"], cfg["box"], 1.5, orc.POT_PHS, (), dt, nsteps, ktemp=kt, seed=31337)
+    assert np.array_equal(img, oimg)
+    assert np.max(np.abs(x - ox)) < 1e-10
+    assert np.array_equal(t[:, 3], ot[:, 3]) and np.allclose(t[:, :2], ot[:, :2], rtol=1e-10)
+    e.close()
+
+
+def test_nve_energy_drift_no_worse_than_oracle(md, orc):
+    """E = U + KE over a short NVE horizon from an NVT-melted state."""
+    cfg, v0, e = _setup(md, mode="list")
+    dt = 1e-3
+    e.run_nvt(2000, dt, 1.4737, 0.1, thermo=False)
+    x, v, f, img = e.download()
+    t = e.run_nve(2000, dt)
+    ox, ov, of, oimg, ot = orc.run(orc.NVE, x, v, f, img, cfg["diam"], cfg["box"], 1.5, orc.POT_PHS, (), dt, 2000)
+    Eg, Eo = t[:, 0] + t[:, 2], ot[:, 0] + ot[:, 2]
+    drift_g = np.max(np.abs(Eg - Eg[0])) / abs(Eg[0])
+    drift_o = np.max(np.abs(Eo - Eo[0])) / abs(Eo[0])
+    assert drift_g <= 1.05 * drift_o + 1e-12, (drift_g, drift_o)
+    assert drift_g < 5e-3
+    e.close()
+
+
+def test_momentum_and_temperature(md, orc):
+    cfg, v0, e = _setup(md, n=8192)
+    t = e.run_nvt(3000, 1e-3, 1.4737, 0.1)
+    _, v, _, _ = e.download()
+    assert np.max(np.abs(v.sum(axis=0))) < 1e-8          # velocity Verlet + uniform rescale conserve total momentum
+    nf = 3 * (8192 - 1.0)
+    T = 2 * t[1000:, 2] / nf
+    assert abs(T.mean() - 1.4737) < 0.02, T.mean()      # Bussi thermostat holds the target temperature
+    assert relerr(orc.kinetic(v), t[-1, 2]) < 1e-12
+    e.close()
