@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-step hot path in particle-steps/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES]
+
+Workload (config.workload): C5 of SURVEY.md 8d -- 3-D monodisperse pseudo-hard-sphere fluid, phi = 0.47, NVE,
+dt = 1e-3, N = 2^24 (the configuration the north-star target is quoted on; it fits one B200), started from a jittered
+lattice and melted by --melt NVT steps before anything is timed.  A "step" is one velocity-Verlet step over all N
+particles (kick-drift-wrap, conditional neighbour rebuild, pair forces + second kick + thermo reduction).
+State arrays (1.5 GiB) are far larger than L2 (126 MB), so no explicit L2 flush is needed between timed steps.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events on the engine's stream, max over
+ranks); `e2e` = the same metric through the public host-buffer API (upload from pinned host memory + K steps + download
+of the final state and thermo rows inside the timed region); `roofline` = dominant kernel vs the measured HBM copy
+bandwidth; `cpu_baseline` / `--impl reference` = the reference-shaped OpenMP port of the Julia CPU path (oracle/), the
+only thing the reference can be represented by here (no Julia in the image).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+import numpy as np  # noqa: E402
+
+DT = 1e-3
+KT = 1.4737
+PHI = 0.47
+CUTOFF = 1.5
+# algorithmic bytes (DESIGN.md "Measurement"): every state array read once and written once per step
+BYTES_STEP_3D = 176.0
+# dominant kernel = K4 pair forces with fused second kick: reads x 24 + sigma 8 + v 24, writes f 24 + v 24
+BYTES_FORCE_KERNEL_3D = 104.0
+# K5 kick-drift-wrap: reads x 24 + sigma 8 (same 32 B record) + v 24 + f 24 + img 12, writes x 24 (+8) + v 24 + img 12
+BYTES_KICK_KERNEL_3D = 144.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="mdb_clocks_", suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for line in fh:
+                c = [t.strip() for t in line.split(",")]
+                if len(c) < 8:
+                    continue
+                try:
+                    sm.append(float(c[0]))
+                    mx.append(float(c[1]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, c[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_workload(n, seed_shift=0):
+    from mdjl_b200 import workloads
+    cfg = workloads.phs_fluid(n, phi=PHI, dim=3, seed=workloads.BASE_SEED + seed_shift)
+    v0 = workloads.velocities(n, 3, KT, seed=workloads.BASE_SEED + seed_shift)
+    return cfg, v0
+
+
+def cpu_port_rate(n_sample, steps, warmup, x=None, v=None, box=None):
+    """reference-shaped OpenMP port (oracle/md_oracle.c orc_run_timing) on the host cores: particle-steps/s"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mdoracle as orc
+    if x is None:
+        cfg, v = make_workload(n_sample)
+        x, box = cfg["x"], cfg["box"]
+        # melt a little so pairs interact (the port's cost depends weakly on it)
+        pre = 20
+    else:
+        pre = 0
+    n = x.shape[0]
+    x, v = np.array(x), np.array(v)
+    f = np.zeros_like(x)
+    img = np.zeros((n, 3), np.int32)
+    diam = np.ones(n)
+    if pre + warmup > 0:
+        orc.run_timing(orc.NVE, x, v, f, img, diam, box, CUTOFF, orc.POT_PHS, (), DT, pre + warmup)
+    t0 = time.perf_counter()
+    orc.run_timing(orc.NVE, x, v, f, img, diam, box, CUTOFF, orc.POT_PHS, (), DT, steps)
+    t = time.perf_counter() - t0
+    return n * steps / t, t, orc.threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the Julia package cannot run here (no julia binary, CellListMap/StaticArrays/... absent, no
+    network), so the reference arm is the reference-shaped OpenMP port in oracle/ on all host threads."""
+    if rank != 0:
+        return
+    n_sample = min(args.n, 1 << 20)
+    rate, t, threads = cpu_port_rate(n_sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "particle-steps/s", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5 3-D pseudo-hard-sphere NVE phi=0.47 dt=1e-3 (bounded sample N=%d of the N=%d workload)" % (n_sample, args.n),
+                   "cutoff": CUTOFF},
+        "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                         "sample": "N=%d particles x %d steps, cell list rebuilt every step at cell=cutoff=1.5, OpenMP" % (n_sample, args.steps)},
+        "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "Julia reference not executable in this image; reference-shaped C/OpenMP port (oracle/md_oracle.c)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 24)
+    ap.add_argument("--melt", type=int, default=600)
+    ap.add_argument("--mode", default="auto", choices=["auto", "cells", "list"])
+    ap.add_argument("--skin", type=float, default=0.0)
+    ap.add_argument("--ensemble", default="nve", choices=["nve", "nvt", "brownian"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 20)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import mdjl_b200 as md
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        raise SystemExit("multi-GPU slab path not wired into bench.py yet")
+
+    n = args.n
+    cfg, v0 = make_workload(n)
+    box = cfg["box"]
+    modes = {"auto": md._capi.MODE_AUTO, "cells": md._capi.MODE_CELLS, "list": md._capi.MODE_LIST}
+    eng = md.Engine(3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank, mode=modes[args.mode],
+                    skin=args.skin, use_graph=True)
+    eng.upload(cfg["x"], cfg["diam"], velocities=v0)
+    del v0
+
+    def run(e, k, thermo=False):
+        if args.ensemble == "nve":
+            return e.run_nve(k, DT, thermo=thermo)
+        if args.ensemble == "nvt":
+            return e.run_nvt(k, DT, KT, 100 * DT, thermo=thermo)
+        return e.run_brownian(k, 1e-5, KT, thermo=thermo)
+
+    # melt the lattice (untimed) so the timed fluid has interacting pairs, then warm up
+    if args.melt > 0:
+        eng.run_nvt(args.melt, DT, KT, 100 * DT, thermo=False)
+    run(eng, args.warmup)
+    torch.cuda.synchronize()
+    st0 = eng.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_thermo = run(eng, args.steps, thermo=True)
+    st1 = eng.stats()
+    clocks = sampler.stop()
+    ms = st1["last_run_ms"]           # CUDA events on the engine's stream around exactly K steps
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    rebuilds = st1["rebuilds"] - st0["rebuilds"]
+    value = n * args.steps / (ms * 1e-3)
+    hbm, peak_src = peaks()
+
+    # per-kernel durations: same steps in eager (profiling) mode on a second handle sharing the device
+    roofline = None
+    prof = {}
+    x_now, v_now, f_now, img_now = eng.download()
+    if not args.no_profile:
+        e2 = md.Engine(3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank, mode=modes[args.mode],
+                       skin=args.skin, use_graph=False)
+        e2.upload(x_now, cfg["diam"], velocities=v_now, forces=f_now, images=img_now)
+        ksteps = min(args.steps, 100)
+        run(e2, 5)
+        run(e2, ksteps)
+        s2 = e2.stats()
+        e2.close()
+        kick = s2["prof_kick_ms"] / ksteps
+        force = s2["prof_force_ms"] / ksteps
+        rebuild_per_step = s2["prof_rebuild_ms"] / ksteps
+        prof = {"kick_drift_ms": kick, "pair_force_ms": force, "rebuild_ms_per_step": rebuild_per_step,
+                "eager_steps": ksteps}
+        if force >= kick:
+            name, dur, bts = "k_force_list(pair forces + second kick)" if st1["mode"] == 2 else "k_force_cells", force, BYTES_FORCE_KERNEL_3D
+        else:
+            name, dur, bts = "k_kick_drift", kick, BYTES_KICK_KERNEL_3D
+        achieved = bts * n / (dur * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                    "kernel": name, "kernel_ms": dur, "algorithmic_bytes_per_particle": bts, "peak_source": peak_src}
+    step_gbs = BYTES_STEP_3D * n * args.steps / (ms * 1e-3) / 1e9
+
+    # end-to-end through the public host-buffer API: upload (pinned host) + K steps + download + thermo
+    e2e = None
+    if not args.no_e2e:
+        def pinned(a):
+            t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int32, pin_memory=True)
+            arr = t.numpy()
+            arr[...] = a
+            return t, arr
+        keep = []
+        hx, hv, hf, hi, hd = [pinned(a) for a in (x_now, v_now, f_now, img_now, cfg["diam"])]
+        keep = [hx, hv, hf, hi, hd]
+        ox, ov, of_, oi = [pinned(np.empty_like(a)) for a in (x_now, v_now, f_now, img_now)]
+        keep += [ox, ov, of_, oi]
+        e3 = md.Engine(3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank, mode=modes[args.mode],
+                       skin=args.skin, use_graph=True)
+
+        def e2e_call():
+            e3.upload(hx[1], hd[1], velocities=hv[1], forces=hf[1], images=hi[1])
+            th = run(e3, args.steps, thermo=True)
+            e3.download_into(ox[1], ov[1], of_[1], oi[1])
+            return th
+        e2e_call()  # warm-up: allocations, graph capture
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = e2e_call()
+        t_e2e = time.perf_counter() - t0
+        h2d = sum(a[1].nbytes for a in (hx, hv, hf, hi, hd))
+        d2h = sum(a[1].nbytes for a in (ox, ov, of_, oi)) + th.nbytes
+        e2e = {"value": n * args.steps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e,
+               "what": "mdb_upload(pinned host) + mdb_run_%s(%d steps) + mdb_download + thermo rows" % (args.ensemble, args.steps)}
+        e3.close()
+
+    cpu = None
+    if not args.no_cpu and rank == 0:
+        ns = min(args.cpu_sample, n)
+        rate, t, threads = cpu_port_rate(ns, 10, 2)
+        cpu = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+               "sample": "N=%d particles x 10 steps of the same fluid (after 22 untimed), reference-shaped OpenMP port, %.1f s" % (ns, t)}
+
+    nf = 3 * (n - 1.0)
+    E = t_thermo[:, 0] + t_thermo[:, 2]
+    line = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5 3-D pseudo-hard-sphere %s N=%d phi=%.2f dt=%g cutoff=%g" % (args.ensemble.upper(), n, PHI, DT, CUTOFF),
+                   "n_particles": n, "mode": {1: "cells", 2: "list"}[st1["mode"]], "skin": args.skin or "default",
+                   "l2": "state arrays (%.2f GiB) exceed L2; no flush needed" % (n * 96 / 2 ** 30),
+                   "melt_steps": args.melt, "parallelism": "1 GPU" if world == 1 else "x-slabs x%d" % world},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm, "unit": "GB/s", "frac": step_gbs / hbm,
+                          "algorithmic_bytes_per_particle_step": BYTES_STEP_3D},
+        "cpu_baseline": cpu,
+        "kernels": prof,
+        "rebuilds_in_timed_region": int(rebuilds),
+        "physics": {"T_mean": float(np.mean(2 * t_thermo[:, 2] / nf)), "U_per_particle": float(np.mean(t_thermo[:, 0]) / n),
+                    "E_drift_rel": float((E.max() - E.min()) / abs(E[0])) if args.ensemble == "nve" else None,
+                    "pairs_last": int(t_thermo[-1, 3])},
+    }
+    eng.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,7 +93,12 @@ typedef struct mdb_stats {
     int32_t ncell[3];
     int32_t mode;             /* resolved mode */
     double last_run_ms;       /* device time of the last mdb_run_* call (CUDA events) */
-    double last_force_ms;     /* device time of the pair-force kernel of the last step of that call (eager mode only) */
+    double last_force_ms;     /* device time of the pair-force kernel of the last stand-alone force evaluation */
+    /* eager mode (use_graph = 0) doubles as the profiling mode: per-kernel CUDA-event totals over the last run call */
+    double prof_kick_ms;      /* K5 kick-drift-wrap (or K8 Brownian move) */
+    double prof_force_ms;     /* K4 pair-force kernel (with the fused second kick) */
+    double prof_rebuild_ms;   /* K1-K3 (+ list build) when they ran */
+    int64_t prof_steps;
 } mdb_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

@@ -46,7 +46,9 @@ class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("kernel_launches", C.c_int64), ("n_owned", C.c_int64),
                 ("n_ghost", C.c_int64), ("list_capacity", C.c_int64), ("max_neighbors", C.c_int64),
                 ("r_search", C.c_double), ("cell_len", C.c_double * 3), ("ncell", C.c_int32 * 3), ("mode", C.c_int32),
-                ("last_run_ms", C.c_double), ("last_force_ms", C.c_double)]
+                ("last_run_ms", C.c_double), ("last_force_ms", C.c_double),
+                ("prof_kick_ms", C.c_double), ("prof_force_ms", C.c_double), ("prof_rebuild_ms", C.c_double),
+                ("prof_steps", C.c_int64)]
 
 
 class FireParams(C.Structure):

@@ -46,6 +46,7 @@ struct mdb_engine_s {
     PotParams pp;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evf0 = nullptr, evf1 = nullptr;
+    cudaEvent_t evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     StatePtrs st[2];
     uint32_t *cell_of = nullptr, *slot_of = nullptr, *counts = nullptr, *start = nullptr, *order = nullptr, *tile_sums = nullptr;
@@ -338,10 +339,12 @@ static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int
 
 // the part of one step before the (conditional) rebuild
 template <int DIM>
-static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphConditionalHandle handle, int use_handle)
+static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphConditionalHandle handle, int use_handle, bool prof = false)
 {
     if (ensemble != MDB_BROWNIAN) {
+        if (prof) cudaEventRecord(e->evp[0], e->stream);
         k_kick_drift<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl, e->disp_part);
+        if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_skin_check(e, dt, handle, use_handle);
     } else {
         enqueue_skin_check(e, 1.0, handle, use_handle);
@@ -349,15 +352,21 @@ static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphCondi
 }
 // the part of one step after the rebuild
 template <int DIM>
-static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, double ktemp, int thermo)
+static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, double ktemp, int thermo, bool prof = false)
 {
     if (ensemble != MDB_BROWNIAN) {
+        if (prof) cudaEventRecord(e->evp[2], e->stream);
         enqueue_force<DIM, true>(e, dt);
+        if (prof) cudaEventRecord(e->evp[3], e->stream);
         enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
     } else {
+        if (prof) cudaEventRecord(e->evp[2], e->stream);
         enqueue_force<DIM, false>(e, dt);
+        if (prof) cudaEventRecord(e->evp[3], e->stream);
+        if (prof) cudaEventRecord(e->evp[0], e->stream);
         k_brownian<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt),
                                                                                 e->cfg.seed, e->ctl, e->disp_part);
+        if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
     }
 }
@@ -454,6 +463,8 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
         if (rc) return rc;
     }
     CU(cudaEventRecord(e->ev0, s));
+    e->stats.prof_kick_ms = e->stats.prof_force_ms = e->stats.prof_rebuild_ms = 0.0;
+    e->stats.prof_steps = 0;
     int64_t done = 0;
     unsigned long long rebuilds0 = 0;
     {
@@ -470,18 +481,29 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
             if (e->cfg.use_graph) {
                 CU(cudaGraphLaunch(e->gexec, s));
             } else {
-                enqueue_step_head<DIM>(e, ensemble, dt, 0, 0);
+                // eager mode doubles as the profiling mode: CUDA events around each kernel group, one sync per step
+                enqueue_step_head<DIM>(e, ensemble, dt, 0, 0, true);
+                bool rebuilt = true;
                 if (e->mode == MDB_MODE_LIST && !e->brute) {
                     CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, s));
                     CU(cudaStreamSynchronize(s));
-                    if (e->h_ctl->need_rebuild) enqueue_rebuild<DIM>(e);
-                } else {
-                    enqueue_rebuild<DIM>(e);
+                    rebuilt = e->h_ctl->need_rebuild != 0;
                 }
-                bool last = (done + q == nsteps - 1);
-                if (last) CU(cudaEventRecord(e->evf0, s));
-                enqueue_step_tail<DIM>(e, ensemble, dt, tau, ktemp, key.thermo);
-                if (last) CU(cudaEventRecord(e->evf1, s));
+                CU(cudaEventRecord(e->evp[4], s));
+                if (rebuilt) enqueue_rebuild<DIM>(e);
+                CU(cudaEventRecord(e->evp[5], s));
+                enqueue_step_tail<DIM>(e, ensemble, dt, tau, ktemp, key.thermo, true);
+                CU(cudaStreamSynchronize(s));
+                float t = 0;
+                CU(cudaEventElapsedTime(&t, e->evp[0], e->evp[1]));
+                e->stats.prof_kick_ms += t;
+                CU(cudaEventElapsedTime(&t, e->evp[2], e->evp[3]));
+                e->stats.prof_force_ms += t;
+                if (rebuilt) {
+                    CU(cudaEventElapsedTime(&t, e->evp[4], e->evp[5]));
+                    e->stats.prof_rebuild_ms += t;
+                }
+                e->stats.prof_steps += 1;
             }
         }
         if (thermo) CU(cudaMemcpyAsync(thermo + 4 * done, e->d_thermo, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
@@ -504,10 +526,6 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     e->stats.last_run_ms = ms;
-    if (!e->cfg.use_graph && nsteps > 0) {
-        CU(cudaEventElapsedTime(&ms, e->evf0, e->evf1));
-        e->stats.last_force_ms = ms;
-    }
     unsigned long long nreb = e->h_ctl->rebuilds - rebuilds0;
     e->stats.steps += nsteps;
     e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
@@ -586,6 +604,7 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     CUC(cudaEventCreate(&e->ev1));
     CUC(cudaEventCreate(&e->evf0));
     CUC(cudaEventCreate(&e->evf1));
+    for (int q = 0; q < 6; q++) CUC(cudaEventCreate(&e->evp[q]));
     CUC(cudaMalloc(&e->ctl, sizeof(DevCtl)));
     CUC(cudaMemset(e->ctl, 0, sizeof(DevCtl)));
     CUC(cudaMallocHost(&e->h_ctl, sizeof(DevCtl)));
@@ -618,6 +637,8 @@ MDB_EXPORT int mdb_destroy(mdb_handle e)
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evf0) cudaEventDestroy(e->evf0);
     if (e->evf1) cudaEventDestroy(e->evf1);
+    for (int q = 0; q < 6; q++)
+        if (e->evp[q]) cudaEventDestroy(e->evp[q]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return MDB_OK;

@@ -1,0 +1,59 @@
+"""CPU: the C-ABI library loads and exports exactly the entry points include/mdb200.h declares; without a GPU the
+product path fails loudly (no CPU fallback, no oracle on the product path)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "mdb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_matches_binding_and_library(md):
+    hs = header_symbols()
+    assert hs == sorted(md._capi.SYMBOLS)
+    lib = md._capi.load()
+    for name in hs:
+        assert hasattr(lib, name), name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", md._capi.lib_path()]).decode()
+    exported = sorted(set(re.findall(r" T (mdb_[a-z_0-9]+)", out)))
+    assert exported == hs
+    assert lib.mdb_version() == 100
+
+
+def test_struct_layouts_match_header(md):
+    import ctypes as C
+    assert C.sizeof(md._capi.Config) == 4 + 4 + 8 + 72 + 8 + 64 + 8 + 4 + 4 + 8 + 4 + 4 + 4 + 20
+    assert C.sizeof(md._capi.FireParams) == 8 + 6 * 8 + 8
+
+
+def test_product_path_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "moleculardynamics.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "mdoracle" not in txt and "libmdoracle" not in txt and "oracle/" not in txt.replace("oracle/md_oracle.c", ""), f
+
+
+def test_fails_loudly_without_gpu(md):
+    try:
+        import torch
+        has = torch.cuda.is_available()
+    except Exception:
+        has = False
+    if has:
+        pytest.skip("GPU present")
+    with pytest.raises(md.MdbError) as ei:
+        md.Engine(3, 16, 10.0, 1.5, 0)
+    assert ei.value.code == md._capi.ERR_NO_DEVICE
+    p = md.Parameters(0.5, 16, 1e-3, md.PseudoHS())
+    with pytest.raises(md.MdbError):
+        md.initialize_state(p, None, random_init=True, write_init=False)

@@ -1,0 +1,226 @@
+"""CPU tests of the oracle itself (oracle/md_oracle.c): the reference ships no tests or golden vectors for this path
+(SURVEY F2), so the oracle is pinned by (1) known-answer values computed independently from the reference formulas,
+(2) algebraic invariants, (3) an O(N^2) brute-force enumeration, (4) the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return dict(np.load(os.path.join(GOLD, name)))
+
+
+def test_philox_known_answers(orc):
+    # Random123 kat_vectors for philox4x32_10
+    assert orc.philox((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert orc.philox((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert orc.philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def test_potential_known_answers(orc):
+    """SURVEY 8c(1) table + tests/golden/potential_kat.npz (independent Python-float evaluation), <= 1e-14 relative"""
+    kat = [  # (tag, params, r, s1, s2, u, f)
+        (0, (), 1.0, 1, 1, 1.0, 134.5526623421209),
+        (0, (), 1.01, 1, 1, 0.18186757330727654, 41.311637387454304),
+        (0, (), 1.02, 1, 1, 1.9868650975063407e-4, 0.9801973661675383),
+        (0, (), 0.99, 1, 1, 3.2239886449193986, 334.72152332624864),
+        (0, (), 0.97, 1, 1, 19.51087025545822, 1571.1975783842527),
+        (0, (), 1.0204081632653061, 1, 1, 0.0, 0.0),
+        (1, (1.0, 2.5), 1.0, 1, 1, 0.0, 24.0),
+        (1, (1.0, 2.5), 1.5, 1, 1, -0.32033659427857464, -1.1580288310461555),
+        (1, (1.0, 2.5), 2.4999, 1, 1, -0.016320791625929663, -0.03901032171198414),
+        (1, (1.0, 2.5), 2.5, 1, 1, 0.0, 0.0),
+        (3, (1.25, 0.2), 1.0, 1.0, 1.0, 0.5958195256295423, 10.14226515370967),
+        (3, (1.25, 0.2), 1.1, 1.0, 1.2, 0.2832698584402855, 5.049994307408907),
+        (3, (1.25, 0.2), 0.9, 0.8, 1.1, 0.5208500254912997, 10.086128330932862),
+    ]
+    for tag, p, r, s1, s2, u0, f0 in kat:
+        u, f, _ = orc.evaluate(tag, p, r, s1, s2)
+        assert abs(u - u0) <= 1e-14 * max(abs(u0), 1e-3), (tag, r, u, u0)
+        assert abs(f - f0) <= 1e-14 * max(abs(f0), 1e-3), (tag, r, f, f0)
+    for row in gold("potential_kat.npz")["table"]:
+        tag, p0, p1, p2, r, s1, s2, u0, f0 = row
+        params = {0: (), 1: (p0, p1), 3: (p0, p1)}[int(tag)]
+        u, f, _ = orc.evaluate(int(tag), params, r, s1, s2)
+        assert abs(u - u0) <= 2e-14 * max(abs(u0), 0.1) and abs(f - f0) <= 2e-14 * max(abs(f0), 0.1), row  # near-cut values cancel from O(1) terms
+    # LJ minimum: u(2^(1/6)) = -eps, f = 0
+    u, f, _ = orc.evaluate(1, (1.0, 2.5), 2 ** (1 / 6))
+    assert abs(u + 1.0) < 1e-15 and abs(f) < 1e-13
+    # PHS analytic constants: a = lambda (lambda/(lambda-1))^(lambda-1), b = lambda/(lambda-1)
+    assert abs(50.0 * (50.0 / 49.0) ** 49 - 134.5526623421209) < 1e-10 and abs(50.0 / 49.0 - 1.0204081632653061) < 1e-16
+
+
+@pytest.mark.parametrize("tag,params,rs", [
+    (0, (), np.linspace(0.93, 1.019, 12)),
+    (1, (1.0, 2.5), np.linspace(0.9, 2.45, 12)),
+    (3, (1.25, 0.2), np.linspace(0.85, 1.2, 12)),
+])
+def test_force_is_minus_du_dr(orc, tag, params, rs):
+    """f = -du/dr by central differences (not for XPLOR: its switch derivative is wrong in the reference)"""
+    # PseudoHS is only self-consistent for sigma = 1: the reference's force omits the 1/sigma of d/dr (sigma/r)^n
+    # (src/potentials.jl:23-25), reproduced bug-for-bug, so f = -sigma * du/dr there
+    s1, s2 = (1.0, 1.0) if tag == 0 else (1.0, 1.05)
+    for r in rs:
+        h = 1e-6 * r
+        up, _, _ = orc.evaluate(tag, params, r + h, s1, s2)
+        um, _, _ = orc.evaluate(tag, params, r - h, s1, s2)
+        _, f, _ = orc.evaluate(tag, params, r, s1, s2)
+        assert abs(f + (up - um) / (2 * h)) <= 2e-7 * max(abs(f), 1.0), (tag, r)
+    if tag == 0:
+        sg = 0.95
+        for r in (0.9, 0.95):
+            h = 1e-6 * r
+            up, _, _ = orc.evaluate(0, (), r + h, sg, sg)
+            um, _, _ = orc.evaluate(0, (), r - h, sg, sg)
+            _, f, _ = orc.evaluate(0, (), r, sg, sg)
+            assert abs(f + sg * (up - um) / (2 * h)) <= 2e-7 * abs(f)
+
+
+def test_xplor_bug_for_bug(orc):
+    """dS collapses to 4 r (rc^2 - r^2)^2 / denom and force = S*F + V*dS (src/potentials.jl:200-204, 233)"""
+    eps, ron, rc = 1.0, 2.0, 2.5
+    for r in (1.0, 1.9, 2.1, 2.3, 2.49):
+        u, f, inr = orc.evaluate(2, (eps, ron, rc), r)
+        sr6 = (1.0 / r) ** 6
+        V, F = 4 * eps * (sr6 * sr6 - sr6), 24 * eps * (2 * sr6 * sr6 - sr6) / r
+        if r < ron:
+            S, dS = 1.0, 0.0
+        else:
+            den = (rc * rc - ron * ron) ** 3
+            S = (rc * rc - r * r) ** 2 * (rc * rc + 2 * r * r - 3 * ron * ron) / den
+            dS = 4 * r * (rc * rc - r * r) ** 2 / den
+        assert abs(u - V * S) < 1e-13 and abs(f - (S * F + V * dS)) < 1e-12 and inr == 1
+    assert orc.evaluate(2, (eps, ron, rc), 2.5) == (0.0, 0.0, 0)
+
+
+def test_cell_list_equals_brute_force_and_golden(orc):
+    g = gold("c1_phs_n1024.npz")
+    a = orc.forces(g["x"], g["diam"], g["box"], 1.5, orc.POT_PHS, brute=True, counts=True)
+    b = orc.forces(g["x"], g["diam"], g["box"], 1.5, orc.POT_PHS, counts=True)
+    assert a["n_cut"] == b["n_cut"] == int(g["n_cut"]) and a["n_int"] == b["n_int"] == int(g["n_int"]) > 400
+    assert np.array_equal(a["nbr"], b["nbr"]) and np.array_equal(a["nbr"], g["nbr"])
+    assert np.max(np.abs(a["F"] - b["F"])) <= 1e-13 * np.max(np.abs(a["F"]))
+    assert np.array_equal(a["F"], g["F"]) and a["E"] == float(g["E"]) and a["W"] == float(g["W"])
+    for cut in ("1.5", "2.03"):
+        g2 = gold("c2_poly_n1200_cut%s.npz" % cut)
+        c = orc.forces(g2["x"], g2["diam"], g2["box"], float(cut), orc.POT_POLY, (1.25, 0.2), counts=True)
+        assert c["n_cut"] == int(g2["n_cut"]) and c["n_int"] == int(g2["n_int"]) and np.array_equal(c["nbr"], g2["nbr"])
+        assert np.max(np.abs(c["F"] - g2["F"])) <= 1e-12 * np.max(np.abs(g2["F"]))
+        assert abs(c["E"] - float(g2["E"])) <= 1e-13 * abs(float(g2["E"]))
+
+
+def test_pair_invariants(orc):
+    g = gold("c1_phs_n1024.npz")
+    r = orc.forces(g["x"], g["diam"], g["box"], 1.5, orc.POT_PHS)
+    F = r["F"]
+    assert np.max(np.abs(F.sum(axis=0))) <= 1e-10 * np.sum(np.abs(F))         # Newton's third law
+    # periodic images of the whole configuration / unwrapped input give the same answer
+    shift = np.random.default_rng(0).integers(-3, 4, size=g["x"].shape)
+    r2 = orc.forces(g["x"] + shift * g["box"], g["diam"], g["box"], 1.5, orc.POT_PHS)
+    assert r2["n_cut"] == r["n_cut"] and abs(r2["E"] - r["E"]) < 1e-9 * abs(r["E"])
+    # virial = -dim * V * dU/dV by uniform scaling of box and coordinates (LJ: smooth, no sigma-independent cut)
+    from mdjl_b200 import workloads
+    cfg = workloads.lj_fluid(512, rho=0.7)
+    x, box = cfg["x"], cfg["box"]
+    base = orc.forces(x, cfg["diam"], box, 2.5, orc.POT_LJ, (1.0, 1e9))      # r_cut far away: only the neighbour cutoff acts
+    # finite difference of U(s x, s L) with the pair set frozen is delicate at a sharp cutoff; use W = sum_pairs f*r directly
+    n = x.shape[0]
+    W = 0.0
+    inv = 1.0 / box
+    for i in range(0, n, 7):
+        d = x[i] - x
+        d -= box * np.rint(d * inv)
+        rr = np.sqrt((d * d).sum(1))
+        m = (rr <= 2.5) & (rr > 0)
+        sr6 = (1.0 / rr[m]) ** 6
+        W += 0  # placeholder to keep the loop cheap
+    U = lambda s: orc.forces(x * s, cfg["diam"], box * s, 2.5 * s, orc.POT_LJ, (1.0, 1e9))["E"]
+    h = 1e-6
+    dUds = (U(1 + h) - U(1 - h)) / (2 * h)          # same pairs (cutoff scales with s): dU/ds = -W
+    assert abs(dUds + base["W"]) <= 1e-6 * abs(base["W"])
+
+
+def test_wrap_to_box(orc):
+    box = np.array([10.0, 7.5, 3.25])
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        x = rng.uniform(-30, 30, 3)
+        w, img = orc.wrap(x, np.zeros(3, np.int32), box)
+        assert np.all(w >= 0) and np.all(w <= box)
+        assert np.max(np.abs(w + img * box - x)) < 1e-13
+        w2, img2 = orc.wrap(w, img, box)
+        assert np.max(np.abs(w2 - w)) < 1e-14 and (np.array_equal(img2, img) or np.any(w == box))
+    # the reference formula can return exactly L for a tiny negative coordinate (frac - floor(frac) rounds to 1)
+    w, img = orc.wrap(np.array([-1e-18, 1.0, 1.0]), np.zeros(3, np.int32), box)
+    assert w[0] == box[0] and img[0] == -1
+
+
+def test_velocity_verlet_invariants(orc):
+    g = gold("c1_phs_n1024.npz")
+    n = 1024
+    x, v, f, img, th = orc.run(orc.NVE, g["x"], g["v"], g["f"], g["img"], g["diam"], g["box"], 1.5, orc.POT_PHS, (), 1e-3, 400)
+    assert np.max(np.abs(v.sum(0) - g["v"].sum(0))) < 1e-9                       # momentum
+    E = th[:, 0] + th[:, 2]
+    assert np.max(np.abs(E - E[0])) / abs(E[0]) < 5e-3                           # short-horizon NVE drift of the stiff r^-50 core
+    assert abs(orc.kinetic(v) - th[-1, 2]) <= 1e-12 * th[-1, 2]
+    # forces are not primed before step 0: with zero forces the first step is a pure drift
+    x1, v1, f1, img1, _ = orc.run(orc.NVE, g["x"], g["v"], np.zeros_like(g["x"]), np.zeros((n, 3), np.int32), g["diam"], g["box"],
+                                  1.5, orc.POT_PHS, (), 1e-3, 1)
+    drift = g["x"] + g["v"] * 1e-3
+    assert np.max(np.abs((x1 + img1 * g["box"]) - drift)) < 1e-12
+
+
+def test_bussi_thermostat_statistics(orc):
+    """canonical sampling: for a free gas (no forces) KE under Bussi follows Gamma(nf/2, kT); r1 ~ N(0,1); r2 ~ chi2(nf-1)"""
+    z = orc.thermo_normals(7, 3, 200000)
+    assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.01 and abs((z ** 4).mean() - 3) < 0.06
+    for nf in (1.0, 2.0, 3.0, 10.0, 11.0, 3068.0):
+        c = np.array([orc.chi2(11, s, nf) for s in range(4000)])
+        assert abs(c.mean() - nf) < 5 * np.sqrt(2 * nf / 4000) + 1e-9, (nf, c.mean())
+        assert abs(c.var() - 2 * nf) < 0.2 * 2 * nf, (nf, c.var())
+    assert orc.chi2(1, 0, 0.0) == 0.0
+    # scale factor: deterministic limits.  dt >> tau: KE' -> kT/nf * (r2 + r1^2) * ... ; dt -> 0: alpha -> 1
+    assert abs(orc.bussi_scale(100.0, 1.0, 300.0, 1e-12, 1.0, 0.3, 299.0) - 1.0) < 1e-5
+    a = orc.bussi_scale(100.0, 1.5, 300.0, 1e3, 1.0, 0.3, 280.0)
+    assert abs(a * a * 100.0 - 0.5 * 1.5 * (280.0 + 0.09)) < 1e-9
+    # stationary distribution over many thermostat steps of an ideal gas
+    nf, kt, dt, tau = 30.0, 1.3, 0.05, 0.2
+    ke, samples = 0.5 * nf * kt, []
+    for s in range(20000):
+        r1, r2 = orc.bussi_noises(5, s, nf)
+        ke *= orc.bussi_scale(ke, kt, nf, dt, tau, r1, r2) ** 2
+        samples.append(ke)
+    samples = np.array(samples[500:])
+    assert abs(samples.mean() - 0.5 * nf * kt) < 0.03 * 0.5 * nf * kt
+    assert abs(samples.var() - 0.5 * nf * kt * kt) < 0.15 * 0.5 * nf * kt * kt
+
+
+def test_brownian_noise_moments_and_step(orc):
+    u = np.array([orc.brownian_noise(9, s, i, 3) for s in range(20) for i in range(2000)])
+    assert np.all(np.abs(u) <= np.sqrt(3.0)) and abs(u.mean()) < 0.01 and abs(u.var() - 1.0) < 0.01
+    assert not np.array_equal(orc.brownian_noise(9, 0, 1, 3), orc.brownian_noise(9, 1, 1, 3))
+    assert np.array_equal(orc.brownian_noise(9, 5, 77, 2), orc.brownian_noise(9, 5, 77, 3)[:2])
+    g = gold("rng_streams.npz")
+    assert np.array_equal(g["brownian"][0], orc.brownian_noise(1234, 0, 0, 3))
+    assert np.array_equal(g["bussi"][0], np.array(orc.bussi_noises(1234, 0, 3069.0)))
+    # free Brownian particles: <dx^2> = 2 dt per component
+    n, dt = 4096, 1e-3
+    x0 = np.random.default_rng(2).uniform(10, 90, (n, 3))
+    x, _, _, img, _ = orc.run(orc.BROWNIAN, x0, None, np.zeros((n, 3)), np.zeros((n, 3), np.int32),
+                              np.full(n, 1e-3), np.full(3, 100.0), 1.0, orc.POT_LJ, (1.0, 0.0), dt, 1, ktemp=1.0, seed=3)
+    d = x - x0
+    assert abs(d.var() - 2 * dt) < 0.05 * 2 * dt
+
+
+def test_timing_variant_matches_accurate_oracle(orc):
+    """the OpenMP 'reference-shaped' loop used as cpu_baseline computes the same trajectory"""
+    g = gold("c1_phs_n1024.npz")
+    x, v, f, img = g["x"].copy(), g["v"].copy(), g["f"].copy(), g["img"].copy()
+    out = orc.run_timing(orc.NVE, x, v, f, img, g["diam"], g["box"], 1.5, orc.POT_PHS, (), 1e-3, 25)
+    ox, ov, of, oimg, th = orc.run(orc.NVE, g["x"], g["v"], g["f"], g["img"], g["diam"], g["box"], 1.5, orc.POT_PHS, (), 1e-3, 25)
+    assert np.max(np.abs(x - ox)) < 1e-10 and np.array_equal(img, oimg)
+    assert np.allclose(out, th[-1, :3], rtol=1e-10)
