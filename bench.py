@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "cells", "list"])
     ap.add_argument("--skin", type=float, default=0.0)
     ap.add_argument("--ensemble", default="nve", choices=["nve", "nvt", "brownian"])
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph (ncu cannot profile kernel nodes of graphs with conditional nodes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -198,7 +199,7 @@ def main():
     box = cfg["box"]
     modes = {"auto": md._capi.MODE_AUTO, "cells": md._capi.MODE_CELLS, "list": md._capi.MODE_LIST}
     eng = md.Engine(3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank, mode=modes[args.mode],
-                    skin=args.skin, use_graph=True)
+                    skin=args.skin, use_graph=not args.eager)
     eng.upload(cfg["x"], cfg["diam"], velocities=v0)
     del v0
 

@@ -1,0 +1,222 @@
+# MolecularDynamicsB200.jl -- the reference-side binding of include/mdb200.h.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia (SURVEY.md F4).  It is the `ccall` layer a
+# maintainer of MolecularDynamics.jl adds so that the existing API
+#     Parameters(...) -> initialize_state(...) -> state.velocities = initialize_velocities(...) -> run_simulation!(...)
+# keeps working with the per-step loop (src/simulation.jl:88-108, :231-250) executed by libmdb200.so on a B200.
+# INTEGRATION.md walks through it.  The Python package moleculardynamics.jl_b200/ mirrors this file one to one and is
+# what tests/ and bench.py drive.
+module MolecularDynamicsB200
+
+using MolecularDynamics
+using MolecularDynamics: Parameters, SimulationState, Ensemble, NVE, NVT, Brownian, Potential, PseudoHS, LennardJones,
+                         LennardJonesXPLOR, energy_lrc, pressure_lrc, compute_box_volume, open_files,
+                         write_to_file_lammps, finalize_simulation!
+using StaticArrays, Printf, LinearAlgebra
+
+const libmdb = get(ENV, "MDB200_LIB", "libmdb200.so")
+
+# ---- include/mdb200.h mirrored -------------------------------------------------------------------------------
+struct MdbConfig
+    dim::Int32
+    potential::Int32
+    n_particles::Int64
+    unitcell::NTuple{9,Float64}
+    cutoff::Float64
+    pot_params::NTuple{8,Float64}
+    seed::UInt64
+    device::Int32
+    mode::Int32
+    skin::Float64
+    use_graph::Int32
+    rank::Int32
+    nranks::Int32
+    reserved::NTuple{5,Int32}
+end
+
+const MDB_OK = Cint(0)
+const Handle = Ptr{Cvoid}
+
+struct MdbError <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(h::Handle, rc::Cint)
+    rc == MDB_OK && return nothing
+    msg = unsafe_string(ccall((:mdb_last_error, libmdb), Cstring, (Handle,), h))
+    throw(MdbError(rc, msg))
+end
+
+# Potential subtype -> (device functor tag, parameters): the plugin contract of src/types.jl:1-6.
+# A subtype without a method here has no device functor; like the reference's fallback `evaluate` it is an error.
+potential_tag(::PseudoHS) = (Int32(0), ())
+potential_tag(p::LennardJones) = (Int32(1), (p.epsilon, p.r_cut))
+potential_tag(p::LennardJonesXPLOR) = (Int32(2), (p.ϵ, p.r_on, p.r_cut))
+potential_tag(p::Potential) = error("evaluate not implemented on the device for potential type: $(typeof(p))")
+# the README's user-defined plugin (README.md:82-145) registers itself like this:
+#   MolecularDynamicsB200.potential_tag(p::Polydisperse) = (Int32(3), (1.25, 0.2))
+
+pad8(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, 8)
+
+"""
+    GPUSystem
+
+Takes the place of `CellListMap.ParticleSystem` in `SimulationState.system` (src/types.jl:15-17).  Exposes the
+property names the drivers touch (`positions`, `xpositions`, `energy_and_forces`) but the data lives in HBM.
+"""
+mutable struct GPUSystem{D}
+    handle::Handle
+    n::Int
+    cutoff::Float64
+    function GPUSystem{D}(cfg::MdbConfig) where {D}
+        h = Ref{Handle}(C_NULL)
+        rc = ccall((:mdb_create, libmdb), Cint, (Ref{MdbConfig}, Ref{Handle}), cfg, h)
+        rc == MDB_OK || throw(MdbError(rc, unsafe_string(ccall((:mdb_last_error, libmdb), Cstring, (Handle,), C_NULL))))
+        sys = new{D}(h[], Int(cfg.n_particles), cfg.cutoff)
+        finalizer(s -> ccall((:mdb_destroy, libmdb), Cint, (Handle,), s.handle), sys)
+        return sys
+    end
+end
+
+# Vector{MVector{D,Float64}} <-> the AoS host image the C ABI takes (zero-copy for SVector, one copy for MVector)
+flat(v::Vector{<:StaticVector{D,T}}) where {D,T} = T[x[k] for x in v for k in 1:D]
+unflat(::Val{D}, a::Vector{T}) where {D,T} = [MVector{D,T}(ntuple(k -> a[(i - 1) * D + k], D)) for i in 1:(length(a) ÷ D)]
+
+function upload!(sys::GPUSystem{D}, positions, diameters; velocities=nothing, forces=nothing, images=nothing) where {D}
+    p(x) = x === nothing ? C_NULL : pointer(x)
+    x, d = flat(positions), Vector{Float64}(diameters)
+    v = velocities === nothing ? nothing : flat(velocities)
+    f = forces === nothing ? nothing : flat(forces)
+    im = images === nothing ? nothing : flat(images)
+    GC.@preserve x d v f im check(sys.handle, ccall((:mdb_upload, libmdb), Cint,
+        (Handle, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), sys.handle, p(x), p(v), p(f), p(d), p(im)))
+end
+
+function download(sys::GPUSystem{D}; positions=true, velocities=true, forces=true, images=true) where {D}
+    x = positions ? Vector{Float64}(undef, D * sys.n) : nothing
+    v = velocities ? Vector{Float64}(undef, D * sys.n) : nothing
+    f = forces ? Vector{Float64}(undef, D * sys.n) : nothing
+    im = images ? Vector{Int32}(undef, D * sys.n) : nothing
+    p(a) = a === nothing ? C_NULL : pointer(a)
+    GC.@preserve x v f im check(sys.handle, ccall((:mdb_download, libmdb), Cint,
+        (Handle, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}), sys.handle, p(x), p(v), p(f), p(im)))
+    u(a) = a === nothing ? nothing : unflat(Val(D), a)
+    return u(x), u(v), u(f), u(im)
+end
+
+struct EnergyAndForcesView{D}
+    sys::GPUSystem{D}
+end
+function thermo(sys::GPUSystem)
+    out = zeros(4)
+    check(sys.handle, ccall((:mdb_thermo, libmdb), Cint, (Handle, Ptr{Float64}), sys.handle, out))
+    return out
+end
+function Base.getproperty(sys::GPUSystem{D}, name::Symbol) where {D}
+    name === :positions || name === :xpositions ? download(sys; velocities=false, forces=false, images=false)[1] :
+    name === :energy_and_forces ? EnergyAndForcesView{D}(sys) : getfield(sys, name)
+end
+function Base.getproperty(v::EnergyAndForcesView, name::Symbol)
+    sys = getfield(v, :sys)
+    name === :forces ? download(sys; positions=false, velocities=false, images=false)[3] :
+    name === :energy ? thermo(sys)[1] : name === :virial ? thermo(sys)[2] : getfield(v, name)
+end
+
+"map_pairwise!(energy_and_forces!, system) of src/simulation.jl:99-104 on the device"
+function map_pairwise!(sys::GPUSystem)
+    e, w, n = Ref(0.0), Ref(0.0), Ref(Int64(0))
+    check(sys.handle, ccall((:mdb_compute_forces, libmdb), Cint, (Handle, Ref{Float64}, Ref{Float64}, Ref{Int64}), sys.handle, e, w, n))
+    return e[], w[], n[]
+end
+
+"""
+    to_gpu(state, params; cutoff=1.5, seed=rand(UInt64), device=0, mode=0, skin=0.0)
+
+Move a `SimulationState` produced by the stock `initialize_state` (src/initialization.jl:112-157) to the GPU: the
+`system` field is replaced by a `GPUSystem` holding positions, velocities (if already assigned), forces, images.
+"""
+function to_gpu(state::SimulationState, params::Parameters; cutoff=1.5, seed=rand(UInt64), device=0, mode=0, skin=0.0)
+    D = state.dimension
+    U = state.unitcell
+    all(U[i, j] == 0 for i in 1:D, j in 1:D if i != j) || throw(MdbError(4, "only diagonal unit cells are supported"))
+    tag, pp = potential_tag(params.potential)
+    cell = ntuple(q -> (r = (q - 1) ÷ 3 + 1; c = (q - 1) % 3 + 1; (r <= D && c <= D) ? Float64(U[r, c]) : 0.0), 9)
+    cfg = MdbConfig(D, tag, length(state.system.xpositions), cell, cutoff, pad8(pp), seed, device, mode, skin, 1, 0, 1,
+                    ntuple(_ -> Int32(0), 5))
+    sys = GPUSystem{D}(cfg)
+    upload!(sys, state.system.xpositions, state.diameters;
+            velocities=isempty(state.velocities) ? nothing : state.velocities,
+            forces=state.system.energy_and_forces.forces, images=state.images)
+    return SimulationState(sys, state.diameters, state.rng, state.unitcell, state.velocities, state.images, D, state.nf)
+end
+
+set_velocities!(sys::GPUSystem, v) = (a = flat(v); GC.@preserve a check(sys.handle,
+    ccall((:mdb_set_velocities, libmdb), Cint, (Handle, Ptr{Float64}), sys.handle, a)))
+
+function run_chunk!(sys::GPUSystem, ::NVE, params, steps, first_step)
+    t = zeros(4, length(steps))
+    check(sys.handle, ccall((:mdb_run_nve, libmdb), Cint, (Handle, Int64, Float64, Ptr{Float64}), sys.handle, length(steps), params.dt, t))
+    return t
+end
+function run_chunk!(sys::GPUSystem, ens::NVT, params, steps, first_step)
+    kt = Float64[ens.ktemp(s + 1) for s in steps]          # ensemble.ktemp(step + 1), src/simulation.jl:108, src/integrate.jl:49
+    t = zeros(4, length(steps))
+    check(sys.handle, ccall((:mdb_run_nvt, libmdb), Cint, (Handle, Int64, Float64, Ptr{Float64}, Float64, Ptr{Float64}),
+        sys.handle, length(steps), params.dt, kt, ens.tau, t))
+    return t
+end
+function run_chunk!(sys::GPUSystem, ens::Brownian, params, steps, first_step)
+    t = zeros(4, length(steps))
+    check(sys.handle, ccall((:mdb_run_brownian, libmdb), Cint, (Handle, Int64, Float64, Float64, Ptr{Float64}),
+        sys.handle, length(steps), params.dt, ens.ktemp, t))
+    return t
+end
+
+"""
+    run_simulation!(state::SimulationState{<:GPUSystem}, params, ensemble, total_steps, frequency, pathname; ...)
+
+Same signature, files and thermo rows as src/simulation.jl:40-178 / :181-308.  The loop body runs on the GPU in chunks that
+end exactly at the steps where the reference writes output; only then is state brought back for the text writers.
+"""
+function MolecularDynamics.run_simulation!(state::SimulationState{<:GPUSystem}, params::Parameters, ensemble::Ensemble,
+        total_steps::Int, frequency::Int, pathname::String; traj_name::String="trajectory.xyz",
+        thermo_name::String="thermo.txt", compress::Bool=false, log_times::Bool=false)
+    (trajectory_file, thermo_file) = open_files(pathname, traj_name, thermo_name)
+    open(io -> println(io, "# Step Energy Temperature Pressure"), thermo_file, "a")
+    sys, D, N = state.system, state.dimension, params.n_particles
+    volume = compute_box_volume(state.unitcell)
+    isempty(state.velocities) || set_velocities!(sys, state.velocities)     # lazily assigned velocities (SURVEY Q12)
+    virial, nprom, done = 0.0, 0, 0
+    for step in 0:frequency:(total_steps - 1)
+        t = run_chunk!(sys, ensemble, params, done:step, done)               # steps done..step inclusive
+        if ensemble isa Brownian
+            for (k, s) in enumerate(done:step)
+                if mod(s, 10) == 0
+                    virial += t[2, k]; nprom += 1                            # src/simulation.jl:253-256
+                end
+            end
+        end
+        done = step + 1
+        U, W, KE = t[1, end], t[2, end], t[3, end]
+        if ensemble isa Brownian
+            row = (step, U / N, ensemble.ktemp, virial / (D * nprom * volume) + params.ρ * ensemble.ktemp)
+            virial, nprom = 0.0, 0
+        else
+            T = 2.0 * KE / state.nf
+            row = (step, (U + energy_lrc(params.potential, N, volume)) / N, T,
+                   W / (D * volume) + params.ρ * T + pressure_lrc(params.potential, N, volume))
+        end
+        open(io -> Printf.format(io, Printf.Format("%d %.6f %.6f %.6f\n"), row...), thermo_file, "a")
+        x, _, _, img = download(sys; velocities=false, forces=false)
+        write_to_file_lammps(trajectory_file, step, state.unitcell, N, x, img, state.diameters, D; mode="a")
+    end
+    done < total_steps && run_chunk!(sys, ensemble, params, done:(total_steps - 1), done)
+    _, v, _, img = download(sys; positions=false, forces=false)
+    ensemble isa Brownian || (state.velocities = v)
+    state.images = img
+    finalize_simulation!(trajectory_file, pathname, total_steps, state, params, compress)
+    return nothing
+end
+
+end # module

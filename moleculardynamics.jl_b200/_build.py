@@ -5,7 +5,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(CSRC, "libmdb200.so")
+# MDB200_LIB / MDB200_NVCC_EXTRA: build and load tuning variants side by side (tools/tune_force.py)
+LIB = os.environ.get("MDB200_LIB") or os.path.join(CSRC, "libmdb200.so")
 SOURCES = ["engine.cu"]
 HEADERS = ["kernels.cuh", "potentials.cuh", "rng.cuh", os.path.join("..", "..", "include", "mdb200.h")]
 
@@ -36,7 +37,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    extra = os.environ.get("MDB200_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)

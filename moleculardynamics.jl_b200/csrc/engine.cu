@@ -55,7 +55,10 @@ struct mdb_engine_s {
     int32_t *nnbr = nullptr;
     int kmax = 0;
     int64_t nl_stride = 0;
-    double *part = nullptr, *disp_part = nullptr;
+    double *part = nullptr;
+    uint32_t *ovf = nullptr;  // overflow particle list (MDB_MODE_LIST)
+    int nsm = 148;
+    int force_cta_per_sm = 4, stream_cta_per_sm = 4;
     DevCtl *ctl = nullptr;
     DevCtl *h_ctl = nullptr;  // pinned mirror
     double *d_thermo = nullptr, *d_ktemp = nullptr, *d_scratch = nullptr;
@@ -93,6 +96,11 @@ static int fail(Engine *e, int code, const std::string &msg)
     } while (0)
 
 static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
+// persistent grids: a multiple of the SM count, CTAs walk tiles with a grid stride
+// exactly one resident wave (occupancy API), so no CTA waits for a second wave
+static inline int force_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kForceBlock), e->nsm * e->force_cta_per_sm)); }
+static inline int stream_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * e->stream_cta_per_sm)); }
+constexpr int kOverflowGrid = 8;
 
 template <class F>
 static bool dispatch_pot(int tag, F &&f)
@@ -127,7 +135,8 @@ static void free_state(Engine *e)
         e->st[b] = StatePtrs{};
     }
     cudaFree(e->cell_of); cudaFree(e->slot_of); cudaFree(e->counts); cudaFree(e->start); cudaFree(e->order); cudaFree(e->tile_sums);
-    cudaFree(e->nl); cudaFree(e->nnbr);
+    cudaFree(e->nl); cudaFree(e->nnbr); cudaFree(e->ovf);
+    e->ovf = nullptr;
     e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
     e->nl = nullptr; e->nnbr = nullptr;
 }
@@ -274,6 +283,7 @@ static int alloc_state(Engine *e, int64_t n)
     CU(cudaMalloc(&e->slot_of, sizeof(uint32_t) * e->cap));
     CU(cudaMalloc(&e->order, sizeof(uint32_t) * e->cap));
     CU(cudaMalloc(&e->nnbr, sizeof(int32_t) * e->cap));
+    CU(cudaMalloc(&e->ovf, sizeof(uint32_t) * e->cap));
     return MDB_OK;
 }
 
@@ -298,7 +308,7 @@ static void enqueue_rebuild(Engine *e)
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
             k_build_list<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
-                                                                         e->nnbr, e->ctl);
+                                                                         e->nnbr, e->ovf, e->ctl);
         }
     }
 }
@@ -310,30 +320,60 @@ static void enqueue_force(Engine *e, double dt)
     cudaStream_t s = e->stream;
     const int n = e->n;
     ForceOut out{e->part};
-    int blocks = nblk(n, kForceBlock);
+    int blocks = force_grid(e);
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         if (e->brute)
             k_force_brute<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->cutoff2, pot, e->pp, dt, out);
-        else if (e->mode == MDB_MODE_LIST)
-            k_force_list<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->nl, e->nl_stride, e->kmax,
-                                                                       e->nnbr, e->cutoff2, pot, e->pp, dt, out);
-        else
+        else if (e->mode == MDB_MODE_LIST) {
+            k_force_list<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->nl, e->nl_stride, e->kmax, e->nnbr,
+                                                                       e->cutoff2, e->r_grid + e->skin, pot, e->pp, dt, out);
+            k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
+                                                                                  e->pp, dt, out, blocks);
+        } else
             k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out);
     });
 }
+template <int DIM>
+static void query_occupancy(Engine *e)
+{
+    int best = 32;
+    dispatch_pot(e->cfg.potential, [&](auto pot) {
+        typedef decltype(pot) Pot;
+        int a = 0, b = 0;
+        if (e->brute) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_brute<DIM, Pot, true>, kForceBlock, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_brute<DIM, Pot, false>, kForceBlock, 0);
+        } else if (e->mode == MDB_MODE_LIST) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, true>, kForceBlock, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, false>, kForceBlock, 0);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_cells<DIM, Pot, true>, kForceBlock, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_cells<DIM, Pot, false>, kForceBlock, 0);
+        }
+        best = std::max(1, std::min(a, b));
+    });
+    e->force_cta_per_sm = best;
+    int c = 0, d = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_kick_drift<DIM>, kStreamBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_brownian<DIM>, kStreamBlock, 0);
+    e->stream_cta_per_sm = std::max(1, std::min(c, d));
+    while (e->nsm * e->force_cta_per_sm + kOverflowGrid > kMaxPartials) e->force_cta_per_sm--;
+}
+
+static int force_slots(const Engine *e) { return force_grid(e) + ((e->mode == MDB_MODE_LIST && !e->brute) ? kOverflowGrid : 0); }
+static int force_kernel_count(const Engine *e) { return (e->mode == MDB_MODE_LIST && !e->brute) ? 2 : 1; }
 
 static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHandle handle, int use_handle)
 {
     int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
-    k_skin_check<<<1, kStreamBlock, 0, e->stream>>>(nblk(e->n, kStreamBlock), e->disp_part, scale, e->skin, always, e->ctl, handle,
-                                                    use_handle);
+    k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, always, e->ctl, handle, use_handle);
 }
 
 static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance)
 {
     double nf = e->dim * ((double)e->N - 1.0);  // src/initialization.jl:124
-    k_finalize<<<1, kStreamBlock, 0, e->stream>>>(nblk(e->n, kForceBlock), e->part, ensemble, nf, dt, tau, e->d_ktemp, e->cfg.seed,
+    k_finalize<<<1, kStreamBlock, 0, e->stream>>>(force_slots(e), e->part, ensemble, nf, dt, tau, e->d_ktemp, e->cfg.seed,
                                                   thermo ? e->d_thermo : nullptr, advance, e->ctl);
 }
 
@@ -343,7 +383,7 @@ static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphCondi
 {
     if (ensemble != MDB_BROWNIAN) {
         if (prof) cudaEventRecord(e->evp[0], e->stream);
-        k_kick_drift<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl, e->disp_part);
+        k_kick_drift<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_skin_check(e, dt, handle, use_handle);
     } else {
@@ -364,13 +404,13 @@ static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, do
         enqueue_force<DIM, false>(e, dt);
         if (prof) cudaEventRecord(e->evp[3], e->stream);
         if (prof) cudaEventRecord(e->evp[0], e->stream);
-        k_brownian<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt),
-                                                                                e->cfg.seed, e->ctl, e->disp_part);
+        k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed,
+                                                                      e->ctl);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
     }
 }
-static int step_fixed_kernels(int ensemble) { return ensemble == MDB_BROWNIAN ? 4 : 4; }
+static int step_fixed_kernels(const Engine *e, int ensemble) { return 3 + force_kernel_count(e) + (ensemble == MDB_BROWNIAN ? 0 : 0); }
 
 template <int DIM>
 static int build_graph(Engine *e, const GraphKey &key)
@@ -513,7 +553,7 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
     }
     if (ensemble == MDB_NVT) {
         // the scale of the last step is still pending (it is normally fused into the next kick)
-        k_scale<DIM><<<nblk(e->n, kStreamBlock), kStreamBlock, 0, s>>>(e->n, e->ctl);
+        k_scale<DIM><<<stream_grid(e), kStreamBlock, 0, s>>>(e->n, e->ctl);
         k_reset_alpha<<<1, 1, 0, s>>>(e->ctl);
         e->stats.kernel_launches += 2;
     }
@@ -529,7 +569,7 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
     unsigned long long nreb = e->h_ctl->rebuilds - rebuilds0;
     e->stats.steps += nsteps;
     e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
-    e->stats.kernel_launches += nsteps * step_fixed_kernels(ensemble) + (int64_t)nreb * rebuild_kernel_count(e);
+    e->stats.kernel_launches += nsteps * step_fixed_kernels(e, ensemble) + (int64_t)nreb * rebuild_kernel_count(e);
     e->stats.max_neighbors = e->h_ctl->max_nnbr;
     e->rng_step = e->h_ctl->rng_step;
     if (e->mode == MDB_MODE_LIST && e->h_ctl->max_nnbr > e->kmax) {
@@ -611,8 +651,11 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     memset(e->h_ctl, 0, sizeof(DevCtl));
     CUC(cudaMalloc(&e->part, sizeof(double) * 4 * kMaxPartials));
     CUC(cudaMemset(e->part, 0, sizeof(double) * 4 * kMaxPartials));
-    CUC(cudaMalloc(&e->disp_part, sizeof(double) * kMaxPartials));
-    CUC(cudaMemset(e->disp_part, 0, sizeof(double) * kMaxPartials));
+    {
+        int nsm = 0;
+        CUC(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device));
+        if (nsm > 0) e->nsm = nsm;
+    }
     CUC(cudaMalloc(&e->d_thermo, sizeof(double) * 4 * e->chunk));
     CUC(cudaMalloc(&e->d_ktemp, sizeof(double) * e->chunk));
     CUC(cudaMalloc(&e->d_scratch, sizeof(double) * 16));
@@ -630,7 +673,7 @@ MDB_EXPORT int mdb_destroy(mdb_handle e)
     drop_graph(e);
     free_state(e);
     free_stage(e);
-    cudaFree(e->part); cudaFree(e->disp_part); cudaFree(e->ctl); cudaFree(e->d_thermo); cudaFree(e->d_ktemp); cudaFree(e->d_scratch);
+    cudaFree(e->part); cudaFree(e->ctl); cudaFree(e->d_thermo); cudaFree(e->d_ktemp); cudaFree(e->d_scratch);
     cudaFree(e->d_count);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -652,7 +695,6 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     CU(cudaSetDevice(e->cfg.device));
     const int64_t n = e->N;
     const size_t d = (size_t)e->dim;
-    if (n > (int64_t)kMaxPartials * kForceBlock) return fail(e, MDB_ERR_INVALID_ARG, "too many particles for one handle");
     // diameter extrema decide the potential's range (non-additive mixtures)
     double smin = diameters[0], smax = diameters[0];
     for (int64_t i = 1; i < n; i++) {
@@ -669,6 +711,8 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     if ((rc = ensure_stage(e, n))) return rc;
     if ((rc = plan_neighbors(e))) return rc;
     if ((rc = alloc_neighbors(e))) return rc;
+    if (e->dim == 3) query_occupancy<3>(e);
+    else query_occupancy<2>(e);
     cudaStream_t s = e->stream;
     CU(cudaMemcpyAsync(e->sx, positions, sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(e->sd, diameters, sizeof(double) * n, cudaMemcpyHostToDevice, s));
@@ -684,7 +728,6 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     c.st[1] = e->st[1];
     *e->h_ctl = c;
     CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(e->disp_part, 0, sizeof(double) * kMaxPartials, s));
     int blocks = nblk(n, kStreamBlock);
     if (e->dim == 3)
         k_import<3><<<blocks, kStreamBlock, 0, s>>>(n, e->sx, velocities ? e->sv : nullptr, forces ? e->sf : nullptr, e->sd,
@@ -792,7 +835,7 @@ MDB_EXPORT int mdb_compute_forces(mdb_handle e, double *energy, double *virial, 
     }
     CU(cudaEventRecord(e->evf1, e->stream));
     enqueue_finalize(e, MDB_BROWNIAN, 0.0, 1.0, 0, 0);  // ensemble 2: no kinetic part, no thermostat
-    e->stats.kernel_launches += 2;
+    e->stats.kernel_launches += 1 + force_kernel_count(e);
     CU(cudaEventRecord(e->ev1, e->stream));
     if ((rc = sync_ctl(e))) return rc;
     CU(cudaGetLastError());

@@ -17,7 +17,7 @@ namespace mdb {
 constexpr int kForceBlock = 128;   // threads per CTA in the pair kernels
 constexpr int kStreamBlock = 256;  // threads per CTA in the streaming (integrator / sort) kernels
 constexpr int kQueue = 8;          // deferred-hit queue depth per thread (sparse-hit potentials)
-constexpr int kMaxPartials = 1 << 17;
+constexpr int kMaxPartials = 4096;  // per-CTA partial slots (persistent grids are far smaller)
 
 struct Grid {
     int nc[3];
@@ -48,7 +48,8 @@ struct DevCtl {
     int max_nnbr;                 // largest neighbour count at the last list build
     int nonfinite;
     int cur;                      // which of the two state buffers is live (flipped on device by the re-sort)
-    int rebuilds_lo;
+    int n_overflow;               // particles whose neighbour count exceeded the list capacity at the last build
+    unsigned long long dmax2_bits;  // bit pattern of the largest squared displacement bound of the last move
     unsigned long long rebuilds;
     StatePtrs st[2];
     double fire[8];               // FIRE scalars: dt, alpha, steps_since_neg, converged, P, vnorm2, fnorm2, energy
@@ -426,42 +427,51 @@ __device__ __forceinline__ void pair_accumulate(const Pot &pot, const PotParams 
 }
 
 struct ForceOut {
-    double *part;  // [4][kMaxPartials]: sum_i e_i, sum_i w_i, sum_i n_i, sum_i |v_i|^2
+    double *part;  // [4][kMaxPartials]: per-CTA sums of e_i, w_i, n_i, |v_i|^2
 };
 
-// epilogue shared by the force kernels: store f, optional second half kick (src/integrate.jl:28-38) with the
-// kinetic-energy partial (src/thermostat.jl:50-60), block partials of e, w, n.
+// per-thread running sums across the tiles a persistent CTA walks
+struct ThreadSums {
+    double e = 0.0, w = 0.0, np = 0.0, v2 = 0.0;
+};
+
+// per-particle epilogue shared by the force kernels: store f, optional second half kick (src/integrate.jl:28-38;
+// x*0.5 == x/2.0 bit-for-bit) with the kinetic-energy term (src/thermostat.jl:50-60).
 template <int DIM, bool KICK2>
-__device__ __forceinline__ void force_epilogue(bool active, int i, const double (&F)[3], double e, double w, double np,
-                                               StatePtrs s, double dt, ForceOut out)
+__device__ __forceinline__ void particle_epilogue(int i, const double (&F)[3], const StatePtrs &s, double dt, ThreadSums &acc)
 {
-    double v2 = 0.0;
-    if (active) {
 #pragma unroll
-        for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
-        if (KICK2) {
+    for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
+    if (KICK2) {
+        double v2 = 0.0;
 #pragma unroll
-            for (int k = 0; k < DIM; k++) {
-                double v = s.vel[k * s.cap + i];
-                v += F[k] * dt / 2.0;
-                s.vel[k * s.cap + i] = v;
-                v2 = (k == 0) ? v * v : v2 + v * v;
-            }
+        for (int k = 0; k < DIM; k++) {
+            double v = s.vel[k * s.cap + i];
+            v += (F[k] * dt) * 0.5;
+            s.vel[k * s.cap + i] = v;
+            v2 = (k == 0) ? v * v : v2 + v * v;
         }
-    }
-    double r[4] = {e, w, np, v2};
-    block_reduce<4, kForceBlock>(r);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) out.part[q * kMaxPartials + blockIdx.x] = r[q];
+        acc.v2 += v2;
     }
 }
 
-// deferred-hit queue: for sparse-hit potentials (PseudoHS: ~1 interacting neighbour out of ~26 candidates) a hit in
-// any lane would drag the whole warp through sqrt + divisions every iteration; hits are parked and drained together.
+// one deterministic CTA reduction at the end of the persistent loop
+__device__ __forceinline__ void cta_epilogue(const ThreadSums &acc, ForceOut out, int slot)
+{
+    double r[4] = {acc.e, acc.w, acc.np, acc.v2};
+    block_reduce<4, kForceBlock>(r);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) out.part[q * kMaxPartials + slot] = r[q];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// K4a  pair forces straight from the cell list (MDB_MODE_CELLS; also the list-less fallback)
+// K4a  pair forces straight from the cell list (MDB_MODE_CELLS: the reference's rebuild-every-step shape)
 // Replaces map_pairwise! + energy_and_forces! + evaluate + reducer (src/pairwise.jl:17-39, src/potentials.jl).
+// Persistent CTAs walk 128-particle tiles; candidates that pass the cutoff and the potential's conservative range
+// test are parked in a per-thread shared-memory queue and evaluated together at the end of the tile, so the rare
+// sqrt/divide path (about 1 interacting neighbour out of ~26 candidates for PseudoHS) is not replayed per candidate.
 // ------------------------------------------------------------------------------------------------
 template <int DIM, class Pot, bool KICK2>
 __global__ void __launch_bounds__(kForceBlock)
@@ -470,60 +480,68 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
 {
     __shared__ uint32_t queue[kQueue][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
-    int i = blockIdx.x * kForceBlock + threadIdx.x;
-    bool active = i < n;
-    double F[3] = {0.0, 0.0, 0.0}, e = 0.0, w = 0.0, np = 0.0;
-    double4 pi = make_double4(0, 0, 0, 1);
-    int nq = 0;
     const double4 *__restrict__ pos = s.pos;
-    auto drain_one = [&]() {
-        if (nq > 0) {
-            uint32_t ent = queue[--nq][threadIdx.x];
-            int j = (int)(ent & 0x7ffffffu);
-            int code = (int)(ent >> 27);
-            int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
-            double4 pj = ldg_pos(&pos[j]);
-            double dx = (pi.x - pj.x) - kx * g.L[0], dy = (pi.y - pj.y) - ky * g.L[1];
-            double d2 = fma(dy, dy, dx * dx), dz = 0.0;
-            if (DIM == 3) {
-                dz = (pi.z - pj.z) - kz * g.L[2];
-                d2 = fma(dz, dz, d2);
+    ThreadSums acc;
+    const int ntiles = (n + kForceBlock - 1) / kForceBlock;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i = tile * kForceBlock + threadIdx.x;
+        const bool active = i < n;
+        double F[3] = {0.0, 0.0, 0.0};
+        double4 pi = make_double4(0, 0, 0, 1);
+        int nq = 0;
+        auto drain_one = [&]() {
+            if (nq > 0) {
+                uint32_t ent = queue[--nq][threadIdx.x];
+                int j = (int)(ent & 0x7ffffffu);
+                int code = (int)(ent >> 27);
+                int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
+                double4 pj = ldg_pos(&pos[j]);
+                double dx = (pi.x - pj.x) - kx * g.L[0], dy = (pi.y - pj.y) - ky * g.L[1];
+                double d2 = fma(dy, dy, dx * dx), dz = 0.0;
+                if (DIM == 3) {
+                    dz = (pi.z - pj.z) - kz * g.L[2];
+                    d2 = fma(dz, dz, d2);
+                }
+                pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
-            pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
-        }
-    };
-    if (active) {
-        pi = pos[i];
-        int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
-        int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
-        int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
-        traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, cutoff2,
-                            [&](int j, double dx, double dy, double dz, double d2, double sj, int code) {
-                                if (Pot::kSparseHits) {
-                                    queue[nq++][threadIdx.x] = (uint32_t)j | ((uint32_t)code << 27);
-                                    if (nq == kQueue) {
-                                        while (nq > 0) drain_one();
+        };
+        if (active) {
+            pi = pos[i];
+            int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
+            int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
+            int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
+            traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, cutoff2,
+                                [&](int j, double dx, double dy, double dz, double d2, double sj, int code) {
+                                    if (pot.may_interact(pp, d2, pi.w, sj)) {
+                                        if (Pot::kSparseHits) {
+                                            queue[nq++][threadIdx.x] = (uint32_t)j | ((uint32_t)code << 27);
+                                            if (nq == kQueue) {
+                                                while (nq > 0) drain_one();
+                                            }
+                                        } else {
+                                            pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, sj, F, acc.e, acc.w, acc.np);
+                                        }
                                     }
-                                } else {
-                                    pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, sj, F, e, w, np);
-                                }
-                            });
+                                });
+        }
+        // all lanes drain together: iterations = deepest queue in the warp
+        if (Pot::kSparseHits) {
+            while (__any_sync(0xffffffffu, nq > 0)) drain_one();
+        }
+        if (active) particle_epilogue<DIM, KICK2>(i, F, s, dt, acc);
     }
-    if (Pot::kSparseHits) {
-        // all lanes drain together: iterations = max queue depth in the warp
-        while (__any_sync(0xffffffffu, nq > 0)) drain_one();
-    }
-    force_epilogue<DIM, KICK2>(active, i, F, e, w, np, s, dt, out);
+    cta_epilogue(acc, out, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4b  Verlet list build (r_list = r_search + skin) and list-driven pair forces (MDB_MODE_LIST)
-// nl is column-major: nl[k * stride + i], coalesced across the warp.
+// nl is column-major: nl[k * stride + i], coalesced across the warp.  Particles with more than kmax neighbours are
+// appended to the overflow list and handled exactly by k_force_overflow.
 // ------------------------------------------------------------------------------------------------
 template <int DIM>
 __global__ void __launch_bounds__(kForceBlock)
 k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
-             uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, DevCtl *ctl)
+             uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, uint32_t *__restrict__ ovf, DevCtl *ctl)
 {
     const double4 *__restrict__ pos = ctl->st[ctl->cur].pos;
     int i = blockIdx.x * kForceBlock + threadIdx.x;
@@ -539,6 +557,7 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
                                 cnt++;
                             });
         nnbr[i] = cnt;
+        if (cnt > kmax) ovf[atomicAdd(&ctl->n_overflow, 1)] = (uint32_t)i;
     }
     int m = cnt;
 #pragma unroll
@@ -550,87 +569,148 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
     }
 }
 
+// minimum image of a listed pair: positions are re-wrapped every step, so the image is decided per evaluation,
+// dx = (xi - xj) - k*L with k = +-1 when |xi - xj| > L/2 (the oracle's nearbyint gives the same k for listed pairs)
+template <int DIM>
+__device__ __forceinline__ double separation_wrap(const Grid &g, const double4 &pi, const double4 &pj, double &dx, double &dy, double &dz)
+{
+    dx = pi.x - pj.x;
+    if (dx > g.hL[0]) dx -= g.L[0];
+    else if (dx < -g.hL[0]) dx += g.L[0];
+    dy = pi.y - pj.y;
+    if (dy > g.hL[1]) dy -= g.L[1];
+    else if (dy < -g.hL[1]) dy += g.L[1];
+    double d2 = fma(dy, dy, dx * dx);
+    dz = 0.0;
+    if (DIM == 3) {
+        dz = pi.z - pj.z;
+        if (dz > g.hL[2]) dz -= g.L[2];
+        else if (dz < -g.hL[2]) dz += g.L[2];
+        d2 = fma(dz, dz, d2);
+    }
+    return d2;
+}
+template <int DIM>
+__device__ __forceinline__ double separation_plain(const double4 &pi, const double4 &pj, double &dx, double &dy, double &dz)
+{
+    dx = pi.x - pj.x;
+    dy = pi.y - pj.y;
+    double d2 = fma(dy, dy, dx * dx);
+    dz = 0.0;
+    if (DIM == 3) {
+        dz = pi.z - pj.z;
+        d2 = fma(dz, dz, d2);
+    }
+    return d2;
+}
+
+#ifndef MDB_UNROLL
+#define MDB_UNROLL 8
+#endif
+#ifndef MDB_FORCE_MIN_CTAS
+#define MDB_FORCE_MIN_CTAS 1
+#endif
+constexpr int kUnroll = MDB_UNROLL;  // independent neighbour gathers in flight per thread
+
 template <int DIM, class Pot, bool KICK2>
-__global__ void __launch_bounds__(kForceBlock)
-k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, const uint32_t *__restrict__ nl, int64_t stride,
-             int kmax, const int32_t *__restrict__ nnbr, double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out)
+__global__ void __launch_bounds__(kForceBlock, MDB_FORCE_MIN_CTAS)
+k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ nl, int64_t stride,
+             int kmax, const int32_t *__restrict__ nnbr, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt, ForceOut out)
 {
     __shared__ uint32_t queue[kQueue][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
-    int i = blockIdx.x * kForceBlock + threadIdx.x;
-    bool active = i < n;
-    double F[3] = {0.0, 0.0, 0.0}, e = 0.0, w = 0.0, np = 0.0;
-    double4 pi = make_double4(0, 0, 0, 1);
-    int nq = 0;
     const double4 *__restrict__ pos = s.pos;
-    // positions are re-wrapped every step, so the image of a listed pair is decided per evaluation:
-    // dx = (xi - xj) - k*L with k = +-1 when |xi - xj| > L/2 (identical to the oracle's nearbyint for listed pairs)
-    auto separation = [&](const double4 &pj, double &dx, double &dy, double &dz) -> double {
-        dx = pi.x - pj.x;
-        if (dx > g.hL[0]) dx -= g.L[0];
-        else if (dx < -g.hL[0]) dx += g.L[0];
-        dy = pi.y - pj.y;
-        if (dy > g.hL[1]) dy -= g.L[1];
-        else if (dy < -g.hL[1]) dy += g.L[1];
-        double d2 = fma(dy, dy, dx * dx);
-        dz = 0.0;
-        if (DIM == 3) {
-            dz = pi.z - pj.z;
-            if (dz > g.hL[2]) dz -= g.L[2];
-            else if (dz < -g.hL[2]) dz += g.L[2];
-            d2 = fma(dz, dz, d2);
+    ThreadSums acc;
+    const int ntiles = (n + kForceBlock - 1) / kForceBlock;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i = tile * kForceBlock + threadIdx.x;
+        bool active = i < n;
+        double F[3] = {0.0, 0.0, 0.0};
+        double4 pi = make_double4(0, 0, 0, 1);
+        int nq = 0, cnt = 0;
+        bool wrap = false;
+        if (active) {
+            pi = pos[i];
+            cnt = nnbr[i];
+            if (cnt > kmax) {  // handled in full by k_force_overflow
+                active = false;
+                cnt = 0;
+            }
+            // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
+            wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
+            if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
         }
-        return d2;
-    };
-    auto drain_one = [&]() {
-        if (nq > 0) {
-            int j = (int)queue[--nq][threadIdx.x];
+        auto drain_one = [&]() {
+            if (nq > 0) {
+                int j = (int)queue[--nq][threadIdx.x];
+                double4 pj = ldg_pos(&pos[j]);
+                double dx, dy, dz;
+                double d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
+                pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
+            }
+        };
+        for (int k0 = 0; k0 < cnt; k0 += kUnroll) {
+            uint32_t jj[kUnroll];
+            double4 pj[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) jj[u] = (k0 + u < cnt) ? nl[(int64_t)(k0 + u) * stride + i] : (uint32_t)i;
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) pj[u] = ldg_pos(&pos[jj[u]]);
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                double dx, dy, dz;
+                double d2 = wrap ? separation_wrap<DIM>(g, pi, pj[u], dx, dy, dz) : separation_plain<DIM>(pi, pj[u], dx, dy, dz);
+                if (k0 + u < cnt && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
+                    if (Pot::kSparseHits) queue[nq++][threadIdx.x] = jj[u];
+                    else pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj[u].w, F, acc.e, acc.w, acc.np);
+                }
+            }
+            if (Pot::kSparseHits && nq > kQueue - kUnroll) {
+                while (nq > 0) drain_one();
+            }
+        }
+        if (Pot::kSparseHits) {
+            while (__any_sync(0xffffffffu, nq > 0)) drain_one();
+        }
+        if (active) particle_epilogue<DIM, KICK2>(i, F, s, dt, acc);
+    }
+    cta_epilogue(acc, out, blockIdx.x);
+}
+
+// list overflow (more than kmax neighbours within r_list): exact fallback through the stale-but-conservative
+// build-time cells.  Slot order is the build-time cell order, so the home cell is found by bisection on `start`.
+// One warp-lane per overflowing particle; normally the overflow list is empty and this kernel exits at once.
+template <int DIM, class Pot, bool KICK2>
+__global__ void __launch_bounds__(kForceBlock)
+k_force_overflow(const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, const uint32_t *__restrict__ ovf,
+                 double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out, int slot0)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    const double4 *__restrict__ pos = s.pos;
+    const int novf = ctl->n_overflow;
+    ThreadSums acc;
+    for (int q = blockIdx.x * kForceBlock + threadIdx.x; q < novf; q += gridDim.x * kForceBlock) {
+        const int i = (int)ovf[q];
+        double F[3] = {0.0, 0.0, 0.0};
+        double4 pi = pos[i];
+        int64_t ncell = (int64_t)g.nc[0] * g.nc[1] * g.nc[2];
+        int64_t lo = 0, hi = ncell;  // start[lo] <= i < start[hi]
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if (start[mid] <= (uint32_t)i) lo = mid;
+            else hi = mid;
+        }
+        int cx = (int)(lo % g.nc[0]), cy = (int)((lo / g.nc[0]) % g.nc[1]), cz = (int)(lo / ((int64_t)g.nc[0] * g.nc[1]));
+        traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, 1e300, [&](int j, double, double, double, double, double, int) {
             double4 pj = ldg_pos(&pos[j]);
             double dx, dy, dz;
-            double d2 = separation(pj, dx, dy, dz);
-            pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
-        }
-    };
-    auto candidate = [&](int j) {
-        double4 pj = ldg_pos(&pos[j]);
-        double dx, dy, dz;
-        double d2 = separation(pj, dx, dy, dz);
-        if (d2 <= cutoff2) {
-            if (Pot::kSparseHits) {
-                queue[nq++][threadIdx.x] = (uint32_t)j;
-                if (nq == kQueue) {
-                    while (nq > 0) drain_one();
-                }
-            } else {
-                pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
-            }
-        }
-    };
-    if (active) {
-        pi = pos[i];
-        int cnt = nnbr[i];
-        if (cnt <= kmax) {
-            for (int k = 0; k < cnt; k++) candidate((int)nl[(int64_t)k * stride + i]);
-        } else {
-            // list overflow: exact fallback through the (stale but conservative) build-time cells.
-            // slot order is the build-time cell order, so the home cell is found by bisection on `start`.
-            int64_t ncell = (int64_t)g.nc[0] * g.nc[1] * g.nc[2];
-            int64_t lo = 0, hi = ncell;  // start[lo] <= i < start[hi]
-            while (hi - lo > 1) {
-                int64_t mid = (lo + hi) >> 1;
-                if (start[mid] <= (uint32_t)i) lo = mid;
-                else hi = mid;
-            }
-            int cx = (int)(lo % g.nc[0]), cy = (int)((lo / g.nc[0]) % g.nc[1]), cz = (int)(lo / ((int64_t)g.nc[0] * g.nc[1]));
-            // search everything in the 27 build-time cells; the candidate test re-derives the image
-            traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, 1e300,
-                                [&](int j, double, double, double, double, double, int) { candidate(j); });
-        }
+            double d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
+            if (d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj.w))
+                pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
+        });
+        particle_epilogue<DIM, KICK2>(i, F, s, dt, acc);
     }
-    if (Pot::kSparseHits) {
-        while (__any_sync(0xffffffffu, nq > 0)) drain_one();
-    }
-    force_epilogue<DIM, KICK2>(active, i, F, e, w, np, s, dt, out);
+    cta_epilogue(acc, out, slot0 + blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -642,30 +722,36 @@ __global__ void __launch_bounds__(kForceBlock)
 k_force_brute(int n, const DevCtl *__restrict__ ctl, Grid g, double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out)
 {
     const StatePtrs s = ctl->st[ctl->cur];
-    int i = blockIdx.x * kForceBlock + threadIdx.x;
-    bool active = i < n;
-    double F[3] = {0.0, 0.0, 0.0}, e = 0.0, w = 0.0, np = 0.0;
-    if (active) {
-        double4 pi = s.pos[i];
-        double inv[3] = {g.invL[0], g.invL[1], g.invL[2]};
-        for (int j = 0; j < n; j++) {
-            if (j == i) continue;
-            double4 pj = ldg_pos(&s.pos[j]);
-            double dx = pi.x - pj.x;
-            dx = dx - nearbyint(dx * inv[0]) * g.L[0];
-            double dy = pi.y - pj.y;
-            dy = dy - nearbyint(dy * inv[1]) * g.L[1];
-            double d2 = fma(dy, dy, dx * dx), dz = 0.0;
-            if (DIM == 3) {
-                dz = pi.z - pj.z;
-                dz = dz - nearbyint(dz * inv[2]) * g.L[2];
-                d2 = fma(dz, dz, d2);
+    ThreadSums acc;
+    const int ntiles = (n + kForceBlock - 1) / kForceBlock;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i = tile * kForceBlock + threadIdx.x;
+        if (i < n) {
+            double F[3] = {0.0, 0.0, 0.0};
+            double4 pi = s.pos[i];
+            double inv[3] = {g.invL[0], g.invL[1], g.invL[2]};
+            for (int j = 0; j < n; j++) {
+                if (j == i) continue;
+                double4 pj = ldg_pos(&s.pos[j]);
+                double dx = pi.x - pj.x;
+                dx = dx - nearbyint(dx * inv[0]) * g.L[0];
+                double dy = pi.y - pj.y;
+                dy = dy - nearbyint(dy * inv[1]) * g.L[1];
+                double d2 = fma(dy, dy, dx * dx), dz = 0.0;
+                if (DIM == 3) {
+                    dz = pi.z - pj.z;
+                    dz = dz - nearbyint(dz * inv[2]) * g.L[2];
+                    d2 = fma(dz, dz, d2);
+                }
+                if (d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj.w))
+                    pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
-            if (d2 <= cutoff2) pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
+            particle_epilogue<DIM, KICK2>(i, F, s, dt, acc);
         }
     }
-    force_epilogue<DIM, KICK2>(active, i, F, e, w, np, s, dt, out);
+    cta_epilogue(acc, out, blockIdx.x);
 }
+
 
 // debug pair counter: pairs with d2 <= cutoff^2 (what map_pairwise! visits); per-particle counts in original order
 template <int DIM>
@@ -716,60 +802,41 @@ k_count_pairs(int n, const DevCtl *__restrict__ ctl, Grid g,
 // K5  first half of velocity Verlet, fused with the pending Bussi rescale and the periodic wrap:
 //   v <- v*alpha (bussi!, src/thermostat.jl:45-47, deferred from the previous step)
 //   v += (f*dt)/2 ; x += v*dt ; x = wrap_to_box(x)   (src/integrate.jl:8-21, src/boundary.jl:7-17)
-// also emits the block maximum of |v|^2 that bounds this step's displacement (Verlet-skin bookkeeping).
+// Grid-stride CTAs; each folds its largest |v|^2 into ctl->dmax2_bits with one atomicMax (order-independent, so
+// deterministic): that bounds this step's displacement for the Verlet-skin bookkeeping.
 // ------------------------------------------------------------------------------------------------
 template <int DIM>
 __global__ void __launch_bounds__(kStreamBlock)
-k_kick_drift(int n, Grid g, double dt, const DevCtl *__restrict__ ctl, double *__restrict__ vmax_part)
+k_kick_drift(int n, Grid g, double dt, DevCtl *__restrict__ ctl)
 {
     const StatePtrs s = ctl->st[ctl->cur];
-    int i = blockIdx.x * kStreamBlock + threadIdx.x;
-    double v2 = 0.0;
-    if (i < n) {
-        const double alpha = ctl->alpha;
-        double4 p = s.pos[i];
+    const double alpha = ctl->alpha;
+    double vmax2 = 0.0;
+    for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
+        double4 p = ld_pos(&s.pos[i]);
         double x[3] = {p.x, p.y, p.z};
+        double v2 = 0.0;
 #pragma unroll
         for (int k = 0; k < DIM; k++) {
             double v = s.vel[k * s.cap + i];
             double f = s.frc[k * s.cap + i];
             v = v * alpha;
-            v += f * dt / 2.0;
+            v += (f * dt) * 0.5;  // == f*dt/2.0 bit-for-bit
             s.vel[k * s.cap + i] = v;
             v2 = (k == 0) ? v * v : v2 + v * v;
             double xv = x[k] + v * dt;
-            double invL = g.invL[k];
-            double frac = invL * xv;
+            double frac = g.invL[k] * xv;
             double ncr = floor(frac);
             if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
             x[k] = g.L[k] * (frac - ncr);
         }
-        s.pos[i] = make_double4(x[0], x[1], x[2], p.w);
+        st_pos(&s.pos[i], make_double4(x[0], x[1], x[2], p.w));
+        vmax2 = fmax(vmax2, v2);
     }
-    double r[1] = {v2};
+    double r[1] = {vmax2};
     block_reduce<1, kStreamBlock, true>(r);
-    if (threadIdx.x == 0) vmax_part[blockIdx.x] = r[0];
-}
-
-// second half kick alone (used when the force kernel ran without the fused epilogue)
-template <int DIM>
-__global__ void k_kick2(int n, const DevCtl *__restrict__ ctl, double dt, double *__restrict__ part)
-{
-    const StatePtrs s = ctl->st[ctl->cur];
-    int i = blockIdx.x * kStreamBlock + threadIdx.x;
-    double v2 = 0.0;
-    if (i < n) {
-#pragma unroll
-        for (int k = 0; k < DIM; k++) {
-            double v = s.vel[k * s.cap + i];
-            v += s.frc[k * s.cap + i] * dt / 2.0;
-            s.vel[k * s.cap + i] = v;
-            v2 = (k == 0) ? v * v : v2 + v * v;
-        }
-    }
-    double r[1] = {v2};
-    block_reduce<1, kStreamBlock>(r);
-    if (threadIdx.x == 0) part[3 * kMaxPartials + blockIdx.x] = r[0];
+    // non-negative doubles order like their bit patterns; NaN (0x7ff8...) compares above everything and forces a rebuild
+    if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
 }
 
 // apply a pending Bussi scale to the resident velocities (end of an NVT run) : src/thermostat.jl:45-47
@@ -777,9 +844,8 @@ template <int DIM>
 __global__ void k_scale(int n, DevCtl *ctl)
 {
     const StatePtrs s = ctl->st[ctl->cur];
-    int i = blockIdx.x * kStreamBlock + threadIdx.x;
     const double alpha = ctl->alpha;
-    if (i < n) {
+    for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
 #pragma unroll
         for (int k = 0; k < DIM; k++) s.vel[k * s.cap + i] = s.vel[k * s.cap + i] * alpha;
     }
@@ -790,6 +856,7 @@ __global__ void k_flip(DevCtl *ctl)
 {
     ctl->cur ^= 1;
     ctl->max_nnbr = 0;
+    ctl->n_overflow = 0;
     ctl->rebuilds += 1;
 }
 
@@ -797,70 +864,63 @@ __global__ void k_flip(DevCtl *ctl)
 // sigma = sqrt(2 dt), src/simulation.jl:212).  Noise keyed by (original particle id, RNG step).
 template <int DIM>
 __global__ void __launch_bounds__(kStreamBlock)
-k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, const DevCtl *__restrict__ ctl,
-           double *__restrict__ dmax_part)
+k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, DevCtl *__restrict__ ctl)
 {
     const StatePtrs s = ctl->st[ctl->cur];
-    int i = blockIdx.x * kStreamBlock + threadIdx.x;
-    double d2 = 0.0;
-    if (i < n) {
+    const unsigned long long rng_step = ctl->rng_step;
+    double dmax2 = 0.0;
+    for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
         double noise[3];
-        brownian_noise<DIM>(seed, ctl->rng_step, (uint32_t)s.id[i], noise);
-        double4 p = s.pos[i];
+        brownian_noise<DIM>(seed, rng_step, (uint32_t)s.id[i], noise);
+        double4 p = ld_pos(&s.pos[i]);
         double x[3] = {p.x, p.y, p.z};
+        double d2 = 0.0;
 #pragma unroll
         for (int k = 0; k < DIM; k++) {
             double f = s.frc[k * s.cap + i];
             double xv = x[k] + (f * dt / ktemp) + (noise[k] * sigma);
             double del = xv - x[k];
             d2 = (k == 0) ? del * del : d2 + del * del;
-            double invL = g.invL[k];
-            double frac = invL * xv;
+            double frac = g.invL[k] * xv;
             double ncr = floor(frac);
             if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
             x[k] = g.L[k] * (frac - ncr);
         }
-        s.pos[i] = make_double4(x[0], x[1], x[2], p.w);
+        st_pos(&s.pos[i], make_double4(x[0], x[1], x[2], p.w));
+        dmax2 = fmax(dmax2, d2);
     }
-    double r[1] = {d2};
+    double r[1] = {dmax2};
     block_reduce<1, kStreamBlock, true>(r);
-    if (threadIdx.x == 0) dmax_part[blockIdx.x] = r[0];
+    if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-skin: fold the per-block displacement bounds, decide whether the Verlet list must be rebuilt before the
-// coming force evaluation, and drive the conditional graph node.  part holds max |v|^2 (scale = dt) or max |dx|^2 (scale = 1).
+// K-skin: consume the displacement bound of the move that just happened, decide whether the Verlet list must be
+// rebuilt before the coming force evaluation, and drive the conditional graph node.
+// dmax2 holds max |v|^2 (scale = dt) or max |dx|^2 (scale = 1).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_skin_check(int nblocks, double *__restrict__ part, double scale, double skin, int always, DevCtl *ctl,
-                             cudaGraphConditionalHandle handle, int use_handle)
+__global__ void k_skin_check(double scale, double skin, int always, DevCtl *ctl, cudaGraphConditionalHandle handle, int use_handle)
 {
-    double m = 0.0;
-    for (int q = threadIdx.x; q < nblocks; q += blockDim.x) {
-        m = fmax(m, part[q]);
-        part[q] = 0.0;  // consumed
-    }
-    double r[1] = {m};
-    block_reduce<1, kStreamBlock, true>(r);
-    if (threadIdx.x == 0) {
-        double disp = ctl->disp + sqrt(r[0]) * scale;
-        // NaN-safe: a non-finite bound forces a rebuild
-        int need = always || !ctl->list_valid || !(2.0 * disp <= skin);
-        ctl->disp = need ? 0.0 : disp;
-        ctl->need_rebuild = need;
-        if (use_handle) cudaGraphSetConditional(handle, need ? 1u : 0u);
-    }
+    double m = __longlong_as_double((long long)ctl->dmax2_bits);
+    ctl->dmax2_bits = 0ull;  // consumed
+    double disp = ctl->disp + sqrt(m) * scale;
+    // NaN-safe: a non-finite bound forces a rebuild
+    int need = always || !ctl->list_valid || !(2.0 * disp <= skin);
+    ctl->disp = need ? 0.0 : disp;
+    ctl->need_rebuild = need;
+    if (use_handle) cudaGraphSetConditional(handle, need ? 1u : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K9  thermo: fixed-order second stage of the block partials (deterministic), kinetic energy / temperature
+// K9  thermo: fixed-order second stage of the per-CTA partials (deterministic), kinetic energy / temperature
 // (src/thermostat.jl:50-67), and the Bussi-Donadio-Parrinello scale for NVT (src/thermostat.jl:20-48) drawn from the
 // counter-based RNG.  Feeds the scalars read at src/simulation.jl:118-131.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_finalize(int nblocks, const double *__restrict__ part, int ensemble, double nf, double dt, double tau,
+__global__ void k_finalize(int nslots, const double *__restrict__ part, int ensemble, double nf, double dt, double tau,
                            const double *__restrict__ ktemp, uint64_t seed, double *__restrict__ thermo, int advance, DevCtl *ctl)
 {
     double r[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int q = threadIdx.x; q < nblocks; q += blockDim.x) {
+    for (int q = threadIdx.x; q < nslots; q += blockDim.x) {
 #pragma unroll
         for (int c = 0; c < 4; c++) r[c] += part[c * kMaxPartials + q];
     }
@@ -896,6 +956,7 @@ __global__ void k_finalize(int nblocks, const double *__restrict__ part, int ens
         }
     }
 }
+
 
 __global__ void k_bussi_hooks(int what, double a0, double a1, double a2, double a3, double a4, double a5, double a6, uint64_t seed,
                               uint64_t step, double *out)
