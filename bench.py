@@ -156,6 +156,110 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def main_slabs(args, rank, world, local_rank):
+    """N > 1: the same N-particle workload cut into x-slabs, one process per GPU (strong scaling).  Ghost columns
+    travel with ncclSend/ncclRecv every step, migration at neighbour rebuilds, ncclAllReduce for the rebuild consensus
+    and the global thermo scalars.  Timing: barrier + synchronize on both sides, CUDA events on each rank's stream,
+    MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+    import mdjl_b200 as md
+    from mdjl_b200 import slabs
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    uid = slabs.broadcast_unique_id(dist, rank, md.unique_id, device=dev)
+    n = args.n
+    cfg, v0 = make_workload(n)
+    box = cfg["box"]
+    ring = md.SlabRing.nccl(rank, world, uid, 3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank,
+                            skin=args.skin)
+    ring.upload(cfg["x"], cfg["diam"], velocities=v0)
+
+    def run(k, thermo=False):
+        if args.ensemble == "nve":
+            return ring.run_nve(k, DT, thermo=thermo)
+        if args.ensemble == "nvt":
+            return ring.run_nvt(k, DT, KT, 100 * DT, thermo=thermo)
+        return ring.run_brownian(k, 1e-5, KT, thermo=thermo)
+
+    def sync():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.melt > 0:
+        ring.run_nvt(args.melt, DT, KT, 100 * DT, thermo=False)
+    run(args.warmup)
+    sync()
+    st0 = ring.lead.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_thermo = run(args.steps, thermo=True)
+    sync()
+    st1 = ring.lead.stats()
+    clocks = sampler.stop()
+    t = torch.tensor([st1["last_run_ms"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = torch.tensor([st1["kernel_launches"] - st0["kernel_launches"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(launches)
+    value = n * args.steps / (ms * 1e-3)
+    hbm, peak_src = peaks()
+
+    e2e = None
+    if not args.no_e2e:
+        ids, x_now, v_now, f_now, img_now = ring.download_local()
+        # every rank hands the engine the global arrays it would hold in a replicated host state
+        gx = [None] * world
+        dist.all_gather_object(gx, (ids, x_now, v_now, f_now, img_now))
+        X, V, F, I = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3), np.int32)
+        for (i_, x_, v_, f_, m_) in gx:
+            X[i_], V[i_], F[i_], I[i_] = x_, v_, f_, m_
+        del gx
+        sync()
+        t0 = time.perf_counter()
+        ring.upload(X, cfg["diam"], velocities=V, forces=F, images=I)
+        th = run(args.steps, thermo=True)
+        out = ring.download_local()
+        sync()
+        t_e2e = time.perf_counter() - t0
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+        own = out[0].size
+        e2e = {"value": n * args.steps / t_e2e, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": own * (3 * 24 + 8 + 12 + 4) / args.steps, "d2h_bytes_per_step": (own * (3 * 24 + 12 + 4) + th.nbytes) / args.steps,
+               "seconds": t_e2e, "what": "per rank: mdb_upload(global host arrays -> own slab) + %d steps + mdb_download_owned" % args.steps}
+
+    nf = 3 * (n - 1.0)
+    E = t_thermo[:, 0] + t_thermo[:, 2]
+    step_gbs = BYTES_STEP_3D * n * args.steps / (ms * 1e-3) / 1e9
+    line = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5 3-D pseudo-hard-sphere %s N=%d phi=%.2f dt=%g cutoff=%g" % (args.ensemble.upper(), n, PHI, DT, CUTOFF),
+                   "n_particles": n, "mode": "list", "skin": args.skin or "default",
+                   "l2": "per-rank state (%.2f GiB) exceeds L2" % (n * 96 / 2 ** 30 / world),
+                   "melt_steps": args.melt, "parallelism": "x-slabs x%d, NCCL send/recv ghosts + allreduce, eager launches" % world},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
+        "roofline": None,
+        "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm * world, "unit": "GB/s", "frac": step_gbs / (hbm * world),
+                          "algorithmic_bytes_per_particle_step": BYTES_STEP_3D},
+        "cpu_baseline": None,
+        "owned_per_rank": int(st1["n_owned"]),
+        "rebuilds_in_timed_region": int(st1["rebuilds"] - st0["rebuilds"]),
+        "physics": {"T_mean": float(np.mean(2 * t_thermo[:, 2] / nf)), "U_per_particle": float(np.mean(t_thermo[:, 0]) / n),
+                    "E_drift_rel": float((E.max() - E.min()) / abs(E[0])) if args.ensemble == "nve" else None,
+                    "pairs_last": int(t_thermo[-1, 3])},
+    }
+    ring.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,11 +292,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
-    dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        raise SystemExit("multi-GPU slab path not wired into bench.py yet")
+        return main_slabs(args, rank, world, local_rank)
 
     n = args.n
     cfg, v0 = make_workload(n)

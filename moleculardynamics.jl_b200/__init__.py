@@ -4,7 +4,7 @@ Importable as `mdjl_b200` (see ../mdjl_b200.py; the directory name carries a dot
 reference's exports (src/MolecularDynamics.jl:29-35).
 """
 from . import _build, _capi
-from ._capi import Engine, MdbError
+from ._capi import Engine, MdbError, SlabRing, unique_id
 from .api import (NVE, NVT, Brownian, EnergyAndForces, ExponentialRamp, GPUSystem, LennardJones, LennardJonesXPLOR,
                   LinearRamp, Parameters, Polydisperse, Potential, PseudoHS, SimulationState, energy_lrc, evaluate,
                   initial_temperature_for_velocities, initialize_state, initialize_velocities, lattice_positions,

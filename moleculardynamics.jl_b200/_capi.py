@@ -129,6 +129,15 @@ def _f64(a, shape=None):
     return a
 
 
+def unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks, e.g. torch.distributed.broadcast)"""
+    buf = C.create_string_buffer(128)
+    rc = load().mdb_comm_unique_id(buf)
+    if rc != OK:
+        raise MdbError(rc, (load().mdb_last_error(None) or b"").decode())
+    return buf.raw
+
+
 class Engine:
     """Thin object wrapper over one mdb_handle (one GPU, one host thread)."""
 
@@ -275,6 +284,26 @@ class Engine:
         p = np.ascontiguousarray(params, dtype=np.float64)
         self._check(self._lib.mdb_set_user_potential(self._h, body.encode(), _d(p), p.size, rng))
 
+    def download_owned(self):
+        """-> (ids, x, v, f, img) of the particles this slab currently owns (device slot order)"""
+        cap = int(self.stats()["n_owned"]) + 0
+        # the owned count can change at rebuilds; ask for a safe upper bound
+        cap = max(cap * 2 + 1024, 1024)
+        ids = np.empty(cap, dtype=np.int32)
+        x = np.empty((cap, self.dim))
+        v = np.empty((cap, self.dim))
+        f = np.empty((cap, self.dim))
+        im = np.empty((cap, self.dim), dtype=np.int32)
+        cnt = C.c_int64()
+        self._check(self._lib.mdb_download_owned(self._h, cap, _i(ids), _d(x), _d(v), _d(f), _i(im), C.byref(cnt)))
+        k = cnt.value
+        return ids[:k].copy(), x[:k].copy(), v[:k].copy(), f[:k].copy(), im[:k].copy()
+
+    def comm_init(self, unique_id):
+        """join the NCCL slab ring (one process per GPU); unique_id = bytes from unique_id() on rank 0"""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.mdb_comm_init(self._h, buf))
+
     def stats(self):
         s = Stats()
         self._check(self._lib.mdb_get_stats(self._h, C.byref(s)))
@@ -292,3 +321,73 @@ class Engine:
 
     def synchronize(self):
         self._check(self._lib.mdb_synchronize(self._h))
+
+
+class SlabRing:
+    """x-slab decomposition driver.
+
+    * in-process ring (`SlabRing.local(P, ...)`): P slab engines on ONE device sharing a stream, exchanging through
+      device copies -- the single-GPU emulation of the multi-rank protocol used by the tests;
+    * NCCL ring (`SlabRing.nccl(rank, world, unique_id, ...)`): one process per GPU; every call is collective.
+    Run calls return GLOBAL thermo rows (identical on every rank)."""
+
+    def __init__(self, engines, lead):
+        self.engines = engines
+        self.lead = lead
+
+    @classmethod
+    def local(cls, nranks, dim, n_particles, box, cutoff, potential, pot_params=(), **kw):
+        engines = [Engine(dim, n_particles, box, cutoff, potential, pot_params, rank=r, nranks=nranks, use_graph=False, **kw)
+                   for r in range(nranks)]
+        arr = (_H * nranks)(*[e._h for e in engines])
+        rc = load().mdb_comm_init_local(arr, nranks)
+        if rc != OK:
+            raise MdbError(rc, (load().mdb_last_error(engines[0]._h) or b"").decode())
+        return cls(engines, engines[0])
+
+    @classmethod
+    def nccl(cls, rank, nranks, uid, dim, n_particles, box, cutoff, potential, pot_params=(), **kw):
+        e = Engine(dim, n_particles, box, cutoff, potential, pot_params, rank=rank, nranks=nranks, use_graph=False, **kw)
+        e.comm_init(uid)
+        return cls([e], e)
+
+    def upload(self, positions, diameters, velocities=None, forces=None, images=None):
+        for e in self.engines:   # every rank is shown the global arrays and keeps its slab
+            e.upload(positions, diameters, velocities, forces, images)
+
+    def set_velocities(self, v):
+        for e in self.engines:
+            e.set_velocities(v)
+
+    def compute_forces(self):
+        return self.lead.compute_forces()
+
+    def run_nve(self, nsteps, dt, thermo=True):
+        return self.lead.run_nve(nsteps, dt, thermo)
+
+    def run_nvt(self, nsteps, dt, ktemp, tau, thermo=True):
+        return self.lead.run_nvt(nsteps, dt, ktemp, tau, thermo)
+
+    def run_brownian(self, nsteps, dt, ktemp, thermo=True):
+        return self.lead.run_brownian(nsteps, dt, ktemp, thermo)
+
+    def download_local(self):
+        """owned particles of the slabs this process holds, concatenated: (ids, x, v, f, img)"""
+        parts = [e.download_owned() for e in self.engines]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+
+    def download(self):
+        """global arrays in original particle order (in-process ring only; with NCCL gather download_local across ranks)"""
+        ids, x, v, f, im = self.download_local()
+        n = self.lead.n
+        if ids.size != n or np.unique(ids).size != n:
+            raise RuntimeError("slab ownership is not a partition: %d ids for %d particles" % (ids.size, n))
+        order = np.argsort(ids)
+        return x[order], v[order], f[order], im[order]
+
+    def stats(self):
+        return [e.stats() for e in self.engines]
+
+    def close(self):
+        for e in self.engines:
+            e.close()

@@ -12,6 +12,10 @@
 
 #include "../../include/mdb200.h"
 #include "kernels.cuh"
+#include "slab.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 using namespace mdb;
 
@@ -77,6 +81,21 @@ struct mdb_engine_s {
     mdb_stats stats;
     uint64_t rng_step = 0;
     std::string err;
+
+    // ---- x-slab decomposition (nranks > 1) -------------------------------------------------------
+    int rank = 0, nranks = 1;
+    bool slab = false;
+    int c0 = 0, nxo = 0, nrows = 0;       // owned global cell columns [c0, c0 + nxo); rows = ny * nz
+    int cap_own = 0, mig_cap = 0, ghost_cap = 0;
+    MigRec *mig_send[2] = {nullptr, nullptr}, *mig_recv[2] = {nullptr, nullptr};  // [0] left, [1] right
+    double4 *gh_send[2] = {nullptr, nullptr};
+    double4 *gpos_raw = nullptr;           // [hdr][left ghosts x ghost_cap][hdr][right ghosts x ghost_cap]
+    uint32_t *row_cnt[2] = {nullptr, nullptr}, *rowoff[2] = {nullptr, nullptr}, *gcnt[2] = {nullptr, nullptr},
+             *gstart[2] = {nullptr, nullptr};
+    int transport = 0;                     // 0 none, 1 in-process ring (tests / one-GPU emulation), 2 NCCL
+    std::vector<mdb_engine_s *> *group = nullptr;  // in-process ring, shared by its members; [0] drives it
+    bool stream_owned = true;
+    ncclComm_t comm = nullptr;
 };
 
 typedef mdb_engine_s Engine;
@@ -204,7 +223,7 @@ static int plan_neighbors(Engine *e)
         e->skin = 0;
         e->r_grid = e->r_search;
     } else {
-        if (e->n > 16384) return fail(e, MDB_ERR_BOX_TOO_SMALL, "box has fewer than 3 cells per direction and N is too large for the all-pairs kernel");
+        if (e->N > 16384) return fail(e, MDB_ERR_BOX_TOO_SMALL, "box has fewer than 3 cells per direction and N is too large for the all-pairs kernel");
         e->mode = MDB_MODE_CELLS;
         e->brute = true;
         e->skin = 0;
@@ -214,7 +233,7 @@ static int plan_neighbors(Engine *e)
     // very dilute systems: do not allocate far more cells than particles
     if (!e->brute) {
         double ncell = (double)nc[0] * nc[1] * nc[2];
-        double limit = std::max(64.0, 8.0 * (double)e->n);
+        double limit = std::max(64.0, 8.0 * (double)e->N);
         if (ncell > limit) {
             double sc = std::pow(limit / ncell, 1.0 / d);
             for (int k = 0; k < d; k++) nc[k] = std::max(3, (int)std::floor(nc[k] * sc));
@@ -229,6 +248,27 @@ static int plan_neighbors(Engine *e)
         g.cinv[k] = (double)nc[k] / e->L[k];
     }
     e->ncell = (int64_t)nc[0] * nc[1] * nc[2];
+    g.slab = 0;
+    g.c0 = 0;
+    g.nxo = nc[0];
+    g.kx_left = g.kx_right = 0;
+    g.g0 = 0xffffffffu;
+    g.gstart_l = g.gstart_r = nullptr;
+    g.gpos_m = nullptr;
+    if (e->slab) {
+        if (e->brute) return fail(e, MDB_ERR_BOX_TOO_SMALL, "slab decomposition needs at least 3 cells per direction");
+        e->c0 = (int)((int64_t)e->rank * nc[0] / e->nranks);
+        int c1 = (int)((int64_t)(e->rank + 1) * nc[0] / e->nranks);
+        e->nxo = c1 - e->c0;
+        if (nc[0] / e->nranks < 2) return fail(e, MDB_ERR_BOX_TOO_SMALL, "each slab needs at least two cell columns");
+        e->nrows = nc[1] * nc[2];
+        g.slab = 1;
+        g.c0 = e->c0;
+        g.nxo = e->nxo;
+        g.kx_left = (e->c0 == 0) ? -1 : 0;
+        g.kx_right = (c1 == nc[0]) ? 1 : 0;
+        e->ncell = (int64_t)e->nxo * e->nrows;
+    }
     // neighbour-slot capacity for the Verlet list
     if (e->mode == MDB_MODE_LIST) {
         double rl = e->r_grid;
@@ -260,6 +300,51 @@ static int alloc_neighbors(Engine *e)
     }
     e->stats.list_capacity = e->mode == MDB_MODE_LIST ? e->kmax : 0;
     drop_graph(e);
+    return MDB_OK;
+}
+
+static void free_slab(Engine *e)
+{
+    for (int d = 0; d < 2; d++) {
+        cudaFree(e->mig_send[d]); cudaFree(e->mig_recv[d]); cudaFree(e->gh_send[d]);
+        cudaFree(e->row_cnt[d]); cudaFree(e->rowoff[d]); cudaFree(e->gcnt[d]); cudaFree(e->gstart[d]);
+        e->mig_send[d] = e->mig_recv[d] = nullptr;
+        e->gh_send[d] = nullptr;
+        e->row_cnt[d] = e->rowoff[d] = e->gcnt[d] = e->gstart[d] = nullptr;
+    }
+    cudaFree(e->gpos_raw);
+    e->gpos_raw = nullptr;
+}
+
+static int alloc_slab(Engine *e)
+{
+    free_slab(e);
+    // capacities: leavers per rebuild are a thin layer (skin/2) of the two faces; a boundary column holds n/nxo particles
+    double per_col = (double)e->n / std::max(1, e->nxo);
+    e->mig_cap = (int)std::max(4096.0, 0.5 * per_col + 1024.0);
+    e->ghost_cap = (int)std::max(4096.0, 2.0 * per_col + 1024.0);
+    size_t nr = (size_t)e->nrows + 1;
+    for (int d = 0; d < 2; d++) {
+        CU(cudaMalloc(&e->mig_send[d], sizeof(MigRec) * (1 + (size_t)e->mig_cap)));
+        CU(cudaMalloc(&e->mig_recv[d], sizeof(MigRec) * (1 + (size_t)e->mig_cap)));
+        CU(cudaMemset(e->mig_send[d], 0, sizeof(MigRec)));
+        CU(cudaMemset(e->mig_recv[d], 0, sizeof(MigRec)));
+        CU(cudaMalloc(&e->gh_send[d], sizeof(double4) * (1 + (size_t)e->ghost_cap)));
+        CU(cudaMemset(e->gh_send[d], 0, sizeof(double4)));
+        CU(cudaMalloc(&e->row_cnt[d], sizeof(uint32_t) * nr));
+        CU(cudaMalloc(&e->rowoff[d], sizeof(uint32_t) * nr));
+        CU(cudaMalloc(&e->gcnt[d], sizeof(uint32_t) * nr));
+        CU(cudaMalloc(&e->gstart[d], sizeof(uint32_t) * nr));
+        CU(cudaMemset(e->rowoff[d], 0, sizeof(uint32_t) * nr));
+        CU(cudaMemset(e->gstart[d], 0, sizeof(uint32_t) * nr));
+    }
+    CU(cudaMalloc(&e->gpos_raw, sizeof(double4) * 2 * (1 + (size_t)e->ghost_cap)));
+    CU(cudaMemset(e->gpos_raw, 0, sizeof(double4) * 2 * (1 + (size_t)e->ghost_cap)));
+    Grid &g = e->grid;
+    g.g0 = (uint32_t)e->cap_own;
+    g.gstart_l = e->gstart[0];
+    g.gstart_r = e->gstart[1];
+    g.gpos_m = e->gpos_raw - (ptrdiff_t)g.g0;
     return MDB_OK;
 }
 
@@ -301,10 +386,10 @@ static void enqueue_rebuild(Engine *e)
         k_scan_tile_sums<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums);
         k_scan_tiles<<<1, 1024, 0, s>>>(e->ntiles, e->tile_sums);
         k_scan_apply<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums, e->start);
-        k_fill<<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->cell_of, e->slot_of, e->start, e->order);
-        k_cellsort<<<nblk(e->ncell, kStreamBlock), kStreamBlock, 0, s>>>(e->ncell, e->start, e->order);
-        k_gather<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->order, e->ctl);
-        k_flip<<<1, 1, 0, s>>>(e->ctl);
+        k_fill<<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->ctl, e->cell_of, e->slot_of, e->start, e->order);
+        k_cellsort<<<nblk(e->ncell, kStreamBlock), kStreamBlock, 0, s>>>(e->ncell, e->start, e->order, 0, e->ctl);
+        k_gather<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->order, e->ctl, nullptr);
+        k_flip<<<1, 1, 0, s>>>(e->ctl, nullptr);
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
             k_build_list<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
@@ -370,11 +455,11 @@ static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHand
     k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, always, e->ctl, handle, use_handle);
 }
 
-static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance)
+static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance, int stage = 0)
 {
     double nf = e->dim * ((double)e->N - 1.0);  // src/initialization.jl:124
     k_finalize<<<1, kStreamBlock, 0, e->stream>>>(force_slots(e), e->part, ensemble, nf, dt, tau, e->d_ktemp, e->cfg.seed,
-                                                  thermo ? e->d_thermo : nullptr, advance, e->ctl);
+                                                  thermo ? e->d_thermo : nullptr, advance, e->ctl, stage);
 }
 
 // the part of one step before the (conditional) rebuild
@@ -481,6 +566,345 @@ static int eager_prepare(Engine *e, double scale)
     } else {
         enqueue_rebuild<DIM>(e);
         e->stats.kernel_launches += rebuild_kernel_count(e);
+    }
+    return MDB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// x-slab ring: transports and the group-level step.  A "group" is the set of slab engines this
+// process drives: all ranks for the in-process ring (same device, shared stream), just this rank for NCCL.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool load_nccl(std::string &why)
+{
+    if (g_nccl.lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) {
+        why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+        return false;
+    }
+#define LOADSYM(field, name)                                          \
+    g_nccl.field = (decltype(g_nccl.field))dlsym(g_nccl.lib, name);  \
+    if (!g_nccl.field) {                                              \
+        why = std::string("missing NCCL symbol ") + name;             \
+        return false;                                                 \
+    }
+    LOADSYM(GetUniqueId, "ncclGetUniqueId")
+    LOADSYM(CommInitRank, "ncclCommInitRank")
+    LOADSYM(CommDestroy, "ncclCommDestroy")
+    LOADSYM(Send, "ncclSend")
+    LOADSYM(Recv, "ncclRecv")
+    LOADSYM(AllReduce, "ncclAllReduce")
+    LOADSYM(GroupStart, "ncclGroupStart")
+    LOADSYM(GroupEnd, "ncclGroupEnd")
+    LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+    return true;
+}
+
+#define NC(call)                                                                                                  \
+    do {                                                                                                          \
+        ncclResult_t _r = (call);                                                                                 \
+        if (_r != ncclSuccess) return fail(e, MDB_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+struct PtrList {
+    double *p[16];
+    int n;
+};
+// in-process stand-in for ncclAllReduce: combine `count` doubles across the ring members and give everyone the result
+__global__ void k_local_allreduce(PtrList pl, int count, int is_max)
+{
+    for (int c = threadIdx.x; c < count; c += blockDim.x) {
+        double acc = pl.p[0][c];
+        for (int r = 1; r < pl.n; r++) acc = is_max ? fmax(acc, pl.p[r][c]) : acc + pl.p[r][c];
+        for (int r = 0; r < pl.n; r++) pl.p[r][c] = acc;
+    }
+}
+
+typedef std::vector<Engine *> Group;
+
+// ring exchange: every rank sends `to_left`/`to_right` and receives `from_left`/`from_right` (bytes each)
+template <class GetBuf>
+static int group_exchange(Group &G, size_t bytes, GetBuf buf)
+{
+    // buf(e, 0) = to_left, 1 = to_right, 2 = from_left, 3 = from_right
+    Engine *e = G[0];
+    if (e->transport == 2) {
+        int P = e->nranks, L = (e->rank + P - 1) % P, R = (e->rank + 1) % P;
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.Send(buf(e, 0), bytes, ncclInt8, L, e->comm, e->stream));
+        NC(g_nccl.Send(buf(e, 1), bytes, ncclInt8, R, e->comm, e->stream));
+        NC(g_nccl.Recv(buf(e, 3), bytes, ncclInt8, R, e->comm, e->stream));
+        NC(g_nccl.Recv(buf(e, 2), bytes, ncclInt8, L, e->comm, e->stream));
+        NC(g_nccl.GroupEnd());
+    } else {
+        int P = (int)G.size();
+        for (int r = 0; r < P; r++) {
+            Engine *me = G[r], *left = G[(r + P - 1) % P], *right = G[(r + 1) % P];
+            CU(cudaMemcpyAsync(buf(left, 3), buf(me, 0), bytes, cudaMemcpyDeviceToDevice, e->stream));
+            CU(cudaMemcpyAsync(buf(right, 2), buf(me, 1), bytes, cudaMemcpyDeviceToDevice, e->stream));
+        }
+    }
+    return MDB_OK;
+}
+
+template <class GetPtr>
+static int group_allreduce(Group &G, int count, bool is_max, GetPtr ptr)
+{
+    Engine *e = G[0];
+    if (e->transport == 2) {
+        NC(g_nccl.AllReduce(ptr(e), ptr(e), count, ncclDouble, is_max ? ncclMax : ncclSum, e->comm, e->stream));
+    } else {
+        PtrList pl;
+        pl.n = (int)G.size();
+        for (int r = 0; r < pl.n; r++) pl.p[r] = ptr(G[r]);
+        k_local_allreduce<<<1, 32, 0, e->stream>>>(pl, count, is_max ? 1 : 0);
+    }
+    return MDB_OK;
+}
+
+static inline void *mig_buf(Engine *e, int which) { return which < 2 ? (void *)e->mig_send[which] : (void *)e->mig_recv[which - 2]; }
+static inline void *ghost_buf(Engine *e, int which)
+{
+    if (which < 2) return e->gh_send[which];
+    return e->gpos_raw + (which == 2 ? 0 : 1 + (size_t)e->ghost_cap);  // left ghosts block, right ghosts block
+}
+
+template <int DIM>
+static int group_exchange_ghosts(Group &G)
+{
+    for (Engine *e : G) {
+        k_slab_pack_ghost<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->nxo, e->start, e->rowoff[0],
+                                                                                      e->rowoff[1], e->gh_send[0], e->gh_send[1],
+                                                                                      e->ghost_cap, e->ctl);
+        e->stats.kernel_launches += 1;
+    }
+    return group_exchange(G, sizeof(double4) * (1 + (size_t)G[0]->ghost_cap), ghost_buf);
+}
+
+// the neighbour rebuild of a slab ring: migration, counting sort of the owned set, ghost columns, Verlet list
+template <int DIM>
+static int group_rebuild(Group &G)
+{
+    int rc;
+    for (Engine *e : G) {
+        cudaStream_t s = e->stream;
+        CU(cudaMemsetAsync(e->counts, 0, sizeof(uint32_t) * (e->ncell + 1), s));
+        k_slab_classify<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(e->ctl, e->grid, e->cell_of, e->slot_of, e->counts,
+                                                                                   e->mig_send[0], e->mig_send[1], e->mig_cap);
+        k_slab_mig_headers<<<1, 1, 0, s>>>(e->ctl, e->mig_send[0], e->mig_send[1], e->mig_cap);
+        e->stats.kernel_launches += 2;
+    }
+    if ((rc = group_exchange(G, sizeof(MigRec) * (1 + (size_t)G[0]->mig_cap), mig_buf))) return rc;
+    for (Engine *e : G) {
+        cudaStream_t s = e->stream;
+        const uint32_t *n_new = e->start + e->ncell;
+        k_slab_unpack<DIM><<<nblk(2 * e->mig_cap, kStreamBlock), kStreamBlock, 0, s>>>(e->ctl, e->grid, e->mig_recv[0], e->mig_recv[1],
+                                                                                     e->cell_of, e->slot_of, e->counts, e->cap_own);
+        k_scan_tile_sums<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums);
+        k_scan_tiles<<<1, 1024, 0, s>>>(e->ntiles, e->tile_sums);
+        k_scan_apply<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums, e->start);
+        k_fill<<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(-1, e->ctl, e->cell_of, e->slot_of, e->start, e->order);
+        k_cellsort<<<nblk(e->ncell, kStreamBlock), kStreamBlock, 0, s>>>(e->ncell, e->start, e->order, 1, e->ctl);
+        k_gather<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(-1, e->order, e->ctl, n_new);
+        k_flip<<<1, 1, 0, s>>>(e->ctl, n_new);
+        k_slab_rowcounts<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, s>>>(e->nrows, e->nxo, e->start, e->row_cnt[0], e->row_cnt[1]);
+        k_slab_rowscan<<<1, 1024, 0, s>>>(e->nrows, e->row_cnt[0], e->rowoff[0], 0u, e->row_cnt[1], e->rowoff[1], 0u);
+        e->stats.kernel_launches += 10;
+    }
+    if ((rc = group_exchange_ghosts<DIM>(G))) return rc;
+    for (Engine *e : G) {
+        cudaStream_t s = e->stream;
+        size_t nr = (size_t)e->nrows + 1;
+        CU(cudaMemsetAsync(e->gcnt[0], 0, sizeof(uint32_t) * nr, s));
+        CU(cudaMemsetAsync(e->gcnt[1], 0, sizeof(uint32_t) * nr, s));
+        const double4 *gl = e->gpos_raw, *gr = e->gpos_raw + 1 + (size_t)e->ghost_cap;
+        k_slab_ghost_count<DIM><<<nblk(2 * e->ghost_cap, kStreamBlock), kStreamBlock, 0, s>>>(e->grid, gl, gr, e->gcnt[0], e->gcnt[1]);
+        uint32_t base_l = e->grid.g0 + 1u, base_r = e->grid.g0 + 1u + (uint32_t)e->ghost_cap + 1u;
+        k_slab_rowscan<<<1, 1024, 0, s>>>(e->nrows, e->gcnt[0], e->gstart[0], base_l, e->gcnt[1], e->gstart[1], base_r);
+        e->stats.kernel_launches += 2;
+        if (e->mode == MDB_MODE_LIST) {
+            double rl2 = e->r_grid * e->r_grid;
+            k_build_list<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
+                                                                                  e->nnbr, e->ovf, e->ctl);
+            e->stats.kernel_launches += 1;
+        }
+    }
+    return MDB_OK;
+}
+
+template <int DIM, bool KICK2>
+static void enqueue_force_slab(Engine *e, double dt)
+{
+    cudaStream_t s = e->stream;
+    ForceOut out{e->part};
+    int blocks = force_grid(e);
+    dispatch_pot(e->cfg.potential, [&](auto pot) {
+        typedef decltype(pot) Pot;
+        if (e->mode == MDB_MODE_LIST) {
+            k_force_list<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, e->nl, e->nl_stride, e->kmax, e->nnbr,
+                                                                       e->cutoff2, e->r_grid + e->skin, pot, e->pp, dt, out);
+            k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
+                                                                                  e->pp, dt, out, blocks);
+        } else {
+            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out);
+        }
+    });
+    e->stats.kernel_launches += force_kernel_count(e);
+}
+
+// make every rank's ghosts and neighbour structure current, then evaluate forces and the global thermo scalars.
+// `moved_scale`: factor turning the pending displacement bound into a length (dt for |v|, 1 for |dx|).
+template <int DIM, bool KICK2>
+static int group_force_phase(Group &G, int ensemble, double dt, double tau, double ktemp, double moved_scale, int thermo, int advance)
+{
+    int rc;
+    Engine *lead = G[0];
+    if ((rc = group_exchange_ghosts<DIM>(G))) return rc;
+    if ((rc = group_allreduce(G, 1, true, [](Engine *e) { return (double *)&e->ctl->dmax2_bits; }))) return rc;
+    for (Engine *e : G) {
+        int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
+        k_skin_check<<<1, 1, 0, e->stream>>>(moved_scale, e->skin, always, e->ctl, 0, 0);
+        e->stats.kernel_launches += 1;
+    }
+    {
+        Engine *e = lead;
+        CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    if (lead->h_ctl->need_rebuild) {
+        if ((rc = group_rebuild<DIM>(G))) return rc;
+    }
+    for (Engine *e : G) {
+        enqueue_force_slab<DIM, KICK2>(e, dt);
+        if (ensemble == MDB_BROWNIAN && advance) {
+            k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(-1, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed, e->ctl);
+            e->stats.kernel_launches += 1;
+        }
+        enqueue_finalize(e, ensemble, dt, tau, 0, 0, 1);
+        e->stats.kernel_launches += 1;
+    }
+    if ((rc = group_allreduce(G, 4, false, [](Engine *e) { return e->ctl->red; }))) return rc;
+    for (Engine *e : G) {
+        enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 2);
+        e->stats.kernel_launches += 1;
+    }
+    return MDB_OK;
+}
+
+static int group_check_errors(Group &G)
+{
+    for (Engine *e : G) {
+        int rc = sync_ctl(e);
+        if (rc) return rc;
+        e->n = e->h_ctl->n_own;
+        e->stats.n_owned = e->n;
+        e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
+        e->stats.max_neighbors = e->h_ctl->max_nnbr;
+        e->rng_step = e->h_ctl->rng_step;
+        if (e->h_ctl->error) {
+            int bits = e->h_ctl->error;
+            std::string m = "slab exchange failed:";
+            if (bits & kErrMigrationOverflow) m += " migration buffer overflow;";
+            if (bits & kErrGhostOverflow) m += " ghost buffer overflow;";
+            if (bits & kErrOwnedOverflow) m += " slab capacity exceeded;";
+            if (bits & kErrLongJump) m += " a particle crossed more than one cell column between rebuilds;";
+            return fail(G[0], MDB_ERR_STATE, m);
+        }
+    }
+    return MDB_OK;
+}
+
+template <int DIM>
+static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const double *ktemp_per_step, double tau, double ktemp,
+                     double *thermo)
+{
+    Engine *lead = G[0];
+    Engine *e = lead;
+    for (Engine *m : G) {
+        if (!m->uploaded) return fail(lead, MDB_ERR_STATE, "mdb_upload has not been called on every slab");
+        if (ensemble != MDB_BROWNIAN && !m->have_vel) return fail(lead, MDB_ERR_STATE, "velocities were never set");
+    }
+    if (nsteps < 0 || !(dt > 0)) return fail(lead, MDB_ERR_INVALID_ARG, "nsteps must be >= 0 and dt > 0");
+    if (ensemble == MDB_NVT && (!ktemp_per_step || !(tau > 0))) return fail(lead, MDB_ERR_INVALID_ARG, "NVT needs ktemp_per_step and tau > 0");
+    if (ensemble == MDB_BROWNIAN && !(ktemp > 0)) return fail(lead, MDB_ERR_INVALID_ARG, "Brownian needs ktemp > 0");
+    cudaStream_t s = lead->stream;
+    CU(cudaEventRecord(lead->ev0, s));
+    int rc;
+    int64_t done = 0;
+    while (done < nsteps) {
+        int64_t m = std::min(lead->chunk, nsteps - done);
+        for (Engine *g : G) {
+            if (ensemble == MDB_NVT)
+                CU(cudaMemcpyAsync(g->d_ktemp, ktemp_per_step + done, sizeof(double) * m, cudaMemcpyHostToDevice, g->stream));
+            CU(cudaMemsetAsync(&g->ctl->step, 0, sizeof(unsigned long long), g->stream));
+        }
+        for (int64_t q = 0; q < m; q++) {
+            if (ensemble != MDB_BROWNIAN) {
+                for (Engine *g : G) {
+                    k_kick_drift<DIM><<<stream_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
+                    g->stats.kernel_launches += 1;
+                }
+                if ((rc = group_force_phase<DIM, true>(G, ensemble, dt, tau, ktemp, dt, thermo ? 1 : 0, 1))) return rc;
+            } else {
+                if ((rc = group_force_phase<DIM, false>(G, ensemble, dt, tau, ktemp, 1.0, thermo ? 1 : 0, 1))) return rc;
+            }
+        }
+        if (thermo) CU(cudaMemcpyAsync(thermo + 4 * done, lead->d_thermo, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
+        done += m;
+        if (done < nsteps) CU(cudaStreamSynchronize(s));
+    }
+    if (ensemble == MDB_NVT) {
+        for (Engine *g : G) {
+            k_scale<DIM><<<stream_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->ctl);
+            k_reset_alpha<<<1, 1, 0, g->stream>>>(g->ctl);
+            g->stats.kernel_launches += 2;
+        }
+    }
+    CU(cudaEventRecord(lead->ev1, s));
+    if ((rc = group_check_errors(G))) return rc;
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, lead->ev0, lead->ev1));
+    for (Engine *g : G) {
+        g->stats.last_run_ms = ms;
+        g->stats.steps += nsteps;
+    }
+    if (lead->h_ctl->nonfinite) {
+        for (Engine *g : G) CU(cudaMemsetAsync(&g->ctl->nonfinite, 0, sizeof(int), g->stream));
+        return fail(lead, MDB_ERR_NONFINITE, "non-finite energy: overlapping particles or unstable time step");
+    }
+    return MDB_OK;
+}
+
+static int slab_group(Engine *e, Group &storage, Group **out)
+{
+    if (e->transport == 0) return fail(e, MDB_ERR_STATE, "nranks > 1: call mdb_comm_init or mdb_comm_init_local first");
+    if (e->transport == 1) {
+        if ((*e->group)[0] != e) return fail(e, MDB_ERR_STATE, "in-process slab ring: drive it through the rank-0 handle");
+        *out = e->group;
+    } else {
+        storage.assign(1, e);
+        *out = &storage;
     }
     return MDB_OK;
 }
@@ -611,7 +1035,8 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     case MDB_POT_PSEUDOHS: case MDB_POT_LJ: case MDB_POT_LJ_XPLOR: case MDB_POT_POLY: break;
     default: return fail(nullptr, MDB_ERR_UNSUPPORTED_POTENTIAL, "no device functor for this Potential subtype (no CPU fallback exists)");
     }
-    if (cfg->nranks > 1) return fail(nullptr, MDB_ERR_INVALID_ARG, "nranks > 1: slab decomposition is not available in this build");
+    if (cfg->nranks > 16 || (cfg->nranks > 1 && (cfg->rank < 0 || cfg->rank >= cfg->nranks)))
+        return fail(nullptr, MDB_ERR_INVALID_ARG, "bad rank / nranks (at most 16 slabs)");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -621,6 +1046,9 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     e->cfg = *cfg;
     e->dim = cfg->dim;
     e->N = cfg->n_particles;
+    e->nranks = cfg->nranks > 1 ? cfg->nranks : 1;
+    e->rank = cfg->nranks > 1 ? cfg->rank : 0;
+    e->slab = e->nranks > 1;
     for (int k = 0; k < 3; k++) e->L[k] = (k < cfg->dim) ? cfg->unitcell[4 * k] : 1.0;
     memcpy(e->pp.p, cfg->pot_params, sizeof(e->pp.p));
     memset(&e->stats, 0, sizeof(e->stats));
@@ -673,6 +1101,23 @@ MDB_EXPORT int mdb_destroy(mdb_handle e)
     drop_graph(e);
     free_state(e);
     free_stage(e);
+    free_slab(e);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    if (e->group) {
+        // the ring is shared: detach this member; the last one out frees it
+        Group *G = e->group;
+        for (auto &m : *G)
+            if (m == e) m = nullptr;
+        Engine *heir = nullptr;
+        for (auto m : *G)
+            if (m && !heir) heir = m;
+        if (!heir) delete G;
+        else if (e->stream_owned) {  // the ring shares one stream: the last member out destroys it
+            heir->stream_owned = true;
+            e->stream_owned = false;
+        }
+        e->group = nullptr;
+    }
     cudaFree(e->part); cudaFree(e->ctl); cudaFree(e->d_thermo); cudaFree(e->d_ktemp); cudaFree(e->d_scratch);
     cudaFree(e->d_count);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
@@ -682,7 +1127,7 @@ MDB_EXPORT int mdb_destroy(mdb_handle e)
     if (e->evf1) cudaEventDestroy(e->evf1);
     for (int q = 0; q < 6; q++)
         if (e->evp[q]) cudaEventDestroy(e->evp[q]);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream && e->stream_owned) cudaStreamDestroy(e->stream);
     delete e;
     return MDB_OK;
 }
@@ -703,44 +1148,93 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     }
     if (!(smin > 0) || !std::isfinite(smax)) return fail(e, MDB_ERR_INVALID_ARG, "diameters must be positive and finite");
     e->smin = smin; e->smax = smax;
-    e->n = (int)n;
     int rc;
-    if (e->cap < n || !e->st[0].pos) {
-        if ((rc = alloc_state(e, n))) return rc;
-    }
-    if ((rc = ensure_stage(e, n))) return rc;
     if ((rc = plan_neighbors(e))) return rc;
+    // slab mode: keep the particles whose (wrapped) position falls in this rank's cell columns
+    std::vector<int32_t> keep;
+    const double *hx = positions, *hv = velocities, *hf = forces, *hd = diameters;
+    const int32_t *hi = images;
+    std::vector<double> bx, bv, bf, bd;
+    std::vector<int32_t> bi;
+    int64_t n_res = n;
+    if (e->slab) {
+        const Grid &g = e->grid;
+        for (int64_t i = 0; i < n; i++) {
+            double xv = positions[i * d];
+            if (xv < 0.0 || xv >= g.L[0]) {
+                double frac = g.invL[0] * xv;
+                xv = g.L[0] * (frac - std::floor(frac));
+            }
+            int cx = (int)(xv * g.cinv[0]);
+            cx = cx < g.nc[0] - 1 ? (cx < 0 ? 0 : cx) : g.nc[0] - 1;
+            if (cx >= e->c0 && cx < e->c0 + e->nxo) keep.push_back((int32_t)i);
+        }
+        n_res = (int64_t)keep.size();
+        bx.resize(n_res * d); bd.resize(n_res);
+        if (velocities) bv.resize(n_res * d);
+        if (forces) bf.resize(n_res * d);
+        if (images) bi.resize(n_res * d);
+        for (int64_t q = 0; q < n_res; q++) {
+            int64_t i = keep[q];
+            bd[q] = diameters[i];
+            for (size_t k = 0; k < d; k++) {
+                bx[q * d + k] = positions[i * d + k];
+                if (velocities) bv[q * d + k] = velocities[i * d + k];
+                if (forces) bf[q * d + k] = forces[i * d + k];
+                if (images) bi[q * d + k] = images[i * d + k];
+            }
+        }
+        hx = bx.data(); hd = bd.data();
+        hv = velocities ? bv.data() : nullptr;
+        hf = forces ? bf.data() : nullptr;
+        hi = images ? bi.data() : nullptr;
+        int64_t n_est = std::max<int64_t>(n_res, n / e->nranks);
+        e->cap_own = (int)(((int64_t)(n_est * 1.25) + 4096 + 31) & ~(int64_t)31);
+    }
+    e->n = (int)n_res;
+    int64_t need_cap = e->slab ? e->cap_own : n_res;
+    if (e->cap < need_cap || !e->st[0].pos) {
+        if ((rc = alloc_state(e, need_cap))) return rc;
+    }
+    if (e->slab) e->cap_own = (int)e->cap;
+    if ((rc = ensure_stage(e, std::max<int64_t>(n_res, 1)))) return rc;
     if ((rc = alloc_neighbors(e))) return rc;
+    if (e->slab && (rc = alloc_slab(e))) return rc;
     if (e->dim == 3) query_occupancy<3>(e);
     else query_occupancy<2>(e);
     cudaStream_t s = e->stream;
-    CU(cudaMemcpyAsync(e->sx, positions, sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(e->sd, diameters, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-    if (velocities) CU(cudaMemcpyAsync(e->sv, velocities, sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
-    if (forces) CU(cudaMemcpyAsync(e->sf, forces, sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
-    if (images) CU(cudaMemcpyAsync(e->si, images, sizeof(int32_t) * n * d, cudaMemcpyHostToDevice, s));
+    if (n_res > 0) {
+        CU(cudaMemcpyAsync(e->sx, hx, sizeof(double) * n_res * d, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(e->sd, hd, sizeof(double) * n_res, cudaMemcpyHostToDevice, s));
+        if (hv) CU(cudaMemcpyAsync(e->sv, hv, sizeof(double) * n_res * d, cudaMemcpyHostToDevice, s));
+        if (hf) CU(cudaMemcpyAsync(e->sf, hf, sizeof(double) * n_res * d, cudaMemcpyHostToDevice, s));
+        if (hi) CU(cudaMemcpyAsync(e->si, hi, sizeof(int32_t) * n_res * d, cudaMemcpyHostToDevice, s));
+        if (e->slab) CU(cudaMemcpyAsync(e->sid, keep.data(), sizeof(int32_t) * n_res, cudaMemcpyHostToDevice, s));
+    }
     // control block: buffer 0 live, nothing pending
     DevCtl c;
     memset(&c, 0, sizeof(c));
     c.alpha = 1.0;
     c.rng_step = e->rng_step;
+    c.n_own = (int)n_res;
+    c.n_tmp = (int)n_res;
     c.st[0] = e->st[0];
     c.st[1] = e->st[1];
     *e->h_ctl = c;
     CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
-    int blocks = nblk(n, kStreamBlock);
+    int blocks = std::max(1, nblk(n_res, kStreamBlock));
     if (e->dim == 3)
-        k_import<3><<<blocks, kStreamBlock, 0, s>>>(n, e->sx, velocities ? e->sv : nullptr, forces ? e->sf : nullptr, e->sd,
-                                                   images ? e->si : nullptr, nullptr, e->st[0], e->grid);
+        k_import<3><<<blocks, kStreamBlock, 0, s>>>(n_res, e->sx, hv ? e->sv : nullptr, hf ? e->sf : nullptr, e->sd,
+                                                   hi ? e->si : nullptr, e->slab ? e->sid : nullptr, e->st[0], e->grid);
     else
-        k_import<2><<<blocks, kStreamBlock, 0, s>>>(n, e->sx, velocities ? e->sv : nullptr, forces ? e->sf : nullptr, e->sd,
-                                                   images ? e->si : nullptr, nullptr, e->st[0], e->grid);
+        k_import<2><<<blocks, kStreamBlock, 0, s>>>(n_res, e->sx, hv ? e->sv : nullptr, hf ? e->sf : nullptr, e->sd,
+                                                   hi ? e->si : nullptr, e->slab ? e->sid : nullptr, e->st[0], e->grid);
     e->stats.kernel_launches += 1;
     CU(cudaStreamSynchronize(s));
     CU(cudaGetLastError());
     e->uploaded = true;
     e->have_vel = velocities != nullptr;
-    e->stats.n_owned = n;
+    e->stats.n_owned = e->n;
     return MDB_OK;
 }
 
@@ -750,6 +1244,15 @@ MDB_EXPORT int mdb_set_velocities(mdb_handle e, const double *velocities)
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload first");
     if (!velocities) return fail(e, MDB_ERR_INVALID_ARG, "null velocities");
     CU(cudaSetDevice(e->cfg.device));
+    {
+        int rc0 = ensure_stage(e, e->N);
+        if (rc0) return rc0;
+        if (e->slab) {
+            rc0 = sync_ctl(e);
+            if (rc0) return rc0;
+            e->n = e->h_ctl->n_own;
+        }
+    }
     const int64_t n = e->n;
     cudaStream_t s = e->stream;
     CU(cudaMemcpyAsync(e->sv, velocities, sizeof(double) * e->N * e->dim, cudaMemcpyHostToDevice, s));
@@ -766,6 +1269,7 @@ MDB_EXPORT int mdb_download(mdb_handle e, double *positions, double *velocities,
 {
     if (!e) return MDB_ERR_INVALID_ARG;
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: use mdb_download_owned on every rank");
     CU(cudaSetDevice(e->cfg.device));
     const int64_t n = e->n;
     const size_t d = (size_t)e->dim;
@@ -792,12 +1296,19 @@ MDB_EXPORT int mdb_download_owned(mdb_handle e, int64_t capacity, int32_t *ids, 
 {
     if (!e) return MDB_ERR_INVALID_ARG;
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
-    if (capacity < e->n) return fail(e, MDB_ERR_INVALID_ARG, "capacity smaller than the owned particle count");
     CU(cudaSetDevice(e->cfg.device));
+    {
+        int rc0 = sync_ctl(e);
+        if (rc0) return rc0;
+        e->n = e->h_ctl->n_own;
+    }
+    if (capacity < e->n) return fail(e, MDB_ERR_INVALID_ARG, "capacity smaller than the owned particle count");
+    int rcs = ensure_stage(e, std::max<int64_t>(e->n, 1));
+    if (rcs) return rcs;
     const int64_t n = e->n;
     const size_t d = (size_t)e->dim;
     cudaStream_t s = e->stream;
-    int blocks = nblk(n, kStreamBlock);
+    int blocks = std::max(1, nblk(n, kStreamBlock));
     if (e->dim == 3)
         k_export<3><<<blocks, kStreamBlock, 0, s>>>(n, e->ctl, positions ? e->sx : nullptr, velocities ? e->sv : nullptr,
                                                    forces ? e->sf : nullptr, images ? e->si : nullptr, 0);
@@ -823,6 +1334,22 @@ MDB_EXPORT int mdb_compute_forces(mdb_handle e, double *energy, double *virial, 
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
     CU(cudaSetDevice(e->cfg.device));
     int rc;
+    if (e->slab) {
+        // collective over the slab ring: every rank (or the rank-0 handle of an in-process ring) calls it;
+        // energy, virial and pair count are the GLOBAL values on every rank
+        Group storage, *G = nullptr;
+        if ((rc = slab_group(e, storage, &G))) return rc;
+        for (Engine *m : *G)
+            if (!m->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload has not been called on every slab");
+        rc = e->dim == 3 ? group_force_phase<3, false>(*G, MDB_BROWNIAN, 0.0, 1.0, 1.0, 1.0, 0, 0)
+                         : group_force_phase<2, false>(*G, MDB_BROWNIAN, 0.0, 1.0, 1.0, 1.0, 0, 0);
+        if (rc) return rc;
+        if ((rc = group_check_errors(*G))) return rc;
+        if (energy) *energy = e->h_ctl->last[0];
+        if (virial) *virial = e->h_ctl->last[1];
+        if (n_pairs) *n_pairs = (int64_t)llround(e->h_ctl->last[3]);
+        return MDB_OK;
+    }
     CU(cudaEventRecord(e->ev0, e->stream));
     if (e->dim == 3) {
         if ((rc = eager_prepare<3>(e, 1.0))) return rc;
@@ -862,6 +1389,7 @@ MDB_EXPORT int mdb_count_pairs(mdb_handle e, double cutoff, int64_t *n_pairs, in
     if (!e) return MDB_ERR_INVALID_ARG;
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
     if (!(cutoff > 0)) return fail(e, MDB_ERR_INVALID_ARG, "cutoff must be > 0");
+    if (e->slab) return fail(e, MDB_ERR_STATE, "mdb_count_pairs is a single-domain debug call");
     CU(cudaSetDevice(e->cfg.device));
     for (int k = 0; k < e->dim; k++)
         if (!(cutoff < 0.5 * e->L[k])) return fail(e, MDB_ERR_BOX_TOO_SMALL, "cutoff must be < L/2");
@@ -928,6 +1456,13 @@ static int run_dispatch(Engine *e, int ensemble, int64_t nsteps, double dt, cons
 {
     if (!e) return MDB_ERR_INVALID_ARG;
     CU(cudaSetDevice(e->cfg.device));
+    if (e->slab) {
+        Group storage, *G = nullptr;
+        int rc = slab_group(e, storage, &G);
+        if (rc) return rc;
+        return e->dim == 3 ? run_group<3>(*G, ensemble, nsteps, dt, kt, tau, ktemp, thermo)
+                           : run_group<2>(*G, ensemble, nsteps, dt, kt, tau, ktemp, thermo);
+    }
     return e->dim == 3 ? run_impl<3>(e, ensemble, nsteps, dt, kt, tau, ktemp, thermo)
                        : run_impl<2>(e, ensemble, nsteps, dt, kt, tau, ktemp, thermo);
 }
@@ -1011,9 +1546,57 @@ MDB_EXPORT int mdb_set_user_potential(mdb_handle e, const char *, const double *
     return fail(e, MDB_ERR_NVRTC, "mdb_set_user_potential: not available in this build");
 }
 
-MDB_EXPORT int mdb_comm_unique_id(char *) { return fail(nullptr, MDB_ERR_NCCL, "slab decomposition is not available in this build"); }
-MDB_EXPORT int mdb_comm_init(mdb_handle e, const char *) { return fail(e, MDB_ERR_NCCL, "slab decomposition is not available in this build"); }
-MDB_EXPORT int mdb_comm_init_local(mdb_handle *, int32_t) { return fail(nullptr, MDB_ERR_NCCL, "slab decomposition is not available in this build"); }
+MDB_EXPORT int mdb_comm_unique_id(char *id)
+{
+    Engine *e = nullptr;
+    if (!id) return fail(e, MDB_ERR_INVALID_ARG, "null id");
+    std::string why;
+    if (!load_nccl(why)) return fail(e, MDB_ERR_NCCL, why);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId uid;
+    NC(g_nccl.GetUniqueId(&uid));
+    memcpy(id, &uid, sizeof(uid));
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_comm_init(mdb_handle e, const char *id)
+{
+    if (!e || !id) return MDB_ERR_INVALID_ARG;
+    if (!e->slab) return fail(e, MDB_ERR_INVALID_ARG, "handle was created with nranks == 1");
+    if (e->transport != 0) return fail(e, MDB_ERR_STATE, "communicator already initialised");
+    std::string why;
+    if (!load_nccl(why)) return fail(e, MDB_ERR_NCCL, why);
+    CU(cudaSetDevice(e->cfg.device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NC(g_nccl.CommInitRank(&e->comm, e->nranks, uid, e->rank));
+    e->transport = 2;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_comm_init_local(mdb_handle *handles, int32_t count)
+{
+    Engine *e = nullptr;
+    if (!handles || count < 2 || count > 16) return fail(e, MDB_ERR_INVALID_ARG, "need 2..16 handles");
+    for (int r = 0; r < count; r++) {
+        Engine *m = handles[r];
+        if (!m || !m->slab || m->nranks != count || m->rank != r || m->transport != 0 || m->cfg.device != handles[0]->cfg.device)
+            return fail(handles[0], MDB_ERR_INVALID_ARG, "handles[r] must be the rank-r slab of a ring of `count` slabs on one device");
+    }
+    Group *G = new Group(handles, handles + count);
+    for (int r = 0; r < count; r++) {
+        Engine *m = handles[r];
+        m->group = G;
+        m->transport = 1;
+        if (r > 0) {  // one stream orders the whole ring
+            cudaStreamSynchronize(m->stream);
+            cudaStreamDestroy(m->stream);
+            m->stream = handles[0]->stream;
+            m->stream_owned = false;
+        }
+    }
+    return MDB_OK;
+}
 
 MDB_EXPORT int mdb_get_stats(mdb_handle e, mdb_stats *out)
 {

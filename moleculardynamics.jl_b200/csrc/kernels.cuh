@@ -25,6 +25,13 @@ struct Grid {
     double L[3];
     double invL[3];  // 1 / L  (IEEE division on the host == the reference's inv(U) for a diagonal cell)
     double hL[3];    // L / 2
+    // x-slab decomposition (nranks > 1): this rank owns the global cell columns [c0, c0 + nxo); the two neighbouring
+    // columns are ghosts held in a separate buffer.  Single domain: slab = 0, c0 = 0, nxo = nc[0] (periodic in x).
+    int slab, c0, nxo;
+    int kx_left, kx_right;           // image shift of the left/right ghost column (-1 / +1 when it wraps around the box)
+    uint32_t g0;                     // neighbour indices >= g0 address ghosts: gpos_m[j]
+    const uint32_t *gstart_l, *gstart_r;  // [ny*nz + 1] ghost index ranges per (cz,cy) row
+    const double4 *gpos_m;           // ghost positions, biased so that gpos_m[g0 + k] is ghost record k
 };
 
 struct StatePtrs {
@@ -49,6 +56,11 @@ struct DevCtl {
     int nonfinite;
     int cur;                      // which of the two state buffers is live (flipped on device by the re-sort)
     int n_overflow;               // particles whose neighbour count exceeded the list capacity at the last build
+    int n_own;                    // particles owned by this handle (changes on the device when slabs migrate)
+    int n_tmp;                    // owned + arrived migrants during a slab rebuild
+    int mig_count[2];             // migrants packed for the left / right neighbour
+    int error;                    // sticky device-side error bits (see kErr*)
+    double red[4];                // slab mode: local sums of U, W, n_pairs, |v|^2 awaiting the all-reduce
     unsigned long long dmax2_bits;  // bit pattern of the largest squared displacement bound of the last move
     unsigned long long rebuilds;
     StatePtrs st[2];
@@ -170,6 +182,7 @@ __global__ void k_export(int64_t n, const DevCtl *__restrict__ ctl, double *__re
                          int32_t *__restrict__ im, int to_original)
 {
     const StatePtrs s = ctl->st[ctl->cur];
+    if (n < 0) n = ctl->n_own;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int64_t o = to_original ? s.id[i] : i;
@@ -192,13 +205,14 @@ template <int DIM>
 __global__ void k_hash(int64_t n, const DevCtl *__restrict__ ctl, Grid g, uint32_t *__restrict__ cell_of,
                        uint32_t *__restrict__ slot_of, uint32_t *__restrict__ counts)
 {
+    if (n < 0) n = ctl->n_own;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double4 p = ctl->st[ctl->cur].pos[i];
     int cx = cell_coord(p.x, g.cinv[0], g.nc[0]);
     int cy = cell_coord(p.y, g.cinv[1], g.nc[1]);
     int cz = (DIM == 3) ? cell_coord(p.z, g.cinv[2], g.nc[2]) : 0;
-    uint32_t c = ((uint32_t)cz * g.nc[1] + cy) * g.nc[0] + cx;
+    uint32_t c = ((uint32_t)cz * g.nc[1] + cy) * g.nxo + (cx - g.c0);
     cell_of[i] = c;
     slot_of[i] = atomicAdd(&counts[c], 1u);
 }
@@ -287,35 +301,57 @@ __global__ void k_scan_apply(int64_t n, const uint32_t *__restrict__ in, const u
     }
 }
 
-__global__ void k_fill(int64_t n, const uint32_t *__restrict__ cell_of, const uint32_t *__restrict__ slot_of,
-                       const uint32_t *__restrict__ start, uint32_t *__restrict__ order)
+constexpr uint32_t kInvalidCell = 0xffffffffu;  // particle that left this slab (migrated away)
+
+__global__ void k_fill(int64_t n, const DevCtl *__restrict__ ctl, const uint32_t *__restrict__ cell_of,
+                       const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ start, uint32_t *__restrict__ order)
 {
+    if (n < 0) n = ctl->n_tmp;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    order[start[cell_of[i]] + slot_of[i]] = (uint32_t)i;
+    uint32_t c = cell_of[i];
+    if (c != kInvalidCell) order[start[c] + slot_of[i]] = (uint32_t)i;
 }
 
 // canonical (ascending previous-slot) order inside each cell: removes the atomic-arrival nondeterminism,
 // so the whole pipeline is a stable counting sort and reruns are bit-identical
-__global__ void k_cellsort(int64_t ncell, const uint32_t *__restrict__ start, uint32_t *__restrict__ order)
+// by_id: order by original particle id instead of previous slot (slab mode: migrants arrive in arbitrary order)
+__global__ void k_cellsort(int64_t ncell, const uint32_t *__restrict__ start, uint32_t *__restrict__ order, int by_id,
+                           const DevCtl *__restrict__ ctl)
 {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= ncell) return;
     uint32_t b = start[c], e = start[c + 1];
-    for (uint32_t a = b + 1; a < e; a++) {
-        uint32_t key = order[a];
-        uint32_t q = a;
-        while (q > b && order[q - 1] > key) {
-            order[q] = order[q - 1];
-            q--;
+    if (!by_id) {
+        for (uint32_t a = b + 1; a < e; a++) {
+            uint32_t key = order[a];
+            uint32_t q = a;
+            while (q > b && order[q - 1] > key) {
+                order[q] = order[q - 1];
+                q--;
+            }
+            order[q] = key;
         }
-        order[q] = key;
+    } else {
+        const int32_t *__restrict__ id = ctl->st[ctl->cur].id;
+        for (uint32_t a = b + 1; a < e; a++) {
+            uint32_t key = order[a];
+            int32_t kid = id[key];
+            uint32_t q = a;
+            while (q > b && id[order[q - 1]] > kid) {
+                order[q] = order[q - 1];
+                q--;
+            }
+            order[q] = key;
+        }
     }
 }
 
 template <int DIM>
-__global__ void k_gather(int64_t n, const uint32_t *__restrict__ order, const DevCtl *__restrict__ ctl)
+__global__ void k_gather(int64_t n, const uint32_t *__restrict__ order, const DevCtl *__restrict__ ctl,
+                         const uint32_t *__restrict__ n_new)
 {
+    if (n < 0) n = *n_new;  // slab mode: the owned count after migration = start[number of owned cells]
     const StatePtrs src = ctl->st[ctl->cur], dst = ctl->st[ctl->cur ^ 1];
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -342,7 +378,8 @@ __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__
                                                const double4 *__restrict__ pos, int i, const double4 &pi, int cx, int cy,
                                                int cz, double r2, Visit &&visit)
 {
-    const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+    const int nx = g.nxo, ny = g.nc[1], nz = g.nc[2];
+    const int lx = cx - g.c0;
     for (int dz = (DIM == 3 ? -1 : 0); dz <= (DIM == 3 ? 1 : 0); dz++) {
         int oz = cz + dz;
         int kz = 0;
@@ -355,26 +392,43 @@ __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__
             int ky = 0;
             if (oy < 0) { oy += ny; ky = -1; }
             else if (oy >= ny) { oy -= ny; ky = 1; }
-            const uint32_t row = ((uint32_t)oz * ny + oy) * nx;
+            const uint32_t rowg = (uint32_t)oz * ny + oy;
+            const uint32_t row = rowg * nx;
             // up to two contiguous segments along x
-            int seg_lo[2], seg_hi[2], seg_k[2], nseg = 1;
-            seg_lo[0] = cx - 1; seg_hi[0] = cx + 1; seg_k[0] = 0;
-            if (cx == 0) {
-                seg_lo[0] = 0; seg_hi[0] = 1; seg_k[0] = 0;
-                seg_lo[1] = nx - 1; seg_hi[1] = nx - 1; seg_k[1] = -1;
-                nseg = 2;
-            } else if (cx == nx - 1) {
-                seg_lo[0] = nx - 2; seg_hi[0] = nx - 1; seg_k[0] = 0;
-                seg_lo[1] = 0; seg_hi[1] = 0; seg_k[1] = 1;
-                nseg = 2;
+            uint32_t seg_b[2], seg_e[2];
+            int seg_k[2], nseg = 1;
+            const double4 *seg_p[2] = {pos, pos};
+            if (!g.slab) {
+                if (lx == 0) {
+                    seg_b[0] = start[row]; seg_e[0] = start[row + 2]; seg_k[0] = 0;
+                    seg_b[1] = start[row + nx - 1]; seg_e[1] = start[row + nx]; seg_k[1] = -1;
+                    nseg = 2;
+                } else if (lx == nx - 1) {
+                    seg_b[0] = start[row + nx - 2]; seg_e[0] = start[row + nx]; seg_k[0] = 0;
+                    seg_b[1] = start[row]; seg_e[1] = start[row + 1]; seg_k[1] = 1;
+                    nseg = 2;
+                } else {
+                    seg_b[0] = start[row + lx - 1]; seg_e[0] = start[row + lx + 2]; seg_k[0] = 0;
+                }
+            } else {
+                const int lo = lx > 0 ? lx - 1 : 0, hi = lx < nx - 1 ? lx + 1 : nx - 1;
+                seg_b[0] = start[row + lo]; seg_e[0] = start[row + hi + 1]; seg_k[0] = 0;
+                if (lx == 0) {
+                    seg_b[1] = g.gstart_l[rowg]; seg_e[1] = g.gstart_l[rowg + 1]; seg_k[1] = g.kx_left; seg_p[1] = g.gpos_m;
+                    nseg = 2;
+                } else if (lx == nx - 1) {
+                    seg_b[1] = g.gstart_r[rowg]; seg_e[1] = g.gstart_r[rowg + 1]; seg_k[1] = g.kx_right; seg_p[1] = g.gpos_m;
+                    nseg = 2;
+                }
             }
             for (int sgi = 0; sgi < nseg; sgi++) {
-                const uint32_t jb = start[row + seg_lo[sgi]], je = start[row + seg_hi[sgi] + 1];
+                const uint32_t jb = seg_b[sgi], je = seg_e[sgi];
                 const int kx = seg_k[sgi];
+                const double4 *__restrict__ src = seg_p[sgi];
                 const int code = (kx + 1) + 3 * (ky + 1) + 9 * (kz + 1);
                 if (code == 13) {
                     for (uint32_t j = jb; j < je; j++) {
-                        double4 pj = ldg_pos(&pos[j]);
+                        double4 pj = ldg_pos(&src[j]);
                         double dx = pi.x - pj.x, dy_ = pi.y - pj.y;
                         double d2 = fma(dy_, dy_, dx * dx);
                         double dz_ = 0.0;
@@ -387,7 +441,7 @@ __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__
                 } else {
                     const double sx = kx * g.L[0], sy = ky * g.L[1], sz = (DIM == 3) ? kz * g.L[2] : 0.0;
                     for (uint32_t j = jb; j < je; j++) {
-                        double4 pj = ldg_pos(&pos[j]);
+                        double4 pj = ldg_pos(&src[j]);
                         double dx = (pi.x - pj.x) - sx, dy_ = (pi.y - pj.y) - sy;
                         double d2 = fma(dy_, dy_, dx * dx);
                         double dz_ = 0.0;
@@ -401,6 +455,12 @@ __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__
             }
         }
     }
+}
+
+// owned neighbours live in the (double-buffered) state, ghosts of an x-slab in their own receive buffer
+__device__ __forceinline__ const double4 *nbr_ptr(const Grid &g, const double4 *pos, uint32_t j)
+{
+    return j >= g.g0 ? g.gpos_m + j : pos + j;
 }
 
 // per-pair update: src/pairwise.jl:26-39 (one side of it: the gather evaluates each pair from both ends,
@@ -482,6 +542,7 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     ThreadSums acc;
+    if (n < 0) n = ctl->n_own;
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = tile * kForceBlock + threadIdx.x;
@@ -495,7 +556,7 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
                 int j = (int)(ent & 0x7ffffffu);
                 int code = (int)(ent >> 27);
                 int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
-                double4 pj = ldg_pos(&pos[j]);
+                double4 pj = ldg_pos(nbr_ptr(g, pos, (uint32_t)j));
                 double dx = (pi.x - pj.x) - kx * g.L[0], dy = (pi.y - pj.y) - ky * g.L[1];
                 double d2 = fma(dy, dy, dx * dx), dz = 0.0;
                 if (DIM == 3) {
@@ -544,6 +605,7 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
              uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, uint32_t *__restrict__ ovf, DevCtl *ctl)
 {
     const double4 *__restrict__ pos = ctl->st[ctl->cur].pos;
+    if (n < 0) n = ctl->n_own;
     int i = blockIdx.x * kForceBlock + threadIdx.x;
     int cnt = 0;
     if (i < n) {
@@ -621,6 +683,7 @@ k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__re
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     ThreadSums acc;
+    if (n < 0) n = ctl->n_own;
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = tile * kForceBlock + threadIdx.x;
@@ -643,7 +706,7 @@ k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__re
         auto drain_one = [&]() {
             if (nq > 0) {
                 int j = (int)queue[--nq][threadIdx.x];
-                double4 pj = ldg_pos(&pos[j]);
+                double4 pj = ldg_pos(nbr_ptr(g, pos, (uint32_t)j));
                 double dx, dy, dz;
                 double d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
@@ -655,7 +718,7 @@ k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__re
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) jj[u] = (k0 + u < cnt) ? nl[(int64_t)(k0 + u) * stride + i] : (uint32_t)i;
 #pragma unroll
-            for (int u = 0; u < kUnroll; u++) pj[u] = ldg_pos(&pos[jj[u]]);
+            for (int u = 0; u < kUnroll; u++) pj[u] = ldg_pos(nbr_ptr(g, pos, jj[u]));
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
                 double dx, dy, dz;
@@ -693,16 +756,16 @@ k_force_overflow(const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restr
         const int i = (int)ovf[q];
         double F[3] = {0.0, 0.0, 0.0};
         double4 pi = pos[i];
-        int64_t ncell = (int64_t)g.nc[0] * g.nc[1] * g.nc[2];
+        int64_t ncell = (int64_t)g.nxo * g.nc[1] * g.nc[2];
         int64_t lo = 0, hi = ncell;  // start[lo] <= i < start[hi]
         while (hi - lo > 1) {
             int64_t mid = (lo + hi) >> 1;
             if (start[mid] <= (uint32_t)i) lo = mid;
             else hi = mid;
         }
-        int cx = (int)(lo % g.nc[0]), cy = (int)((lo / g.nc[0]) % g.nc[1]), cz = (int)(lo / ((int64_t)g.nc[0] * g.nc[1]));
+        int cx = (int)(lo % g.nxo) + g.c0, cy = (int)((lo / g.nxo) % g.nc[1]), cz = (int)(lo / ((int64_t)g.nxo * g.nc[1]));
         traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, 1e300, [&](int j, double, double, double, double, double, int) {
-            double4 pj = ldg_pos(&pos[j]);
+            double4 pj = ldg_pos(nbr_ptr(g, pos, (uint32_t)j));
             double dx, dy, dz;
             double d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
             if (d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj.w))
@@ -723,6 +786,7 @@ k_force_brute(int n, const DevCtl *__restrict__ ctl, Grid g, double cutoff2, Pot
 {
     const StatePtrs s = ctl->st[ctl->cur];
     ThreadSums acc;
+    if (n < 0) n = ctl->n_own;
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = tile * kForceBlock + threadIdx.x;
@@ -811,6 +875,7 @@ k_kick_drift(int n, Grid g, double dt, DevCtl *__restrict__ ctl)
 {
     const StatePtrs s = ctl->st[ctl->cur];
     const double alpha = ctl->alpha;
+    if (n < 0) n = ctl->n_own;
     double vmax2 = 0.0;
     for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
         double4 p = ld_pos(&s.pos[i]);
@@ -845,6 +910,7 @@ __global__ void k_scale(int n, DevCtl *ctl)
 {
     const StatePtrs s = ctl->st[ctl->cur];
     const double alpha = ctl->alpha;
+    if (n < 0) n = ctl->n_own;
     for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
 #pragma unroll
         for (int k = 0; k < DIM; k++) s.vel[k * s.cap + i] = s.vel[k * s.cap + i] * alpha;
@@ -852,8 +918,10 @@ __global__ void k_scale(int n, DevCtl *ctl)
 }
 __global__ void k_reset_alpha(DevCtl *ctl) { ctl->alpha = 1.0; }
 // after the gather-reorder: the other state buffer becomes live
-__global__ void k_flip(DevCtl *ctl)
+__global__ void k_flip(DevCtl *ctl, const uint32_t *__restrict__ n_new)
 {
+    if (n_new) ctl->n_own = (int)*n_new;
+    ctl->mig_count[0] = ctl->mig_count[1] = 0;
     ctl->cur ^= 1;
     ctl->max_nnbr = 0;
     ctl->n_overflow = 0;
@@ -868,6 +936,7 @@ k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, 
 {
     const StatePtrs s = ctl->st[ctl->cur];
     const unsigned long long rng_step = ctl->rng_step;
+    if (n < 0) n = ctl->n_own;
     double dmax2 = 0.0;
     for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
         double noise[3];
@@ -917,15 +986,29 @@ __global__ void k_skin_check(double scale, double skin, int always, DevCtl *ctl,
 // counter-based RNG.  Feeds the scalars read at src/simulation.jl:118-131.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_finalize(int nslots, const double *__restrict__ part, int ensemble, double nf, double dt, double tau,
-                           const double *__restrict__ ktemp, uint64_t seed, double *__restrict__ thermo, int advance, DevCtl *ctl)
+                           const double *__restrict__ ktemp, uint64_t seed, double *__restrict__ thermo, int advance, DevCtl *ctl,
+                           int stage)
 {
+    // stage 0: single domain.  Slabs: stage 1 leaves this rank's sums in ctl->red for the all-reduce,
+    // stage 2 continues from the globally summed ctl->red (identical on every rank).
     double r[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int q = threadIdx.x; q < nslots; q += blockDim.x) {
+    if (stage != 2) {
+        for (int q = threadIdx.x; q < nslots; q += blockDim.x) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) r[c] += part[c * kMaxPartials + q];
+            for (int c = 0; c < 4; c++) r[c] += part[c * kMaxPartials + q];
+        }
+        block_reduce<4, kStreamBlock>(r);
     }
-    block_reduce<4, kStreamBlock>(r);
+    if (threadIdx.x == 0 && stage == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) ctl->red[c] = r[c];
+        return;
+    }
     if (threadIdx.x == 0) {
+        if (stage == 2) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] = ctl->red[c];
+        }
         double U = 0.5 * r[0], W = 0.5 * r[1], NP = 0.5 * r[2];
         double KE = r[3] / 2.0;
         unsigned long long st = ctl->step;
