@@ -371,10 +371,16 @@ def main():
         e3 = md.Engine(3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank, mode=modes[args.mode],
                        skin=args.skin, use_graph=True)
 
+        parts = {}
+
         def e2e_call():
+            ta = time.perf_counter()
             e3.upload(hx[1], hd[1], velocities=hv[1], forces=hf[1], images=hi[1])
+            tb = time.perf_counter()
             th = run(e3, args.steps, thermo=True)
+            tc = time.perf_counter()
             e3.download_into(ox[1], ov[1], of_[1], oi[1])
+            parts.update(upload_s=tb - ta, run_s=tc - tb, download_s=time.perf_counter() - tc)
             return th
         e2e_call()  # warm-up: allocations, graph capture
         torch.cuda.synchronize()
@@ -384,7 +390,7 @@ def main():
         h2d = sum(a[1].nbytes for a in (hx, hv, hf, hi, hd))
         d2h = sum(a[1].nbytes for a in (ox, ov, of_, oi)) + th.nbytes
         e2e = {"value": n * args.steps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e, "breakdown_s": parts,
                "what": "mdb_upload(pinned host) + mdb_run_%s(%d steps) + mdb_download + thermo rows" % (args.ensemble, args.steps)}
         e3.close()
 

@@ -62,7 +62,9 @@ struct mdb_engine_s {
     double *part = nullptr;
     uint32_t *ovf = nullptr;  // overflow particle list (MDB_MODE_LIST)
     int nsm = 148;
-    int force_cta_per_sm = 4, stream_cta_per_sm = 4;
+    int64_t alloc_ncell = -1, alloc_cap = -1;
+    int alloc_kmax = -1, alloc_mode = -1;
+    int force_cta_per_sm = 4, stream_cta_per_sm = 4, kick_cta_per_sm = 4;
     DevCtl *ctl = nullptr;
     DevCtl *h_ctl = nullptr;  // pinned mirror
     double *d_thermo = nullptr, *d_ktemp = nullptr, *d_scratch = nullptr;
@@ -119,6 +121,7 @@ static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
 // exactly one resident wave (occupancy API), so no CTA waits for a second wave
 static inline int force_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kForceBlock), e->nsm * e->force_cta_per_sm)); }
 static inline int stream_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * e->stream_cta_per_sm)); }
+static inline int kick_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * e->kick_cta_per_sm)); }
 constexpr int kOverflowGrid = 8;
 
 template <class F>
@@ -158,6 +161,7 @@ static void free_state(Engine *e)
     e->ovf = nullptr;
     e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
     e->nl = nullptr; e->nnbr = nullptr;
+    e->alloc_ncell = -1;
 }
 
 static void free_stage(Engine *e)
@@ -288,6 +292,14 @@ static int plan_neighbors(Engine *e)
 
 static int alloc_neighbors(Engine *e)
 {
+    // re-uploads of an unchanged system (same grid, list capacity and slot capacity) keep their buffers and their graph
+    if (e->counts && e->alloc_ncell == e->ncell && e->alloc_kmax == (e->mode == MDB_MODE_LIST ? e->kmax : 0) && e->alloc_cap == e->cap &&
+        e->alloc_mode == e->mode)
+        return MDB_OK;
+    e->alloc_ncell = e->ncell;
+    e->alloc_kmax = e->mode == MDB_MODE_LIST ? e->kmax : 0;
+    e->alloc_cap = e->cap;
+    e->alloc_mode = e->mode;
     cudaFree(e->counts); cudaFree(e->start); cudaFree(e->tile_sums); cudaFree(e->nl);
     e->counts = e->start = e->tile_sums = nullptr; e->nl = nullptr;
     CU(cudaMalloc(&e->counts, sizeof(uint32_t) * (e->ncell + 1)));
@@ -443,6 +455,7 @@ static void query_occupancy(Engine *e)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_kick_drift<DIM>, kStreamBlock, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_brownian<DIM>, kStreamBlock, 0);
     e->stream_cta_per_sm = std::max(1, std::min(c, d));
+    e->kick_cta_per_sm = std::max(1, c);
     while (e->nsm * e->force_cta_per_sm + kOverflowGrid > kMaxPartials) e->force_cta_per_sm--;
 }
 
@@ -468,7 +481,7 @@ static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphCondi
 {
     if (ensemble != MDB_BROWNIAN) {
         if (prof) cudaEventRecord(e->evp[0], e->stream);
-        k_kick_drift<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl);
+        k_kick_drift<DIM><<<kick_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_skin_check(e, dt, handle, use_handle);
     } else {
@@ -861,7 +874,7 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
         for (int64_t q = 0; q < m; q++) {
             if (ensemble != MDB_BROWNIAN) {
                 for (Engine *g : G) {
-                    k_kick_drift<DIM><<<stream_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
+                    k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
                     g->stats.kernel_launches += 1;
                 }
                 if ((rc = group_force_phase<DIM, true>(G, ensemble, dt, tau, ktemp, dt, thermo ? 1 : 0, 1))) return rc;
@@ -1419,6 +1432,7 @@ MDB_EXPORT int mdb_count_pairs(mdb_handle e, double cutoff, int64_t *n_pairs, in
             e->grid.nc[k] = nc[k];
             e->grid.cinv[k] = (double)nc[k] / e->L[k];
         }
+        e->grid.nxo = nc[0];
         e->ncell = ncell;
         e->ntiles = nblk(e->ncell, kScanTile);
         e->mode = MDB_MODE_CELLS;
@@ -1490,9 +1504,81 @@ MDB_EXPORT int mdb_thermo(mdb_handle e, double out[4])
     return MDB_OK;
 }
 
-MDB_EXPORT int mdb_fire_minimize(mdb_handle e, const mdb_fire_params *, double *, int32_t *)
+template <int DIM>
+static int fire_impl(Engine *e, const mdb_fire_params *p, double *out, int32_t *converged)
 {
-    return fail(e, MDB_ERR_INVALID_ARG, "mdb_fire_minimize: not available in this build");
+    cudaStream_t s = e->stream;
+    const int n = e->n;
+    int rc;
+    // the velocity array carries the FIRE velocities during the call; the caller's velocities come back afterwards
+    if ((rc = ensure_stage(e, e->N))) return rc;
+    if (e->have_vel) {
+        k_export<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->ctl, nullptr, e->sv, nullptr, nullptr, 1);
+        e->stats.kernel_launches += 1;
+    }
+    k_zero_vel<DIM><<<stream_grid(e), kStreamBlock, 0, s>>>(n, e->ctl);
+    e->stats.kernel_launches += 1;
+    if ((rc = sync_ctl(e))) return rc;
+    double *F = e->h_ctl->fire;
+    F[0] = p->dt_initial; F[1] = p->alpha0; F[2] = 0; F[3] = 0; F[4] = 1; F[5] = 0; F[6] = 0; F[7] = 0;
+    CU(cudaMemcpyAsync(e->ctl->fire, F, sizeof(double) * 8, cudaMemcpyHostToDevice, s));
+    const double ndof = e->dim * ((double)e->N - 1.0);  // src/minimize.jl:63
+    int64_t done = 0;
+    bool conv = false;
+    while (done < p->max_steps && !conv) {
+        int64_t m = std::min<int64_t>(16, p->max_steps - done);
+        for (int64_t q = 0; q < m; q++) {
+            if ((rc = eager_prepare<DIM>(e, 1.0))) return rc;
+            enqueue_force<DIM, false>(e, 0.0);
+            enqueue_finalize(e, MDB_BROWNIAN, 0.0, 1.0, 0, 0);
+            k_fire_kick<DIM><<<stream_grid(e), kStreamBlock, 0, s>>>(n, e->ctl, e->part);
+            k_fire_decide<<<1, kStreamBlock, 0, s>>>(stream_grid(e), e->part, ndof, p->tol, p->dt_initial, p->dt_max, p->alpha0, p->f_inc,
+                                                   p->f_dec, p->n_min, e->ctl);
+            k_fire_move<DIM><<<stream_grid(e), kStreamBlock, 0, s>>>(n, e->grid, e->ctl);
+            e->stats.kernel_launches += 4 + force_kernel_count(e);
+        }
+        done += m;
+        if ((rc = sync_ctl(e))) return rc;
+        conv = e->h_ctl->fire[3] != 0.0;
+        if (e->h_ctl->nonfinite) break;
+    }
+    if (!conv) {  // src/minimize.jl:126-132: one more evaluation for the report
+        if ((rc = eager_prepare<DIM>(e, 1.0))) return rc;
+        enqueue_force<DIM, false>(e, 0.0);
+        enqueue_finalize(e, MDB_BROWNIAN, 0.0, 1.0, 0, 0);
+        e->stats.kernel_launches += 1 + force_kernel_count(e);
+        if ((rc = sync_ctl(e))) return rc;
+    }
+    if (out) {
+        out[0] = e->h_ctl->last[0];
+        out[1] = e->h_ctl->last[2];
+        out[2] = e->h_ctl->fire[7];
+    }
+    if (converged) *converged = conv ? 1 : 0;
+    if (e->have_vel) {
+        k_import_vel<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->sv, e->ctl);
+    } else {
+        k_zero_vel<DIM><<<stream_grid(e), kStreamBlock, 0, s>>>(n, e->ctl);
+    }
+    e->stats.kernel_launches += 1;
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
+    if (e->h_ctl->nonfinite) {
+        CU(cudaMemsetAsync(&e->ctl->nonfinite, 0, sizeof(int), s));
+        return fail(e, MDB_ERR_NONFINITE, "non-finite energy during FIRE: reduce dt_initial / dt_max");
+    }
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_fire_minimize(mdb_handle e, const mdb_fire_params *p, double *out, int32_t *converged)
+{
+    if (!e || !p) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    if (e->slab) return fail(e, MDB_ERR_STATE, "mdb_fire_minimize is single-domain");
+    if (p->max_steps < 0 || !(p->dt_initial > 0) || !(p->dt_max >= p->dt_initial)) return fail(e, MDB_ERR_INVALID_ARG, "bad FIRE parameters");
+    CU(cudaSetDevice(e->cfg.device));
+    return e->dim == 3 ? fire_impl<3>(e, p, out, converged) : fire_impl<2>(e, p, out, converged);
 }
 
 MDB_EXPORT int mdb_bussi_scale_from(mdb_handle e, double ke, double ktemp, double nf, double dt, double tau, double r1, double r2,

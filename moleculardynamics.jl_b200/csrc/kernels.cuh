@@ -667,7 +667,7 @@ __device__ __forceinline__ double separation_plain(const double4 &pi, const doub
 }
 
 #ifndef MDB_UNROLL
-#define MDB_UNROLL 8
+#define MDB_UNROLL 4  // tools/tune_force.py on B200: 4 -> 80 regs, 6 CTAs/SM; 8 -> 128 regs and 35% slower
 #endif
 #ifndef MDB_FORCE_MIN_CTAS
 #define MDB_FORCE_MIN_CTAS 1
@@ -1040,6 +1040,132 @@ __global__ void k_finalize(int nslots, const double *__restrict__ part, int ense
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// FIRE minimiser (src/minimize.jl:31-135), second caller of the force path.  ctl->fire = {dt, alpha, steps_since_neg,
+// converged, mix_a, mix_b, zero_v, steps_done}.  The engine's velocity array holds the FIRE velocities for the
+// duration of the call (it travels with the particle re-sorts); the caller's velocities are saved and restored.
+// ------------------------------------------------------------------------------------------------
+// v += dt*f ; partial sums of P = v.f, |v|^2, |f|^2   (src/minimize.jl:89-96)
+template <int DIM>
+__global__ void __launch_bounds__(kStreamBlock)
+k_fire_kick(int n, const DevCtl *__restrict__ ctl, double *__restrict__ part)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    const double dt = ctl->fire[0];
+    double P = 0.0, vv = 0.0, ff = 0.0;
+    for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double f = s.frc[k * s.cap + i];
+            double v = s.vel[k * s.cap + i];
+            v += dt * f;
+            s.vel[k * s.cap + i] = v;
+            P += v * f;
+            vv += v * v;
+            ff += f * f;
+        }
+    }
+    double r[3] = {P, vv, ff};
+    block_reduce<3, kStreamBlock>(r);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) part[q * kMaxPartials + blockIdx.x] = r[q];
+    }
+}
+
+// scalar logic of one FIRE iteration: convergence test, velocity mixing factors, time-step adaptation (:76-115)
+__global__ void k_fire_decide(int nslots, const double *__restrict__ part, double ndof, double tol, double dt_initial, double dt_max,
+                              double alpha0, double f_inc, double f_dec, int n_min, DevCtl *ctl)
+{
+    double r[3] = {0.0, 0.0, 0.0};
+    for (int q = threadIdx.x; q < nslots; q += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) r[c] += part[c * kMaxPartials + q];
+    }
+    block_reduce<3, kStreamBlock>(r);
+    if (threadIdx.x == 0) {
+        double *F = ctl->fire;
+        if (F[3] != 0.0) return;  // already converged: the remaining iterations of the chunk are no-ops
+        double P = r[0], v_norm = sqrt(r[1]), f_norm = sqrt(r[2]);
+        F[7] += 1.0;
+        ctl->last[2] = f_norm / sqrt(ndof);
+        if (f_norm / sqrt(ndof) < tol) {
+            F[3] = 1.0;
+            return;
+        }
+        double alpha = F[1], dt = F[0];
+        if (v_norm > 0 && f_norm > 0) {
+            F[4] = 1.0 - alpha;
+            F[5] = alpha * (v_norm / f_norm);
+        } else {
+            F[4] = 1.0;
+            F[5] = 0.0;
+        }
+        if (P > 0) {
+            F[2] += 1.0;
+            if (F[2] > (double)n_min) {
+                dt = fmin(dt * f_inc, dt_max);
+                alpha *= 0.99;
+            }
+            F[6] = 0.0;
+        } else {
+            dt = fmax(dt * f_dec, dt_initial);
+            alpha = alpha0;
+            F[2] = 0.0;
+            F[6] = 1.0;
+        }
+        F[0] = dt;
+        F[1] = alpha;
+    }
+}
+
+// v = (1-alpha) v + scale f (or 0) ; x += dt v ; wrap   (:98-123)
+template <int DIM>
+__global__ void __launch_bounds__(kStreamBlock)
+k_fire_move(int n, Grid g, DevCtl *__restrict__ ctl)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    const double *F = ctl->fire;
+    if (F[3] != 0.0) return;
+    const double dt = F[0], ma = F[4], mb = F[5];
+    const bool zero_v = F[6] != 0.0, mix = !(ma == 1.0 && mb == 0.0);
+    double dmax2 = 0.0;
+    for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
+        double4 p = ld_pos(&s.pos[i]);
+        double x[3] = {p.x, p.y, p.z};
+        double d2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double v = s.vel[k * s.cap + i];
+            if (mix) v = ma * v + mb * s.frc[k * s.cap + i];
+            if (zero_v) v = 0.0;
+            s.vel[k * s.cap + i] = v;
+            double step = dt * v;
+            d2 = (k == 0) ? step * step : d2 + step * step;
+            double xv = x[k] + step;
+            double frac = g.invL[k] * xv;
+            double ncr = floor(frac);
+            if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
+            x[k] = g.L[k] * (frac - ncr);
+        }
+        st_pos(&s.pos[i], make_double4(x[0], x[1], x[2], p.w));
+        dmax2 = fmax(dmax2, d2);
+    }
+    double r[1] = {dmax2};
+    block_reduce<1, kStreamBlock, true>(r);
+    if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
+}
+
+template <int DIM>
+__global__ void k_zero_vel(int n, const DevCtl *__restrict__ ctl)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
+#pragma unroll
+        for (int k = 0; k < DIM; k++) s.vel[k * s.cap + i] = 0.0;
+    }
+}
 
 __global__ void k_bussi_hooks(int what, double a0, double a1, double a2, double a3, double a4, double a5, double a6, uint64_t seed,
                               uint64_t step, double *out)

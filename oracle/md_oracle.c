@@ -735,3 +735,67 @@ ORC_API int orc_run_timing(int ensemble, int dim, int64_t n, double *x, double *
     free(start); free(cellof); free(order); free(xs); free(fth); free(eth);
     return (int)nsteps;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * FIRE minimiser: src/minimize.jl:31-135 fire_minimize!, statement by statement.
+ * x, img in/out.  trace (optional, [max_steps][3]) receives per step {energy, F_norm/sqrt(ndof), dt used for the move}.
+ * Returns the number of steps performed (force evaluations in the loop); *converged = 1 when the F_rms test passed.
+ * ---------------------------------------------------------------------------------------- */
+ORC_API int64_t orc_fire(int dim, int64_t n, double *x, int32_t *img, const double *diam, const double *box, double cutoff,
+                         int tag, const double *p, int64_t max_steps, double tol, double dt_initial, double dt_max,
+                         double alpha0, double f_inc, double f_dec, int n_min, double *energy_out, int *converged,
+                         double *trace)
+{
+    double alpha = alpha0;
+    int64_t steps_since_neg = 0;
+    double dt = dt_initial;
+    double *v = calloc(n * dim, sizeof(double));
+    double *f = calloc(n * dim, sizeof(double));
+    double ndof = dim * (n - 1.0);
+    double E = 0.0, W;
+    *converged = 0;
+    int64_t step;
+    for (step = 1; step <= max_steps; step++) {
+        orc_forces(dim, n, x, diam, box, cutoff, tag, p, f, &E, &W, NULL, NULL, NULL);
+        double ff = 0.0;
+        for (int64_t q = 0; q < n * dim; q++) ff += f[q] * f[q];
+        double F_norm = sqrt(ff);
+        if (trace) { trace[3 * (step - 1)] = E; trace[3 * (step - 1) + 1] = F_norm / sqrt(ndof); trace[3 * (step - 1) + 2] = 0.0; }
+        if (F_norm / sqrt(ndof) < tol) {
+            *converged = 1;
+            break;
+        }
+        for (int64_t q = 0; q < n * dim; q++) v[q] += dt * f[q];
+        double P = 0.0, vv = 0.0;
+        for (int64_t q = 0; q < n * dim; q++) { P += v[q] * f[q]; vv += v[q] * v[q]; }
+        double v_norm = sqrt(vv), f_norm = sqrt(ff);
+        if (v_norm > 0 && f_norm > 0) {
+            double scale = alpha * (v_norm / f_norm);
+            for (int64_t q = 0; q < n * dim; q++) v[q] = (1.0 - alpha) * v[q] + scale * f[q];
+        }
+        if (P > 0) {
+            steps_since_neg += 1;
+            if (steps_since_neg > n_min) {
+                dt = fmin(dt * f_inc, dt_max);
+                alpha *= 0.99;
+            }
+        } else {
+            dt = fmax(dt * f_dec, dt_initial);
+            memset(v, 0, sizeof(double) * n * dim);
+            alpha = alpha0;
+            steps_since_neg = 0;
+        }
+        if (trace) trace[3 * (step - 1) + 2] = dt;
+        for (int64_t i = 0; i < n; i++) {
+            for (int k = 0; k < dim; k++) x[i * dim + k] += dt * v[i * dim + k];
+            orc_wrap(dim, x + i * dim, img + i * dim, box);
+        }
+    }
+    if (!*converged) {
+        step = max_steps;
+        orc_forces(dim, n, x, diam, box, cutoff, tag, p, f, &E, &W, NULL, NULL, NULL);
+    }
+    *energy_out = E;
+    free(v); free(f);
+    return step;
+}

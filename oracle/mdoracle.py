@@ -60,6 +60,9 @@ def lib():
         _lib.orc_run.restype = C.c_int
         _lib.orc_run.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, C.c_double, C.c_int, _dp,
                                  C.c_double, C.c_int64, _dp, C.c_double, C.c_double, C.c_uint64, C.c_uint64, _dp]
+        _lib.orc_fire.restype = C.c_int64
+        _lib.orc_fire.argtypes = [C.c_int, C.c_int64, _dp, _ip, _dp, _dp, C.c_double, C.c_int, _dp, C.c_int64] + [C.c_double] * 6 + \
+            [C.c_int, _dp, C.POINTER(C.c_int), _dp]
         _lib.orc_threads.restype = C.c_int
         _lib.orc_run_timing.restype = C.c_int
         _lib.orc_run_timing.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, C.c_double, C.c_int,
@@ -198,3 +201,19 @@ def run_timing(ensemble, x, v, f, img, diam, box, cutoff, tag, params, dt, nstep
     if rc < 0:
         raise RuntimeError("oracle timing run failed rc=%d" % rc)
     return out
+
+
+def fire(x, img, diam, box, cutoff, tag, params, max_steps=10000, tol=1e-6, dt_initial=0.01, dt_max=0.1, alpha0=0.1, f_inc=1.2,
+         f_dec=0.2, n_min=5):
+    """fire_minimize! (src/minimize.jl:31-135) on copies; -> (x, img, energy, steps, converged, trace[steps][3])"""
+    x = np.array(x, dtype=np.float64, order="C")
+    n, dim = x.shape
+    img = np.array(img, dtype=np.int32, order="C")
+    diam = np.ascontiguousarray(diam, dtype=np.float64)
+    box = np.ascontiguousarray(box, dtype=np.float64)
+    q = _params(params)
+    e, conv = C.c_double(), C.c_int()
+    trace = np.zeros((max_steps, 3))
+    steps = lib().orc_fire(dim, n, _d(x), _i(img), _d(diam), _d(box), float(cutoff), tag, _d(q), max_steps, tol, dt_initial, dt_max,
+                           alpha0, f_inc, f_dec, n_min, C.byref(e), C.byref(conv), _d(trace))
+    return x, img, e.value, int(steps), bool(conv.value), trace[:steps]

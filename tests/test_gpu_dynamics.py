@@ -143,3 +143,28 @@ def test_momentum_and_temperature(md, orc):
     assert abs(T.mean() - 1.4737) < 0.02, T.mean()      # Bussi thermostat holds the target temperature
     assert relerr(orc.kinetic(v), t[-1, 2]) < 1e-12
     e.close()
+
+
+def test_fire_minimizer_matches_oracle(md, orc):
+    """mdb_fire_minimize vs the statement-by-statement restatement of fire_minimize! (src/minimize.jl:31-135)"""
+    from mdjl_b200 import workloads
+    p = workloads.poly2d(1200)
+    kw = dict(max_steps=150, tol=1e-6, dt_initial=1e-4, dt_max=1e-2, alpha0=0.1, f_inc=1.2, f_dec=0.2, n_min=5)
+    e = md.Engine(2, 1200, p["box"], 1.5, md._capi.POT_POLY, (1.25, 0.2), seed=1)
+    v_user = workloads.velocities(1200, 2, 0.11)
+    e.upload(p["x"], p["diam"], velocities=v_user)
+    energy, frms, steps, conv = e.fire_minimize(**kw)
+    x, v, f, img = e.download()
+    ox, oimg, oE, osteps, oconv, trace = orc.fire(p["x"], np.zeros((1200, 2), np.int32), p["diam"], p["box"], 1.5, orc.POT_POLY,
+                                                  (1.25, 0.2), **kw)
+    assert conv == oconv is False and steps == osteps == 150
+    assert relerr(energy, oE) < 1e-9 and energy < 0.2 * trace[0, 0]
+    assert np.array_equal(img, oimg) and np.max(np.abs(x - ox)) < 1e-9
+    assert np.array_equal(v, v_user)                       # the caller's velocities are untouched (the reference uses a local v)
+    # a configuration already at a force-free state converges at the first test
+    g = np.stack(np.meshgrid(np.arange(20), np.arange(20), indexing="ij"), -1).reshape(-1, 2) * 2.0 + 1.0
+    e2 = md.Engine(2, 400, 40.0, 1.5, md._capi.POT_LJ, (1.0, 1.5), seed=1)
+    e2.upload(g.astype(float), np.ones(400))
+    energy, frms, steps, conv = e2.fire_minimize()
+    assert conv and steps == 1 and energy == 0.0
+    e.close(); e2.close()
