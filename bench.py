@@ -166,6 +166,10 @@ def main_slabs(args, rank, world, local_rank):
     import mdjl_b200 as md
     from mdjl_b200 import slabs
     dev = torch.device("cuda", local_rank)
+    # NCCL prints its version banner on stdout when NCCL_DEBUG asks for it; stdout carries exactly one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=dev)
     uid = slabs.broadcast_unique_id(dist, rank, md.unique_id, device=dev)
     n = args.n
@@ -174,6 +178,11 @@ def main_slabs(args, rank, world, local_rank):
     ring = md.SlabRing.nccl(rank, world, uid, 3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank,
                             skin=args.skin)
     ring.upload(cfg["x"], cfg["diam"], velocities=v0)
+    ring.compute_forces()   # first collective: communicator warm-up (and its banner) happen here
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
 
     def run(k, thermo=False):
         if args.ensemble == "nve":

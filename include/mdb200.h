@@ -77,7 +77,9 @@ typedef struct mdb_config {
     int32_t use_graph;      /* 1: replay each step as a CUDA graph (conditional rebuild node); 0: eager launches */
     int32_t rank;           /* slab decomposition along x: this handle owns x in [rank, rank+1) * Lx / nranks */
     int32_t nranks;         /* 1 = single domain */
-    int32_t reserved[5];
+    int32_t reserved0;
+    double skin_inner;      /* skin of the inner (tight) list derived from the Verlet list; <= 0 picks a default */
+    int32_t reserved[2];
 } mdb_config;
 
 typedef struct mdb_stats {

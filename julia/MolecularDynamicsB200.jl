@@ -31,7 +31,9 @@ struct MdbConfig
     use_graph::Int32
     rank::Int32
     nranks::Int32
-    reserved::NTuple{5,Int32}
+    reserved0::Int32
+    skin_inner::Float64
+    reserved::NTuple{2,Int32}
 end
 
 const MDB_OK = Cint(0)
@@ -143,7 +145,7 @@ function to_gpu(state::SimulationState, params::Parameters; cutoff=1.5, seed=ran
     tag, pp = potential_tag(params.potential)
     cell = ntuple(q -> (r = (q - 1) ÷ 3 + 1; c = (q - 1) % 3 + 1; (r <= D && c <= D) ? Float64(U[r, c]) : 0.0), 9)
     cfg = MdbConfig(D, tag, length(state.system.xpositions), cell, cutoff, pad8(pp), seed, device, mode, skin, 1, 0, 1,
-                    ntuple(_ -> Int32(0), 5))
+                    Int32(0), 0.0, ntuple(_ -> Int32(0), 2))
     sys = GPUSystem{D}(cfg)
     upload!(sys, state.system.xpositions, state.diameters;
             velocities=isempty(state.velocities) ? nothing : state.velocities,

@@ -55,9 +55,10 @@ struct mdb_engine_s {
     StatePtrs st[2];
     uint32_t *cell_of = nullptr, *slot_of = nullptr, *counts = nullptr, *start = nullptr, *order = nullptr, *tile_sums = nullptr;
     int ntiles = 0;
-    uint32_t *nl = nullptr;
-    int32_t *nnbr = nullptr;
-    int kmax = 0;
+    uint32_t *nl = nullptr, *nl_in = nullptr;
+    int32_t *nnbr = nullptr, *nnbr_in = nullptr;
+    int kmax = 0, kmax_in = 0;
+    double skin_in = 0;
     int64_t nl_stride = 0;
     double *part = nullptr;
     uint32_t *ovf = nullptr;  // overflow particle list (MDB_MODE_LIST)
@@ -157,8 +158,8 @@ static void free_state(Engine *e)
         e->st[b] = StatePtrs{};
     }
     cudaFree(e->cell_of); cudaFree(e->slot_of); cudaFree(e->counts); cudaFree(e->start); cudaFree(e->order); cudaFree(e->tile_sums);
-    cudaFree(e->nl); cudaFree(e->nnbr); cudaFree(e->ovf);
-    e->ovf = nullptr;
+    cudaFree(e->nl); cudaFree(e->nnbr); cudaFree(e->ovf); cudaFree(e->nl_in); cudaFree(e->nnbr_in);
+    e->ovf = nullptr; e->nl_in = nullptr; e->nnbr_in = nullptr;
     e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
     e->nl = nullptr; e->nnbr = nullptr;
     e->alloc_ncell = -1;
@@ -280,6 +281,13 @@ static int plan_neighbors(Engine *e)
         int k = (int)std::ceil(expect * 1.6) + 12;
         k = (k + 3) & ~3;
         e->kmax = std::max(e->kmax, std::max(16, k));
+        // inner (tight) list: radius r_search + skin_in, re-derived from the outer list by the force kernel
+        e->skin_in = e->cfg.skin_inner > 0 ? std::min(e->cfg.skin_inner, e->skin) : 0.25 * e->skin;
+        double ri = e->r_search + e->skin_in;
+        double expect_in = (d == 3) ? rho * 4.18879020478639 * ri * ri * ri : rho * 3.14159265358979 * ri * ri;
+        int ki = (int)std::ceil(expect_in * 1.6) + 6;
+        ki = (ki + 3) & ~3;
+        e->kmax_in = std::max(e->kmax_in, std::min(e->kmax, std::max(8, ki)));
     }
     e->stats.r_search = e->r_search;
     e->stats.mode = e->mode;
@@ -293,15 +301,15 @@ static int plan_neighbors(Engine *e)
 static int alloc_neighbors(Engine *e)
 {
     // re-uploads of an unchanged system (same grid, list capacity and slot capacity) keep their buffers and their graph
-    if (e->counts && e->alloc_ncell == e->ncell && e->alloc_kmax == (e->mode == MDB_MODE_LIST ? e->kmax : 0) && e->alloc_cap == e->cap &&
-        e->alloc_mode == e->mode)
+    if (e->counts && e->alloc_ncell == e->ncell && e->alloc_kmax == (e->mode == MDB_MODE_LIST ? e->kmax + 1000 * e->kmax_in : 0) &&
+        e->alloc_cap == e->cap && e->alloc_mode == e->mode)
         return MDB_OK;
     e->alloc_ncell = e->ncell;
-    e->alloc_kmax = e->mode == MDB_MODE_LIST ? e->kmax : 0;
+    e->alloc_kmax = e->mode == MDB_MODE_LIST ? e->kmax + 1000 * e->kmax_in : 0;
     e->alloc_cap = e->cap;
     e->alloc_mode = e->mode;
-    cudaFree(e->counts); cudaFree(e->start); cudaFree(e->tile_sums); cudaFree(e->nl);
-    e->counts = e->start = e->tile_sums = nullptr; e->nl = nullptr;
+    cudaFree(e->counts); cudaFree(e->start); cudaFree(e->tile_sums); cudaFree(e->nl); cudaFree(e->nl_in);
+    e->counts = e->start = e->tile_sums = nullptr; e->nl = nullptr; e->nl_in = nullptr;
     CU(cudaMalloc(&e->counts, sizeof(uint32_t) * (e->ncell + 1)));
     CU(cudaMalloc(&e->start, sizeof(uint32_t) * (e->ncell + 1)));
     e->ntiles = nblk(e->ncell, kScanTile);
@@ -309,6 +317,7 @@ static int alloc_neighbors(Engine *e)
     if (e->mode == MDB_MODE_LIST) {
         e->nl_stride = (e->cap + 31) & ~(int64_t)31;
         CU(cudaMalloc(&e->nl, sizeof(uint32_t) * e->nl_stride * e->kmax));
+        CU(cudaMalloc(&e->nl_in, sizeof(uint32_t) * e->nl_stride * e->kmax_in));
     }
     e->stats.list_capacity = e->mode == MDB_MODE_LIST ? e->kmax : 0;
     drop_graph(e);
@@ -381,6 +390,7 @@ static int alloc_state(Engine *e, int64_t n)
     CU(cudaMalloc(&e->order, sizeof(uint32_t) * e->cap));
     CU(cudaMalloc(&e->nnbr, sizeof(int32_t) * e->cap));
     CU(cudaMalloc(&e->ovf, sizeof(uint32_t) * e->cap));
+    CU(cudaMalloc(&e->nnbr_in, sizeof(int32_t) * e->cap));
     return MDB_OK;
 }
 
@@ -411,6 +421,16 @@ static void enqueue_rebuild(Engine *e)
 }
 static int rebuild_kernel_count(const Engine *e) { return e->brute ? 0 : (e->mode == MDB_MODE_LIST ? 9 : 8); }
 
+static ListView list_view(const Engine *e)
+{
+    ListView lv;
+    lv.nl = e->nl; lv.nnbr = e->nnbr; lv.nl_in = e->nl_in; lv.nnbr_in = e->nnbr_in;
+    lv.stride = e->nl_stride; lv.kmax = e->kmax; lv.kmax_in = e->kmax_in;
+    double ri = e->r_search + e->skin_in;
+    lv.rin2 = ri * ri;
+    return lv;
+}
+
 template <int DIM, bool KICK2>
 static void enqueue_force(Engine *e, double dt)
 {
@@ -423,8 +443,8 @@ static void enqueue_force(Engine *e, double dt)
         if (e->brute)
             k_force_brute<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->cutoff2, pot, e->pp, dt, out);
         else if (e->mode == MDB_MODE_LIST) {
-            k_force_list<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->nl, e->nl_stride, e->kmax, e->nnbr,
-                                                                       e->cutoff2, e->r_grid + e->skin, pot, e->pp, dt, out);
+            k_force_list<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
+                                                                       pot, e->pp, dt, out);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
                                                                                   e->pp, dt, out, blocks);
         } else
@@ -442,8 +462,10 @@ static void query_occupancy(Engine *e)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_brute<DIM, Pot, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_brute<DIM, Pot, false>, kForceBlock, 0);
         } else if (e->mode == MDB_MODE_LIST) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, true>, kForceBlock, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, false>, kForceBlock, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, true, false>, kForceBlock, 0);
+            if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, true, true>, kForceBlock, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, false, false>, kForceBlock, 0);
+            if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, false, true>, kForceBlock, 0);
         } else {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_cells<DIM, Pot, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_cells<DIM, Pot, false>, kForceBlock, 0);
@@ -465,7 +487,7 @@ static int force_kernel_count(const Engine *e) { return (e->mode == MDB_MODE_LIS
 static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHandle handle, int use_handle)
 {
     int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
-    k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, always, e->ctl, handle, use_handle);
+    k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, e->skin_in, always, e->ctl, handle, use_handle);
 }
 
 static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance, int stage = 0)
@@ -774,8 +796,8 @@ static void enqueue_force_slab(Engine *e, double dt)
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         if (e->mode == MDB_MODE_LIST) {
-            k_force_list<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, e->nl, e->nl_stride, e->kmax, e->nnbr,
-                                                                       e->cutoff2, e->r_grid + e->skin, pot, e->pp, dt, out);
+            k_force_list<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
+                                                                       pot, e->pp, dt, out);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
                                                                                   e->pp, dt, out, blocks);
         } else {
@@ -788,7 +810,8 @@ static void enqueue_force_slab(Engine *e, double dt)
 // make every rank's ghosts and neighbour structure current, then evaluate forces and the global thermo scalars.
 // `moved_scale`: factor turning the pending displacement bound into a length (dt for |v|, 1 for |dx|).
 template <int DIM, bool KICK2>
-static int group_force_phase(Group &G, int ensemble, double dt, double tau, double ktemp, double moved_scale, int thermo, int advance)
+static int group_force_phase(Group &G, int ensemble, double dt, double tau, double ktemp, double moved_scale, int thermo, int advance,
+                             bool reduce_now = true)
 {
     int rc;
     Engine *lead = G[0];
@@ -796,7 +819,7 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
     if ((rc = group_allreduce(G, 1, true, [](Engine *e) { return (double *)&e->ctl->dmax2_bits; }))) return rc;
     for (Engine *e : G) {
         int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
-        k_skin_check<<<1, 1, 0, e->stream>>>(moved_scale, e->skin, always, e->ctl, 0, 0);
+        k_skin_check<<<1, 1, 0, e->stream>>>(moved_scale, e->skin, e->skin_in, always, e->ctl, 0, 0);
         e->stats.kernel_launches += 1;
     }
     {
@@ -813,15 +836,25 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
             k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(-1, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed, e->ctl);
             e->stats.kernel_launches += 1;
         }
-        enqueue_finalize(e, ensemble, dt, tau, 0, 0, 1);
+        if (reduce_now) enqueue_finalize(e, ensemble, dt, tau, 0, 0, 1);
+        else enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 0);  // rank-local row; the chunk is all-reduced later
         e->stats.kernel_launches += 1;
     }
+    if (!reduce_now) return MDB_OK;
     if ((rc = group_allreduce(G, 4, false, [](Engine *e) { return e->ctl->red; }))) return rc;
     for (Engine *e : G) {
         enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 2);
         e->stats.kernel_launches += 1;
     }
     return MDB_OK;
+}
+
+// NVE / Brownian: the thermo rows of a chunk were written rank-locally (halved pair sums, local KE); one all-reduce
+// over the whole chunk makes them global.  Row `m-1` also refreshes ctl->last.
+__global__ void k_last_from_row(const double *__restrict__ thermo, long long row, DevCtl *ctl)
+{
+    for (int c = 0; c < 4; c++) ctl->last[c] = thermo[4 * row + c];
+    if (!(isfinite(ctl->last[0]) && isfinite(ctl->last[2]))) ctl->nonfinite = 1;
 }
 
 static int group_check_errors(Group &G)
@@ -871,15 +904,24 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
                 CU(cudaMemcpyAsync(g->d_ktemp, ktemp_per_step + done, sizeof(double) * m, cudaMemcpyHostToDevice, g->stream));
             CU(cudaMemsetAsync(&g->ctl->step, 0, sizeof(unsigned long long), g->stream));
         }
+        // only the thermostat needs the global kinetic energy inside the step
+        const bool per_step_reduce = (ensemble == MDB_NVT);
         for (int64_t q = 0; q < m; q++) {
             if (ensemble != MDB_BROWNIAN) {
                 for (Engine *g : G) {
                     k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
                     g->stats.kernel_launches += 1;
                 }
-                if ((rc = group_force_phase<DIM, true>(G, ensemble, dt, tau, ktemp, dt, thermo ? 1 : 0, 1))) return rc;
+                if ((rc = group_force_phase<DIM, true>(G, ensemble, dt, tau, ktemp, dt, 1, 1, per_step_reduce))) return rc;
             } else {
-                if ((rc = group_force_phase<DIM, false>(G, ensemble, dt, tau, ktemp, 1.0, thermo ? 1 : 0, 1))) return rc;
+                if ((rc = group_force_phase<DIM, false>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce))) return rc;
+            }
+        }
+        if (!per_step_reduce) {
+            if ((rc = group_allreduce(G, (int)(4 * m), false, [](Engine *e) { return e->d_thermo; }))) return rc;
+            for (Engine *g : G) {
+                k_last_from_row<<<1, 1, 0, g->stream>>>(g->d_thermo, (long long)(m - 1), g->ctl);
+                g->stats.kernel_launches += 1;
             }
         }
         if (thermo) CU(cudaMemcpyAsync(thermo + 4 * done, lead->d_thermo, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
@@ -1009,9 +1051,10 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
     e->stats.kernel_launches += nsteps * step_fixed_kernels(e, ensemble) + (int64_t)nreb * rebuild_kernel_count(e);
     e->stats.max_neighbors = e->h_ctl->max_nnbr;
     e->rng_step = e->h_ctl->rng_step;
-    if (e->mode == MDB_MODE_LIST && e->h_ctl->max_nnbr > e->kmax) {
-        // correctness was kept by the cell fallback; grow the list so the fast path covers everyone next time
-        e->kmax = (e->h_ctl->max_nnbr + 4 + 3) & ~3;
+    if (e->mode == MDB_MODE_LIST && (e->h_ctl->max_nnbr > e->kmax || e->h_ctl->max_nnbr_in > e->kmax_in)) {
+        // correctness was kept by the fallbacks; grow the lists so the fast path covers everyone next time
+        if (e->h_ctl->max_nnbr > e->kmax) e->kmax = (e->h_ctl->max_nnbr + 4 + 3) & ~3;
+        if (e->h_ctl->max_nnbr_in > e->kmax_in) e->kmax_in = std::min(e->kmax, (e->h_ctl->max_nnbr_in + 2 + 3) & ~3);
         int rc = alloc_neighbors(e);
         if (rc) return rc;
         CU(cudaMemsetAsync(&e->ctl->list_valid, 0, sizeof(int), s));

@@ -61,6 +61,9 @@ struct DevCtl {
     int mig_count[2];             // migrants packed for the left / right neighbour
     int error;                    // sticky device-side error bits (see kErr*)
     double red[4];                // slab mode: local sums of U, W, n_pairs, |v|^2 awaiting the all-reduce
+    double disp_in;               // displacement bound since the inner (tight) list was last refreshed
+    int inner_refresh;            // 1: the coming force evaluation re-derives the inner list from the outer one
+    int max_nnbr_in;
     unsigned long long dmax2_bits;  // bit pattern of the largest squared displacement bound of the last move
     unsigned long long rebuilds;
     StatePtrs st[2];
@@ -670,61 +673,139 @@ __device__ __forceinline__ double separation_plain(const double4 &pi, const doub
 #define MDB_UNROLL 4  // tools/tune_force.py on B200: 4 -> 80 regs, 6 CTAs/SM; 8 -> 128 regs and 35% slower
 #endif
 #ifndef MDB_FORCE_MIN_CTAS
-#define MDB_FORCE_MIN_CTAS 1
+#define MDB_FORCE_MIN_CTAS 6  // 80 registers (a few spilled words) and 24 warps/SM beat 122 registers and 16 warps/SM by 7%
 #endif
 constexpr int kUnroll = MDB_UNROLL;  // independent neighbour gathers in flight per thread
 
-template <int DIM, class Pot, bool KICK2>
+// Two-level Verlet list + software pipelining.
+//  * outer list (radius r_search + skin): built from the cells, ~8 candidates per particle for PseudoHS at phi = 0.47;
+//  * inner list (radius r_search + skin_in, skin_in << skin): the candidates of the outer list that can come within
+//    r_search before the inner displacement budget is used up, ~2 per particle.  When ctl->inner_refresh is set this
+//    kernel walks the outer list, rewrites the inner list and evaluates forces in the same pass; otherwise it walks
+//    only the inner list.  Both are supersets of the pairs within r_search, so the pair set is identical.
+//  * the chain of dependent memory round trips per tile (own record -> indices -> neighbour records -> velocity) bounds
+//    the kernel (ncu: long-scoreboard stalls, nothing saturated): the next tile's operands and this tile's velocities
+//    are requested at the top of the tile, and index chunk c+1 is requested with the gathers of chunk c.
+struct ListView {
+    const uint32_t *nl;     // outer list, column-major [kmax][stride]
+    const int32_t *nnbr;
+    uint32_t *nl_in;        // inner list, column-major [kmax_in][stride]
+    int32_t *nnbr_in;
+    int64_t stride;
+    int kmax, kmax_in;
+    double rin2;            // (r_search + skin_in)^2
+};
+
+// SLAB: neighbour indices >= g.g0 address the ghost buffer of an x-slab (single domain: no such indices, no select)
+template <int DIM, class Pot, bool KICK2, bool SLAB>
 __global__ void __launch_bounds__(kForceBlock, MDB_FORCE_MIN_CTAS)
-k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ nl, int64_t stride,
-             int kmax, const int32_t *__restrict__ nnbr, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt, ForceOut out)
+k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt,
+             ForceOut out)
 {
     __shared__ uint32_t queue[kQueue][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
+    const bool refresh = ctl->inner_refresh != 0;  // uniform over the grid
+    const uint32_t *__restrict__ nl = refresh ? lv.nl : lv.nl_in;
+    const int32_t *__restrict__ nnbr = refresh ? lv.nnbr : lv.nnbr_in;
+    const int kcap = refresh ? lv.kmax : lv.kmax_in;
+    const int64_t stride = lv.stride;
     ThreadSums acc;
     if (n < 0) n = ctl->n_own;
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int i = tile * kForceBlock + threadIdx.x;
+    int max_in = 0;
+    // prologue: first tile's operands
+    int tile = blockIdx.x;
+    int i = tile * kForceBlock + threadIdx.x;
+    double4 pi_n = make_double4(0, 0, 0, 1);
+    int cnt_n = 0;
+    uint32_t jn[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) jn[u] = 0;
+    if (tile < ntiles && i < n) {
+        pi_n = pos[i];
+        cnt_n = nnbr[i];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)u * stride + i];  // rows < kUnroll always exist
+    }
+    for (; tile < ntiles; tile += gridDim.x) {
+        i = tile * kForceBlock + threadIdx.x;
         bool active = i < n;
-        double F[3] = {0.0, 0.0, 0.0};
-        double4 pi = make_double4(0, 0, 0, 1);
-        int nq = 0, cnt = 0;
-        bool wrap = false;
-        if (active) {
-            pi = pos[i];
-            cnt = nnbr[i];
-            if (cnt > kmax) {  // handled in full by k_force_overflow
-                active = false;
-                cnt = 0;
-            }
-            // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
-            wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
-            if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
+        const double4 pi = pi_n;
+        int cnt = cnt_n;
+        uint32_t jj[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) jj[u] = jn[u];
+        // this tile's velocities (needed only by the epilogue) and the next tile's operands: in flight during the gathers
+        double vel[3] = {0.0, 0.0, 0.0};
+        if (KICK2 && active) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) vel[k] = s.vel[k * s.cap + i];
         }
+        {
+            const int tn = tile + gridDim.x;
+            const int in = tn * kForceBlock + threadIdx.x;
+            cnt_n = 0;
+            if (tn < ntiles && in < n) {
+                pi_n = pos[in];
+                cnt_n = nnbr[in];
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)u * stride + in];
+            }
+        }
+        // which list this particle walks: normally the grid-uniform choice; a particle whose inner list overflowed
+        // keeps walking its outer list (exact either way)
+        const uint32_t *__restrict__ mynl = nl;
+        bool write_inner = refresh;
+        if (active && !refresh && cnt > kcap) {
+            mynl = lv.nl;
+            cnt = lv.nnbr[i];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) jj[u] = mynl[(int64_t)u * stride + i];
+        }
+        if (active && cnt > lv.kmax) {  // outer list overflow: handled in full by k_force_overflow
+            active = false;
+        }
+        if (!active) cnt = 0;
+        double F[3] = {0.0, 0.0, 0.0};
+        int nq = 0, nin = 0;
+        // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
+        bool wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
+        if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
         auto drain_one = [&]() {
             if (nq > 0) {
                 int j = (int)queue[--nq][threadIdx.x];
-                double4 pj = ldg_pos(nbr_ptr(g, pos, (uint32_t)j));
+                double4 pj = ldg_pos(SLAB ? nbr_ptr(g, pos, (uint32_t)j) : pos + j);
                 double dx, dy, dz;
                 double d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
         };
         for (int k0 = 0; k0 < cnt; k0 += kUnroll) {
-            uint32_t jj[kUnroll];
             double4 pj[kUnroll];
+            uint32_t jc[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; u++) jj[u] = (k0 + u < cnt) ? nl[(int64_t)(k0 + u) * stride + i] : (uint32_t)i;
+            for (int u = 0; u < kUnroll; u++) {
+                jc[u] = (k0 + u < cnt) ? jj[u] : (uint32_t)i;
+                pj[u] = ldg_pos(SLAB ? nbr_ptr(g, pos, jc[u]) : pos + jc[u]);
+            }
+            // next index chunk travels while the gathers above are in flight
+            if (k0 + kUnroll < cnt) {
 #pragma unroll
-            for (int u = 0; u < kUnroll; u++) pj[u] = ldg_pos(nbr_ptr(g, pos, jj[u]));
+                for (int u = 0; u < kUnroll; u++)
+                    jj[u] = (k0 + kUnroll + u < cnt) ? mynl[(int64_t)(k0 + kUnroll + u) * stride + i] : (uint32_t)i;
+            }
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
                 double dx, dy, dz;
                 double d2 = wrap ? separation_wrap<DIM>(g, pi, pj[u], dx, dy, dz) : separation_plain<DIM>(pi, pj[u], dx, dy, dz);
-                if (k0 + u < cnt && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
-                    if (Pot::kSparseHits) queue[nq++][threadIdx.x] = jj[u];
+                const bool valid = k0 + u < cnt;
+                if (write_inner && valid && d2 <= lv.rin2) {
+                    if (nin < lv.kmax_in) lv.nl_in[(int64_t)nin * stride + i] = jc[u];
+                    nin++;
+                }
+                if (valid && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
+                    if (Pot::kSparseHits) queue[nq++][threadIdx.x] = jc[u];
                     else pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj[u].w, F, acc.e, acc.w, acc.np);
                 }
             }
@@ -735,7 +816,30 @@ k_force_list(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__re
         if (Pot::kSparseHits) {
             while (__any_sync(0xffffffffu, nq > 0)) drain_one();
         }
-        if (active) particle_epilogue<DIM, KICK2>(i, F, s, dt, acc);
+        if (write_inner && i < n) {
+            lv.nnbr_in[i] = active ? nin : 0x7fffffff;  // outer-overflow particles never use the inner list
+            max_in = max(max_in, active ? nin : 0);
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
+            if (KICK2) {
+                double v2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; k++) {
+                    double v = vel[k];
+                    v += (F[k] * dt) * 0.5;
+                    s.vel[k * s.cap + i] = v;
+                    v2 = (k == 0) ? v * v : v2 + v * v;
+                }
+                acc.v2 += v2;
+            }
+        }
+    }
+    if (refresh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) max_in = max(max_in, __shfl_xor_sync(0xffffffffu, max_in, o));
+        if ((threadIdx.x & 31) == 0 && max_in > 0) atomicMax(&ctl->max_nnbr_in, max_in);
     }
     cta_epilogue(acc, out, blockIdx.x);
 }
@@ -924,6 +1028,7 @@ __global__ void k_flip(DevCtl *ctl, const uint32_t *__restrict__ n_new)
     ctl->mig_count[0] = ctl->mig_count[1] = 0;
     ctl->cur ^= 1;
     ctl->max_nnbr = 0;
+    ctl->max_nnbr_in = 0;
     ctl->n_overflow = 0;
     ctl->rebuilds += 1;
 }
@@ -968,15 +1073,23 @@ k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, 
 // rebuilt before the coming force evaluation, and drive the conditional graph node.
 // dmax2 holds max |v|^2 (scale = dt) or max |dx|^2 (scale = 1).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_skin_check(double scale, double skin, int always, DevCtl *ctl, cudaGraphConditionalHandle handle, int use_handle)
+__global__ void k_skin_check(double scale, double skin, double skin_in, int always, DevCtl *ctl, cudaGraphConditionalHandle handle,
+                             int use_handle)
 {
     double m = __longlong_as_double((long long)ctl->dmax2_bits);
     ctl->dmax2_bits = 0ull;  // consumed
-    double disp = ctl->disp + sqrt(m) * scale;
+    double step = sqrt(m) * scale;
+    double disp = ctl->disp + step;
     // NaN-safe: a non-finite bound forces a rebuild
     int need = always || !ctl->list_valid || !(2.0 * disp <= skin);
     ctl->disp = need ? 0.0 : disp;
     ctl->need_rebuild = need;
+    // two-level Verlet list: the tight inner list (r_search + skin_in) is re-derived from the outer one by the force
+    // kernel itself whenever its own, smaller, displacement budget is used up
+    double disp_in = ctl->disp_in + step;
+    int need_in = need || !(2.0 * disp_in <= skin_in);
+    ctl->disp_in = need_in ? 0.0 : disp_in;
+    ctl->inner_refresh = need_in;
     if (use_handle) cudaGraphSetConditional(handle, need ? 1u : 0u);
 }
 

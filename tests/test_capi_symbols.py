@@ -30,7 +30,7 @@ def test_header_matches_binding_and_library(md):
 
 def test_struct_layouts_match_header(md):
     import ctypes as C
-    assert C.sizeof(md._capi.Config) == 4 + 4 + 8 + 72 + 8 + 64 + 8 + 4 + 4 + 8 + 4 + 4 + 4 + 20
+    assert C.sizeof(md._capi.Config) == 4 + 4 + 8 + 72 + 8 + 64 + 8 + 4 + 4 + 8 + 4 + 4 + 4 + 4 + 8 + 8
     assert C.sizeof(md._capi.FireParams) == 8 + 6 * 8 + 8
 
 
