@@ -42,6 +42,18 @@ BYTES_FORCE_KERNEL_3D = 104.0
 BYTES_KICK_KERNEL_3D = 144.0
 
 
+def measured_traffic(kernel, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    capture (profiles/r01_traffic.json), scaled by particle count when the run is not at the captured size"""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as fh:
+            t = json.load(fh)[kernel]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["n_particles"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -276,7 +288,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1 << 24)
-    ap.add_argument("--melt", type=int, default=600)
+    ap.add_argument("--melt", type=int, default=1500)
     ap.add_argument("--mode", default="auto", choices=["auto", "cells", "list"])
     ap.add_argument("--skin", type=float, default=0.0)
     ap.add_argument("--ensemble", default="nve", choices=["nve", "nvt", "brownian"])
@@ -360,7 +372,9 @@ def main():
         else:
             name, dur, bts = "k_kick_drift", kick, BYTES_KICK_KERNEL_3D
         achieved = bts * n / (dur * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+        traffic = measured_traffic("k_kick_drift" if name == "k_kick_drift" else "k_force_list", n)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                    "traffic_source": "ncu --set full capture in profiles/ (dram read+write per launch)",
                     "kernel": name, "kernel_ms": dur, "algorithmic_bytes_per_particle": bts, "peak_source": peak_src}
     step_gbs = BYTES_STEP_3D * n * args.steps / (ms * 1e-3) / 1e9
 

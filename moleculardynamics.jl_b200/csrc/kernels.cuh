@@ -777,7 +777,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 int j = (int)queue[--nq][threadIdx.x];
                 double4 pj = ldg_pos(SLAB ? nbr_ptr(g, pos, (uint32_t)j) : pos + j);
                 double dx, dy, dz;
-                double d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
+                double d2 = wrap ? separation_wrap<DIM>(g, pi, pj, dx, dy, dz) : separation_plain<DIM>(pi, pj, dx, dy, dz);
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
         };
