@@ -173,8 +173,11 @@ int mdb_set_rng_step(mdb_handle h, uint64_t step);
 /* ---- user-defined Potential (src/types.jl:1-6 plugin contract) on the device, compiled with NVRTC --------- */
 /* `body` is the CUDA-C body of
  *   __device__ bool evaluate(double r, double sigma1, double sigma2, const double* p, double& u, double& f)
- * returning true when the pair interacts.  `range` = largest r at which it can return true. Must be called before
- * mdb_upload; sets cfg.potential = MDB_POT_USER. */
+ * returning true when the pair interacts (false with u = f = 0 otherwise).  params fills p[0..6] (n_params <= 7);
+ * `range` = largest r at which it can return true.  The body is compiled with NVRTC (sm_100a, -fmad=false) into the same
+ * kernel templates the built-in potentials use (kernels.cuh next to the library).  A comment containing MDB_DENSE_HITS
+ * selects in-line evaluation instead of the deferred-hit queue (for potentials where most pairs in range interact).
+ * Must be called before mdb_upload; sets cfg.potential = MDB_POT_USER.  Compile errors: MDB_ERR_NVRTC + compiler log. */
 int mdb_set_user_potential(mdb_handle h, const char *body, const double *params, int32_t n_params, double range);
 
 /* ---- multi-GPU slabs (new; the reference is single-process) --------------------------------------------- */

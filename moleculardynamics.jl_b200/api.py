@@ -78,6 +78,24 @@ class Polydisperse(Potential):
         return (self.rcut, self.non_additivity)
 
 
+class UserPotential(Potential):
+    """User-defined interaction compiled for the device with NVRTC -- the open plugin contract of the reference
+    (struct MyPot <: Potential + evaluate(::MyPot, r, sigma1, sigma2), src/types.jl:1-6, README.md:68-145).
+
+    `body` is the CUDA-C body of
+        __device__ bool evaluate(double r, double sigma1, double sigma2, const double* p, double& u, double& f)
+    returning true when the pair interacts (false with u = f = 0 otherwise); `params` fills p[0..6]; `range` is the
+    largest r at which it can return true.  Put the token MDB_DENSE_HITS in a comment of the body when most pairs within
+    the range interact (e.g. Lennard-Jones): hits are then evaluated in line instead of through the deferred queue."""
+    tag = _capi.POT_USER
+
+    def __init__(self, body, params=(), range=1.0):
+        self.body, self._params, self.range = str(body), tuple(float(v) for v in params), float(range)
+
+    def params(self):
+        return self._params
+
+
 def energy_lrc(pot, n, volume):
     """src/potentials.jl:111-117,136-141,256-260,281-305: total long-range energy correction (0 unless enabled)."""
     rho = n / volume
@@ -384,8 +402,12 @@ def initialize_state(params, pathname, from_file="", dimension=3, random_init=Fa
     modes = {"auto": _capi.MODE_AUTO, "cells": _capi.MODE_CELLS, "list": _capi.MODE_LIST}
     if seed is None:
         seed = int(rng.integers(0, 2 ** 63 - 1))
-    engine = _capi.Engine(dimension, n_particles, np.diag(unitcell), float(cutoff), pot.tag, pot.params(), seed=seed,
-                          device=device, mode=modes[mode], skin=skin or 0.0, use_graph=use_graph)
+    user = isinstance(pot, UserPotential)
+    engine = _capi.Engine(dimension, n_particles, np.diag(unitcell), float(cutoff), _capi.POT_PSEUDOHS if user else pot.tag,
+                          () if user else pot.params(), seed=seed, device=device, mode=modes[mode], skin=skin or 0.0,
+                          use_graph=use_graph)
+    if user:
+        engine.set_user_potential(pot.body, pot.params(), pot.range)
     engine.upload(positions, diameters)
     system = GPUSystem(engine, cutoff)
     state = SimulationState(system, diameters, rng, unitcell, dimension, nf)

@@ -16,6 +16,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvrtc.h>
 
 using namespace mdb;
 
@@ -99,6 +100,12 @@ struct mdb_engine_s {
     std::vector<mdb_engine_s *> *group = nullptr;  // in-process ring, shared by its members; [0] drives it
     bool stream_owned = true;
     ncclComm_t comm = nullptr;
+
+    // ---- user-defined Potential compiled with NVRTC (mdb_set_user_potential) -----------------------
+    cudaLibrary_t user_lib = nullptr;
+    cudaKernel_t user_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [KICK2][SLAB]
+    cudaKernel_t user_overflow[2] = {nullptr, nullptr}, user_cells[2] = {nullptr, nullptr}, user_brute[2] = {nullptr, nullptr};
+    double user_range = 0;
 };
 
 typedef mdb_engine_s Engine;
@@ -144,6 +151,7 @@ static double pot_range(const Engine *e)
     case MDB_POT_LJ: return PotLJ::range(e->pp, e->smin, e->smax);
     case MDB_POT_LJ_XPLOR: return PotXPLOR::range(e->pp, e->smin, e->smax);
     case MDB_POT_POLY: return PotPoly::range(e->pp, e->smin, e->smax);
+    case MDB_POT_USER: return e->user_range;
     }
     return e->cfg.cutoff;
 }
@@ -431,6 +439,35 @@ static ListView list_view(const Engine *e)
     return lv;
 }
 
+// kernels of a user-defined Potential live in an NVRTC-built library; same signatures as the templates in kernels.cuh
+static void launch_user_force(Engine *e, int n, int kick2, bool slab, double dt, int blocks)
+{
+    cudaStream_t s = e->stream;
+    ForceOut out{e->part};
+    char pot = 0;  // the functor is an empty struct: one byte of kernel parameter space
+    DevCtl *ctl = e->ctl;
+    const DevCtl *cctl = e->ctl;
+    Grid g = e->grid;
+    double cutoff2 = e->cutoff2;
+    PotParams pp = e->pp;
+    const uint32_t *start = e->start, *ovf = e->ovf;
+    if (e->brute) {
+        void *args[] = {&n, &cctl, &g, &cutoff2, &pot, &pp, &dt, &out};
+        cudaLaunchKernel((const void *)e->user_brute[kick2], dim3(blocks), dim3(kForceBlock), args, 0, s);
+    } else if (e->mode == MDB_MODE_LIST) {
+        ListView lv = list_view(e);
+        double rwrap = e->r_grid + e->skin;
+        void *args[] = {&n, &ctl, &g, &lv, &cutoff2, &rwrap, &pot, &pp, &dt, &out};
+        cudaLaunchKernel((const void *)e->user_list[kick2][slab ? 1 : 0], dim3(blocks), dim3(kForceBlock), args, 0, s);
+        int slot0 = blocks;
+        void *args2[] = {&cctl, &g, &start, &ovf, &cutoff2, &pot, &pp, &dt, &out, &slot0};
+        cudaLaunchKernel((const void *)e->user_overflow[kick2], dim3(kOverflowGrid), dim3(kForceBlock), args2, 0, s);
+    } else {
+        void *args[] = {&n, &cctl, &g, &start, &cutoff2, &pot, &pp, &dt, &out};
+        cudaLaunchKernel((const void *)e->user_cells[kick2], dim3(blocks), dim3(kForceBlock), args, 0, s);
+    }
+}
+
 template <int DIM, bool KICK2>
 static void enqueue_force(Engine *e, double dt)
 {
@@ -438,6 +475,10 @@ static void enqueue_force(Engine *e, double dt)
     const int n = e->n;
     ForceOut out{e->part};
     int blocks = force_grid(e);
+    if (e->cfg.potential == MDB_POT_USER) {
+        launch_user_force(e, n, KICK2 ? 1 : 0, false, dt, blocks);
+        return;
+    }
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         if (e->brute)
@@ -455,6 +496,15 @@ template <int DIM>
 static void query_occupancy(Engine *e)
 {
     int best = 32;
+    if (e->cfg.potential == MDB_POT_USER) {
+        int a = 0, b = 0;
+        cudaKernel_t k0 = e->brute ? e->user_brute[0] : (e->mode == MDB_MODE_LIST ? e->user_list[0][e->slab ? 1 : 0] : e->user_cells[0]);
+        cudaKernel_t k1 = e->brute ? e->user_brute[1] : (e->mode == MDB_MODE_LIST ? e->user_list[1][e->slab ? 1 : 0] : e->user_cells[1]);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, (const void *)k0, kForceBlock, 0) != cudaSuccess) a = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, (const void *)k1, kForceBlock, 0) != cudaSuccess) b = 4;
+        cudaGetLastError();
+        best = std::max(1, std::min(a, b));
+    }
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         int a = 0, b = 0;
@@ -793,6 +843,11 @@ static void enqueue_force_slab(Engine *e, double dt)
     cudaStream_t s = e->stream;
     ForceOut out{e->part};
     int blocks = force_grid(e);
+    if (e->cfg.potential == MDB_POT_USER) {
+        launch_user_force(e, -1, KICK2 ? 1 : 0, true, dt, blocks);
+        e->stats.kernel_launches += force_kernel_count(e);
+        return;
+    }
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         if (e->mode == MDB_MODE_LIST) {
@@ -1158,6 +1213,7 @@ MDB_EXPORT int mdb_destroy(mdb_handle e)
     free_state(e);
     free_stage(e);
     free_slab(e);
+    if (e->user_lib) cudaLibraryUnload(e->user_lib);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->group) {
         // the ring is shared: detach this member; the last one out frees it
@@ -1670,9 +1726,139 @@ MDB_EXPORT int mdb_set_rng_step(mdb_handle e, uint64_t step)
     return MDB_OK;
 }
 
-MDB_EXPORT int mdb_set_user_potential(mdb_handle e, const char *, const double *, int32_t, double)
+struct NvrtcApi {
+    void *lib = nullptr;
+    decltype(&nvrtcCreateProgram) CreateProgram = nullptr;
+    decltype(&nvrtcDestroyProgram) DestroyProgram = nullptr;
+    decltype(&nvrtcCompileProgram) CompileProgram = nullptr;
+    decltype(&nvrtcGetProgramLogSize) GetProgramLogSize = nullptr;
+    decltype(&nvrtcGetProgramLog) GetProgramLog = nullptr;
+    decltype(&nvrtcGetCUBINSize) GetCUBINSize = nullptr;
+    decltype(&nvrtcGetCUBIN) GetCUBIN = nullptr;
+    decltype(&nvrtcAddNameExpression) AddNameExpression = nullptr;
+    decltype(&nvrtcGetLoweredName) GetLoweredName = nullptr;
+    decltype(&nvrtcGetErrorString) GetErrorString = nullptr;
+};
+static NvrtcApi g_rtc;
+
+static bool load_nvrtc(std::string &why)
 {
-    return fail(e, MDB_ERR_NVRTC, "mdb_set_user_potential: not available in this build");
+    if (g_rtc.lib) return true;
+    // the toolkit's NVRTC first: a host process may already hold an older libnvrtc.so.12 (e.g. the one PyTorch bundles)
+    const char *names[] = {getenv("MDB200_NVRTC"), "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so"};
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        g_rtc.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (g_rtc.lib) break;
+    }
+    if (!g_rtc.lib) {
+        why = std::string("dlopen(libnvrtc.so.12) failed: ") + dlerror();
+        return false;
+    }
+#define LOADSYM(field, name)                                        \
+    g_rtc.field = (decltype(g_rtc.field))dlsym(g_rtc.lib, name);   \
+    if (!g_rtc.field) {                                             \
+        why = std::string("missing NVRTC symbol ") + name;          \
+        return false;                                               \
+    }
+    LOADSYM(CreateProgram, "nvrtcCreateProgram")
+    LOADSYM(DestroyProgram, "nvrtcDestroyProgram")
+    LOADSYM(CompileProgram, "nvrtcCompileProgram")
+    LOADSYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    LOADSYM(GetProgramLog, "nvrtcGetProgramLog")
+    LOADSYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    LOADSYM(GetCUBIN, "nvrtcGetCUBIN")
+    LOADSYM(AddNameExpression, "nvrtcAddNameExpression")
+    LOADSYM(GetLoweredName, "nvrtcGetLoweredName")
+    LOADSYM(GetErrorString, "nvrtcGetErrorString")
+#undef LOADSYM
+    return true;
+}
+
+// The open plugin contract of the reference (struct MyPot <: Potential + evaluate(::MyPot, r, sigma1, sigma2),
+// src/types.jl:1-6, README.md:68-145) on the device: the user's `evaluate` body becomes the eval() of a functor that the
+// SAME kernel templates (kernels.cuh, read from the directory of this library) are instantiated with by NVRTC.
+MDB_EXPORT int mdb_set_user_potential(mdb_handle e, const char *body, const double *params, int32_t n_params, double range)
+{
+    if (!e || !body) return MDB_ERR_INVALID_ARG;
+    if (e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_set_user_potential must be called before mdb_upload");
+    if (n_params < 0 || n_params > 7 || (n_params > 0 && !params)) return fail(e, MDB_ERR_INVALID_ARG, "at most 7 parameters (p[7] is reserved)");
+    if (!(range > 0)) return fail(e, MDB_ERR_INVALID_ARG, "range must be > 0");
+    std::string why;
+    if (!load_nvrtc(why)) return fail(e, MDB_ERR_NVRTC, why);
+    CU(cudaSetDevice(e->cfg.device));
+    Dl_info info;
+    if (!dladdr((void *)&mdb_version, &info) || !info.dli_fname) return fail(e, MDB_ERR_NVRTC, "cannot locate libmdb200.so on disk");
+    std::string dir(info.dli_fname);
+    size_t slash = dir.find_last_of('/');
+    dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+    const bool dense = strstr(body, "MDB_DENSE_HITS") != nullptr;
+    std::string src;
+    src += "#include \"kernels.cuh\"\nnamespace mdb {\nstruct PotUser {\n";
+    src += std::string("    static constexpr bool kSparseHits = ") + (dense ? "false" : "true") + ";\n";
+    src += "    __device__ __forceinline__ bool eval(const PotParams &P, double r, double sigma1, double sigma2, double &u, double &f) const\n"
+           "    {\n        const double *p = P.p;\n#line 1 \"user_potential\"\n";
+    src += body;
+    src += "\n    }\n"
+           "    __device__ __forceinline__ bool may_interact(const PotParams &P, double d2, double, double) const { return d2 < P.p[7]; }\n"
+           "};\n}\n";
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = g_rtc.CreateProgram(&prog, src.c_str(), "mdb_user_potential.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return fail(e, MDB_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + g_rtc.GetErrorString(r));
+    const std::string D = std::to_string(e->dim);
+    std::vector<std::string> names;
+    for (int k = 0; k < 2; k++) {
+        std::string kk = k ? "true" : "false";
+        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + kk + ", false>");
+        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + kk + ", true>");
+        names.push_back("mdb::k_force_overflow<" + D + ", mdb::PotUser, " + kk + ">");
+        names.push_back("mdb::k_force_cells<" + D + ", mdb::PotUser, " + kk + ">");
+        names.push_back("mdb::k_force_brute<" + D + ", mdb::PotUser, " + kk + ">");
+    }
+    for (auto &nm : names) g_rtc.AddNameExpression(prog, nm.c_str());
+    std::string inc = "-I" + dir;
+    const char *opts[] = {"-arch=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", inc.c_str()};
+    r = g_rtc.CompileProgram(prog, 5, opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        g_rtc.GetProgramLogSize(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) g_rtc.GetProgramLog(prog, &log[0]);
+        g_rtc.DestroyProgram(&prog);
+        return fail(e, MDB_ERR_NVRTC, std::string("user potential does not compile (") + g_rtc.GetErrorString(r) + "):\n" + log);
+    }
+    size_t cs = 0;
+    g_rtc.GetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    g_rtc.GetCUBIN(prog, cubin.data());
+    if (e->user_lib) {
+        cudaLibraryUnload(e->user_lib);
+        e->user_lib = nullptr;
+    }
+    cudaError_t ce = cudaLibraryLoadData(&e->user_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (ce != cudaSuccess) {
+        g_rtc.DestroyProgram(&prog);
+        return fail(e, MDB_ERR_NVRTC, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(ce));
+    }
+    auto get = [&](const std::string &nm, cudaKernel_t *out) -> bool {
+        const char *low = nullptr;
+        if (g_rtc.GetLoweredName(prog, nm.c_str(), &low) != NVRTC_SUCCESS || !low) return false;
+        return cudaLibraryGetKernel(out, e->user_lib, low) == cudaSuccess;
+    };
+    bool ok = true;
+    for (int k = 0; k < 2; k++) {
+        ok = ok && get(names[5 * k + 0], &e->user_list[k][0]) && get(names[5 * k + 1], &e->user_list[k][1]) &&
+             get(names[5 * k + 2], &e->user_overflow[k]) && get(names[5 * k + 3], &e->user_cells[k]) && get(names[5 * k + 4], &e->user_brute[k]);
+    }
+    g_rtc.DestroyProgram(&prog);
+    if (!ok) return fail(e, MDB_ERR_NVRTC, "could not resolve the compiled kernels");
+    memset(e->pp.p, 0, sizeof(e->pp.p));
+    for (int q = 0; q < n_params; q++) e->pp.p[q] = params[q];
+    e->pp.p[7] = range * range * (1.0 + 1e-15);  // conservative squared range for the d2 pre-test
+    e->user_range = range;
+    e->cfg.potential = MDB_POT_USER;
+    drop_graph(e);
+    return MDB_OK;
 }
 
 MDB_EXPORT int mdb_comm_unique_id(char *id)

@@ -6,11 +6,13 @@
 //   img   int32[3][cap]  periodic image counters, id int32[cap] original particle index
 // Reference functions replaced are cited per kernel (paths relative to /root/reference).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
-#include "potentials.cuh"
 #include "rng.cuh"
+#include "potentials.cuh"
 
 namespace mdb {
 
@@ -108,22 +110,44 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV])
     }
 }
 
-// one 256-bit transaction per particle record (LDG.E.256 / STG.E.256 on sm_100a); pos is 32-byte aligned
+// one 256-bit transaction per particle record (LDG.E.256 / STG.E.256 on sm_100a); pos is 32-byte aligned.
+// 256-bit vector accesses need PTX ISA 8.8 (CUDA 12.9); an older NVRTC (user potentials compiled inside a process that
+// already loaded a 12.8 runtime) falls back to two 128-bit accesses.
+#if defined(__CUDACC_RTC__) && defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ < 1209)
+#define MDB_VEC256 0
+#else
+#define MDB_VEC256 1
+#endif
 __device__ __forceinline__ double4 ldg_pos(const double4 *p)
 {
     double4 r;
+#if MDB_VEC256
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+#else
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2+16];" : "=d"(r.z), "=d"(r.w) : "l"(p));
+#endif
     return r;
 }
 __device__ __forceinline__ double4 ld_pos(const double4 *p)
 {
     double4 r;
+#if MDB_VEC256
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+#else
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2+16];" : "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+#endif
     return r;
 }
 __device__ __forceinline__ void st_pos(double4 *p, const double4 &v)
 {
+#if MDB_VEC256
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+#else
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    asm volatile("st.global.v2.f64 [%0+16], {%1,%2};" ::"l"(p), "d"(v.z), "d"(v.w) : "memory");
+#endif
 }
 
 __device__ __forceinline__ int cell_coord(double x, double cinv, int nc)
@@ -1068,6 +1092,7 @@ k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, 
     if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
 }
 
+#ifndef __CUDACC_RTC__
 // ------------------------------------------------------------------------------------------------
 // K-skin: consume the displacement bound of the move that just happened, decide whether the Verlet list must be
 // rebuilt before the coming force evaluation, and drive the conditional graph node.
@@ -1092,6 +1117,8 @@ __global__ void k_skin_check(double scale, double skin, double skin_in, int alwa
     ctl->inner_refresh = need_in;
     if (use_handle) cudaGraphSetConditional(handle, need ? 1u : 0u);
 }
+
+#endif  // !__CUDACC_RTC__
 
 // ------------------------------------------------------------------------------------------------
 // K9  thermo: fixed-order second stage of the per-CTA partials (deterministic), kinetic energy / temperature

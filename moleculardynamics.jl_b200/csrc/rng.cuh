@@ -3,8 +3,15 @@
 // src/integrate.jl:55-59) as north_star prescribes.  Stream layout is specified in oracle/md_oracle.c
 // ("Counter-based RNG") and is identical on both sides.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
 #include <cuda_runtime.h>
+#else
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#endif
 
 namespace mdb {
 

@@ -180,3 +180,70 @@ def test_error_paths(md):
     with pytest.raises(md.MdbError) as ei:  # velocities never set
         e2.run_nve(1, 1e-3)
     assert ei.value.code == _capi.ERR_STATE
+
+
+LJ_BODY = """// MDB_DENSE_HITS -- same statements as lj_unshifted (src/potentials.jl:66-77)
+double epsilon = p[0], r_cut = p[1];
+double sigma = (sigma1 + sigma2) / 2.0;
+if (r >= r_cut) { u = 0.0; f = 0.0; return false; }
+double sr = sigma / r; double sr2 = sr * sr; double sr6 = (sr2 * sr2) * sr2; double sr12 = sr6 * sr6;
+u = 4.0 * epsilon * (sr12 - sr6);
+f = 24.0 * epsilon * (2.0 * sr12 - sr6) / r;
+return true;"""
+
+HARMONIC_BODY = """double s = 0.5 * (sigma1 + sigma2);
+if (r >= s) { u = 0.0; f = 0.0; return false; }
+double x = 1.0 - r / s;
+u = 0.5 * p[0] * x * x;
+f = p[0] * x / s;
+return true;"""
+
+
+def test_user_potential_nvrtc(md, orc):
+    """the open plugin contract on the device: a user `evaluate` body compiled with NVRTC into the same kernel templates"""
+    from mdjl_b200 import workloads
+    cfg = workloads.lj_fluid(4096, rho=0.8, dim=3)
+    cfg = _melt(md, cfg, 3, orc.POT_LJ, (1.0, 2.5), 2.5, 1.2, 2e-3, 400)
+    # (1) user code restating Lennard-Jones must reproduce the built-in functor bit for bit, in both neighbour modes
+    for mode in ("cells", "list"):
+        ref = _engine(md, cfg, 3, 2.5, orc.POT_LJ, (1.0, 2.5), mode)
+        E0, W0, n0 = ref.compute_forces()
+        F0 = ref.download()[2]
+        ref.close()
+        modes = {"cells": md._capi.MODE_CELLS, "list": md._capi.MODE_LIST}
+        e = md.Engine(3, 4096, cfg["box"], 2.5, 0, seed=7, mode=modes[mode])
+        e.set_user_potential(LJ_BODY, (1.0, 2.5), 2.5)
+        e.upload(cfg["x"], cfg["diam"])
+        E, W, n = e.compute_forces()
+        assert (E, W, n) == (E0, W0, n0) and np.array_equal(e.download()[2], F0)
+        e.close()
+    # (2) a potential the library does not ship: harmonic repulsion, against a direct O(N^2) numpy sum
+    rng = np.random.default_rng(4)
+    n, L, k = 1500, 12.0, 30.0
+    x = rng.uniform(0, L, (n, 3))
+    diam = rng.uniform(0.8, 1.2, n)
+    e = md.Engine(3, n, L, 1.5, 0, seed=7)
+    e.set_user_potential(HARMONIC_BODY, (k,), 1.2)
+    e.upload(x, diam, velocities=np.zeros((n, 3)))
+    E, W, npairs = e.compute_forces()
+    F = e.download()[2]
+    d = x[:, None, :] - x[None, :, :]
+    d -= L * np.rint(d / L)
+    r = np.sqrt((d * d).sum(-1))
+    s = 0.5 * (diam[:, None] + diam[None, :])
+    m = (r < s) & (r > 0)
+    xx = np.where(m, 1.0 - r / np.where(m, s, 1.0), 0.0)
+    Eref = 0.25 * k * (xx * xx).sum()
+    fmag = np.where(m, k * xx / s, 0.0)
+    Fref = ((fmag / np.where(m, r, 1.0))[:, :, None] * d).sum(axis=1)
+    assert npairs == int(m.sum()) // 2 and relerr(E, Eref) < 1e-12 and force_error(F, Fref) < 1e-12
+    t = e.run_nve(200, 2e-3)          # soft spheres relax: potential energy converts to kinetic, total is conserved
+    Et = t[:, 0] + t[:, 2]
+    assert abs(Et[-1] - Et[0]) < 2e-3 * abs(Et[0]) and t[-1, 2] > 0
+    e.close()
+    # (3) code that does not compile is reported with the compiler log
+    e = md.Engine(3, 10, 10.0, 1.5, 0)
+    with pytest.raises(md.MdbError) as ei:
+        e.set_user_potential("u = nonsense; return true;", (), 1.0)
+    assert ei.value.code == md._capi.ERR_NVRTC and "nonsense" in str(ei.value)
+    e.close()
