@@ -60,7 +60,9 @@ enum mdb_ensemble { MDB_NVE = 0, MDB_NVT = 1, MDB_BROWNIAN = 2 };
 enum mdb_mode {
     MDB_MODE_AUTO = 0,
     MDB_MODE_CELLS = 1, /* cell list rebuilt and particles re-sorted EVERY step (the reference's shape, src/simulation.jl:100) */
-    MDB_MODE_LIST = 2   /* Verlet list with skin, rebuilt from the cell list when the displacement bound is reached */
+    MDB_MODE_LIST = 2,  /* Verlet list with skin, rebuilt from the cell list when the displacement bound is reached */
+    MDB_MODE_SMALL = 3  /* n <= 4096: the whole step loop runs inside one persistent CTA, thousands of steps per launch
+                           (MDB_MODE_AUTO picks it for such systems; other entry points keep using cells / list) */
 };
 
 typedef struct mdb_config {

@@ -17,7 +17,7 @@ STATUS_NAMES = {0: "MDB_OK", 1: "MDB_ERR_INVALID_ARG", 2: "MDB_ERR_CUDA", 3: "MD
                 8: "MDB_ERR_STATE", 9: "MDB_ERR_NONFINITE", 10: "MDB_ERR_NVRTC"}
 POT_PSEUDOHS, POT_LJ, POT_LJ_XPLOR, POT_POLY, POT_USER = 0, 1, 2, 3, 100
 NVE, NVT, BROWNIAN = 0, 1, 2
-MODE_AUTO, MODE_CELLS, MODE_LIST = 0, 1, 2
+MODE_AUTO, MODE_CELLS, MODE_LIST, MODE_SMALL = 0, 1, 2, 3
 
 # every symbol include/mdb200.h declares (tests/test_capi_symbols.py checks the header against this list and the .so)
 SYMBOLS = [

@@ -399,7 +399,7 @@ def initialize_state(params, pathname, from_file="", dimension=3, random_init=Fa
     if pot.tag is None:
         # no device functor: mirror the reference's `error("evaluate not implemented ...")` (src/types.jl:4-6)
         evaluate(pot, 1.0)
-    modes = {"auto": _capi.MODE_AUTO, "cells": _capi.MODE_CELLS, "list": _capi.MODE_LIST}
+    modes = {"auto": _capi.MODE_AUTO, "cells": _capi.MODE_CELLS, "list": _capi.MODE_LIST, "small": _capi.MODE_SMALL}
     if seed is None:
         seed = int(rng.integers(0, 2 ** 63 - 1))
     user = isinstance(pot, UserPotential)

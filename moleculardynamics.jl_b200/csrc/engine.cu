@@ -13,6 +13,7 @@
 #include "../../include/mdb200.h"
 #include "kernels.cuh"
 #include "slab.cuh"
+#include "small.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -106,6 +107,14 @@ struct mdb_engine_s {
     cudaKernel_t user_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [KICK2][SLAB]
     cudaKernel_t user_overflow[2] = {nullptr, nullptr}, user_cells[2] = {nullptr, nullptr}, user_brute[2] = {nullptr, nullptr};
     double user_range = 0;
+
+    // ---- K0-small: persistent single-CTA step loop for n <= kSmallMaxN ------------------------------
+    bool small = false;
+    uint32_t *small_nl = nullptr;
+    int32_t *small_nnbr = nullptr;
+    double *small_part = nullptr;
+    int small_kmax = 0;
+    double small_skin = 0;
 };
 
 typedef mdb_engine_s Engine;
@@ -167,7 +176,9 @@ static void free_state(Engine *e)
     }
     cudaFree(e->cell_of); cudaFree(e->slot_of); cudaFree(e->counts); cudaFree(e->start); cudaFree(e->order); cudaFree(e->tile_sums);
     cudaFree(e->nl); cudaFree(e->nnbr); cudaFree(e->ovf); cudaFree(e->nl_in); cudaFree(e->nnbr_in);
-    e->ovf = nullptr; e->nl_in = nullptr; e->nnbr_in = nullptr;
+    cudaFree(e->small_nl); cudaFree(e->small_nnbr); cudaFree(e->small_part);
+    e->small_part = nullptr;
+    e->ovf = nullptr; e->nl_in = nullptr; e->nnbr_in = nullptr; e->small_nl = nullptr; e->small_nnbr = nullptr;
     e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
     e->nl = nullptr; e->nnbr = nullptr;
     e->alloc_ncell = -1;
@@ -297,8 +308,21 @@ static int plan_neighbors(Engine *e)
         ki = (ki + 3) & ~3;
         e->kmax_in = std::max(e->kmax_in, std::min(e->kmax, std::max(8, ki)));
     }
+    // tiny systems: the step loop runs inside one persistent CTA (K0-small); the structures above still serve
+    // mdb_compute_forces / mdb_count_pairs / mdb_fire_minimize
+    // measured on B200 (tools/small_probe.py): 15 / 20 / 41 us per step at N = 256 / 1024 / 4096 against 30 / 31 / 32 us for
+    // the graph-replayed multi-kernel step, so MDB_MODE_AUTO switches over at 2048 particles
+    e->small = !e->slab && e->cfg.potential != MDB_POT_USER &&
+               ((want == MDB_MODE_AUTO && e->N <= 2048) || (want == MDB_MODE_SMALL && e->N <= kSmallMaxN));
+    if (e->small) {
+        e->small_skin = std::max(e->cfg.skin > 0 ? e->cfg.skin : 0.0, 0.4 * e->r_search);
+        double rl = e->r_search + e->small_skin;
+        double expect = (d == 3) ? rho * 4.18879020478639 * rl * rl * rl : rho * 3.14159265358979 * rl * rl;
+        int k = (int)std::ceil(expect * 1.8) + 16;
+        e->small_kmax = (int)std::min<int64_t>(std::max<int64_t>(e->N - 1, 1), (k + 3) & ~3);
+    }
     e->stats.r_search = e->r_search;
-    e->stats.mode = e->mode;
+    e->stats.mode = e->small ? (int)MDB_MODE_SMALL : e->mode;
     for (int k = 0; k < 3; k++) {
         e->stats.ncell[k] = nc[k];
         e->stats.cell_len[k] = e->L[k] / nc[k];
@@ -399,6 +423,7 @@ static int alloc_state(Engine *e, int64_t n)
     CU(cudaMalloc(&e->nnbr, sizeof(int32_t) * e->cap));
     CU(cudaMalloc(&e->ovf, sizeof(uint32_t) * e->cap));
     CU(cudaMalloc(&e->nnbr_in, sizeof(int32_t) * e->cap));
+    CU(cudaMalloc(&e->small_nnbr, sizeof(int32_t) * e->cap));
     return MDB_OK;
 }
 
@@ -1019,6 +1044,78 @@ static int slab_group(Engine *e, Group &storage, Group **out)
     return MDB_OK;
 }
 
+// K0-small: one persistent CTA runs a whole chunk of steps per launch
+template <int DIM>
+static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const double *ktemp_per_step, double tau, double ktemp,
+                     double *thermo)
+{
+    cudaStream_t s = e->stream;
+    if (!e->small_nl) CU(cudaMalloc(&e->small_nl, sizeof(uint32_t) * (size_t)e->small_kmax * (size_t)std::max(e->n, 1)));
+    CU(cudaEventRecord(e->ev0, s));
+    int rc = sync_ctl(e);
+    if (rc) return rc;
+    unsigned long long rebuilds0 = e->h_ctl->rebuilds;
+    SmallArgs a;
+    a.n = e->n;
+    a.ensemble = ensemble;
+    a.dt = dt; a.tau = tau; a.ktemp = ktemp;
+    a.nf = e->dim * ((double)e->N - 1.0);
+    a.ktemp_per_step = e->d_ktemp;
+    a.nl = e->small_nl; a.kmax = e->small_kmax;
+    if (!e->small_part) CU(cudaMalloc(&e->small_part, sizeof(double) * 2 * kSmallMaxGrid * 5));
+    a.gpart = e->small_part;
+    a.skin = e->small_skin;
+    double rl = e->r_search + e->small_skin;
+    const double rlist2 = rl * rl;
+    a.cutoff2 = e->cutoff2;
+    // FP32 membership test: coordinates are rounded to float (|err| <= L 2^-24 each), so pad the squared radius
+    double Lmax = std::max(e->L[0], std::max(e->L[1], e->dim == 3 ? e->L[2] : 0.0));
+    double eps = 4.0 * Lmax * 5.9604644775390625e-08;
+    a.rlist2_f = (float)((rlist2 + 2.0 * std::sqrt(3.0) * rl * eps + 3.0 * eps * eps) * (1.0 + 1e-5));
+    a.seed = e->cfg.seed;
+    size_t smem = sizeof(double4) * (size_t)std::max(e->n, 1);
+    int64_t done = 0;
+    while (done < nsteps) {
+        int64_t m = std::min(e->chunk, nsteps - done);
+        if (ensemble == MDB_NVT) CU(cudaMemcpyAsync(e->d_ktemp, ktemp_per_step + done, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+        a.nsteps = m;
+        a.thermo = thermo ? e->d_thermo : nullptr;
+        cudaError_t le = cudaSuccess;
+        dispatch_pot(e->cfg.potential, [&](auto pot) {
+            typedef decltype(pot) Pot;
+            auto kern = k_small_run<DIM, Pot>;
+            le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            DevCtl *ctl = e->ctl;
+            Grid g = e->grid;
+            PotParams pp = e->pp;
+            void *args[] = {&ctl, &g, &a, &pot, &pp};
+            // cooperative launch: all CTAs are co-resident (at most 64 CTAs of 64 threads) and meet at grid-wide barriers
+            if (le == cudaSuccess)
+                le = cudaLaunchCooperativeKernel((const void *)kern, dim3(nblk(e->n, kSmallBlock)), dim3(kSmallBlock), args, smem, s);
+        });
+        CU(le);
+        e->stats.kernel_launches += 1;
+        if (thermo) CU(cudaMemcpyAsync(thermo + 4 * done, e->d_thermo, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));
+        done += m;
+        if (done < nsteps) CU(cudaStreamSynchronize(s));
+    }
+    CU(cudaEventRecord(e->ev1, s));
+    if ((rc = sync_ctl(e))) return rc;
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->stats.last_run_ms = ms;
+    e->stats.steps += nsteps;
+    e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
+    (void)rebuilds0;
+    e->rng_step = e->h_ctl->rng_step;
+    if (e->h_ctl->nonfinite) {
+        CU(cudaMemsetAsync(&e->ctl->nonfinite, 0, sizeof(int), s));
+        return fail(e, MDB_ERR_NONFINITE, "non-finite energy: overlapping particles or unstable time step");
+    }
+    return MDB_OK;
+}
+
 template <int DIM>
 static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const double *ktemp_per_step, double tau, double ktemp,
                     double *thermo)
@@ -1029,6 +1126,7 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
     if (nsteps < 0 || !(dt > 0)) return fail(e, MDB_ERR_INVALID_ARG, "nsteps must be >= 0 and dt > 0");
     if (ensemble == MDB_NVT && (!ktemp_per_step || !(tau > 0))) return fail(e, MDB_ERR_INVALID_ARG, "NVT needs ktemp_per_step and tau > 0");
     if (ensemble == MDB_BROWNIAN && !(ktemp > 0)) return fail(e, MDB_ERR_INVALID_ARG, "Brownian needs ktemp > 0");
+    if (e->small) return run_small<DIM>(e, ensemble, nsteps, dt, ktemp_per_step, tau, ktemp, thermo);
     cudaStream_t s = e->stream;
     GraphKey key;
     key.ensemble = ensemble; key.dt = dt; key.tau = tau; key.ktemp = ktemp; key.thermo = thermo ? 1 : 0;

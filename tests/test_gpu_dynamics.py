@@ -168,3 +168,63 @@ def test_fire_minimizer_matches_oracle(md, orc):
     energy, frms, steps, conv = e2.fire_minimize()
     assert conv and steps == 1 and energy == 0.0
     e.close(); e2.close()
+
+
+@pytest.mark.parametrize("ensemble", ["nve", "nvt", "brownian"])
+def test_small_system_persistent_kernel_matches_oracle(md, orc, ensemble):
+    """K0-small (one persistent CTA, thousands of steps per launch) against the oracle loop and the list-mode engine"""
+    g = dict(np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "c1_phs_n1024.npz")))
+    n = 1024
+    out = {}
+    for mode in ("small", "list"):
+        modes = {"small": md._capi.MODE_SMALL, "list": md._capi.MODE_LIST}
+        e = md.Engine(3, n, g["box"], 1.5, 0, seed=99, mode=modes[mode])
+        e.upload(g["x"], g["diam"], velocities=g["v"], forces=g["f"], images=g["img"])
+        if ensemble == "nve":
+            t = e.run_nve(120, 1e-3)
+        elif ensemble == "nvt":
+            t = e.run_nvt(120, 1e-3, np.linspace(1.4737, 1.3, 120), 0.1)
+        else:
+            t = e.run_brownian(120, 1e-5, 1.4737)
+        out[mode] = (t, e.download(), e.stats(), e.rng_step)
+        e.close()
+    assert out["small"][2]["mode"] == 3 and out["list"][2]["mode"] == 2
+    ens = {"nve": orc.NVE, "nvt": orc.NVT, "brownian": orc.BROWNIAN}[ensemble]
+    kw = dict(ktemp=np.linspace(1.4737, 1.3, 120), tau=0.1) if ensemble == "nvt" else (dict(ktemp=1.4737) if ensemble == "brownian" else {})
+    dt = 1e-5 if ensemble == "brownian" else 1e-3
+    ox, ov, of, oi, ot = orc.run(ens, g["x"], g["v"], g["f"], g["img"], g["diam"], g["box"], 1.5, orc.POT_PHS, (), dt, 120, seed=99, **kw)
+    t, (x, v, f, img), st, rs = out["small"]
+    assert rs == 120 and np.array_equal(img, oi)
+    assert np.array_equal(t[:, 3], ot[:, 3]) and np.allclose(t[:, :3], ot[:, :3], rtol=1e-9, atol=1e-12)
+    assert np.max(np.abs(x - ox)) < 1e-9
+    if ensemble != "brownian":
+        assert np.max(np.abs(v - ov)) < 1e-8
+    assert np.array_equal(t[:, 3], out["list"][0][:, 3])
+    # the large-system entry points keep working on the state the small kernel left behind
+    e = md.Engine(3, n, g["box"], 1.5, 0, seed=99, mode=md._capi.MODE_SMALL)
+    e.upload(g["x"], g["diam"], velocities=g["v"])
+    e.run_nve(10, 1e-3)
+    E, W, npairs = e.compute_forces()
+    xs = e.download()[0]
+    ref = orc.forces(xs, g["diam"], g["box"], 1.5, orc.POT_PHS)
+    assert npairs == ref["n_int"] and relerr(E, ref["E"]) < 1e-12
+    e.close()
+
+
+def test_small_system_2d_polydisperse(md, orc):
+    from mdjl_b200 import workloads
+    p = workloads.poly2d(1200)
+    e = md.Engine(2, 1200, p["box"], 1.5, md._capi.POT_POLY, (1.25, 0.2), seed=3)
+    e.upload(p["x"], p["diam"], velocities=np.zeros((1200, 2)))
+    e.fire_minimize(max_steps=400, tol=1e-3, dt_initial=1e-4, dt_max=5e-3)
+    x0 = e.download()[0]
+    v0 = workloads.velocities(1200, 2, 0.11)
+    e.upload(x0, p["diam"], velocities=v0)
+    assert e.stats()["mode"] == 3
+    t = e.run_nve(60, 1e-3)
+    x, v, f, img = e.download()
+    ox, ov, of, oi, ot = orc.run(orc.NVE, x0, v0, np.zeros_like(x0), np.zeros((1200, 2), np.int32), p["diam"], p["box"], 1.5, orc.POT_POLY,
+                                 (1.25, 0.2), 1e-3, 60)
+    assert np.array_equal(t[:, 3], ot[:, 3]) and np.allclose(t[:, :3], ot[:, :3], rtol=1e-9)
+    assert np.max(np.abs(x - ox)) < 1e-9 and np.array_equal(img, oi)
+    e.close()
