@@ -63,6 +63,7 @@ struct mdb_engine_s {
     double skin_in = 0;
     int64_t nl_stride = 0;
     double *part = nullptr;
+    double *xref = nullptr;   // unwrapped positions at the last list build (exact displacement test, Brownian)
     uint32_t *ovf = nullptr;  // overflow particle list (MDB_MODE_LIST)
     int nsm = 148;
     int64_t alloc_ncell = -1, alloc_cap = -1;
@@ -176,7 +177,8 @@ static void free_state(Engine *e)
     }
     cudaFree(e->cell_of); cudaFree(e->slot_of); cudaFree(e->counts); cudaFree(e->start); cudaFree(e->order); cudaFree(e->tile_sums);
     cudaFree(e->nl); cudaFree(e->nnbr); cudaFree(e->ovf); cudaFree(e->nl_in); cudaFree(e->nnbr_in);
-    cudaFree(e->small_nl); cudaFree(e->small_nnbr); cudaFree(e->small_part);
+    cudaFree(e->small_nl); cudaFree(e->small_nnbr); cudaFree(e->small_part); cudaFree(e->xref);
+    e->xref = nullptr;
     e->small_part = nullptr;
     e->ovf = nullptr; e->nl_in = nullptr; e->nnbr_in = nullptr; e->small_nl = nullptr; e->small_nnbr = nullptr;
     e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
@@ -422,6 +424,7 @@ static int alloc_state(Engine *e, int64_t n)
     CU(cudaMalloc(&e->order, sizeof(uint32_t) * e->cap));
     CU(cudaMalloc(&e->nnbr, sizeof(int32_t) * e->cap));
     CU(cudaMalloc(&e->ovf, sizeof(uint32_t) * e->cap));
+    CU(cudaMalloc(&e->xref, sizeof(double) * 3 * e->cap));
     CU(cudaMalloc(&e->nnbr_in, sizeof(int32_t) * e->cap));
     CU(cudaMalloc(&e->small_nnbr, sizeof(int32_t) * e->cap));
     return MDB_OK;
@@ -448,7 +451,7 @@ static void enqueue_rebuild(Engine *e)
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
             k_build_list<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
-                                                                         e->nnbr, e->ovf, e->ctl);
+                                                                         e->nnbr, e->ovf, e->ctl, e->xref);
         }
     }
 }
@@ -559,10 +562,10 @@ static void query_occupancy(Engine *e)
 static int force_slots(const Engine *e) { return force_grid(e) + ((e->mode == MDB_MODE_LIST && !e->brute) ? kOverflowGrid : 0); }
 static int force_kernel_count(const Engine *e) { return (e->mode == MDB_MODE_LIST && !e->brute) ? 2 : 1; }
 
-static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHandle handle, int use_handle)
+static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHandle handle, int use_handle, int exact = 0)
 {
     int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
-    k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, e->skin_in, always, e->ctl, handle, use_handle);
+    k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, e->skin_in, always, exact, e->ctl, handle, use_handle);
 }
 
 static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance, int stage = 0)
@@ -580,9 +583,10 @@ static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphCondi
         if (prof) cudaEventRecord(e->evp[0], e->stream);
         k_kick_drift<DIM><<<kick_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
-        enqueue_skin_check(e, dt, handle, use_handle);
-    } else {
         enqueue_skin_check(e, 1.0, handle, use_handle);
+    } else {
+        // Brownian: the mover measured the true displacement since the list build (exact test, list mode only)
+        enqueue_skin_check(e, 1.0, handle, use_handle, (e->mode == MDB_MODE_LIST && !e->brute) ? 1 : 0);
     }
 }
 // the part of one step after the rebuild
@@ -600,7 +604,7 @@ static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, do
         if (prof) cudaEventRecord(e->evp[3], e->stream);
         if (prof) cudaEventRecord(e->evp[0], e->stream);
         k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed,
-                                                                      e->ctl);
+                                                                      e->ctl, (e->mode == MDB_MODE_LIST && !e->brute) ? e->xref : nullptr);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
     }
@@ -855,7 +859,7 @@ static int group_rebuild(Group &G)
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
             k_build_list<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
-                                                                                  e->nnbr, e->ovf, e->ctl);
+                                                                                  e->nnbr, e->ovf, e->ctl, nullptr);
             e->stats.kernel_launches += 1;
         }
     }
@@ -899,7 +903,7 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
     if ((rc = group_allreduce(G, 1, true, [](Engine *e) { return (double *)&e->ctl->dmax2_bits; }))) return rc;
     for (Engine *e : G) {
         int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
-        k_skin_check<<<1, 1, 0, e->stream>>>(moved_scale, e->skin, e->skin_in, always, e->ctl, 0, 0);
+        k_skin_check<<<1, 1, 0, e->stream>>>(moved_scale, e->skin, e->skin_in, always, 0, e->ctl, 0, 0);
         e->stats.kernel_launches += 1;
     }
     {
@@ -913,7 +917,8 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
     for (Engine *e : G) {
         enqueue_force_slab<DIM, KICK2>(e, dt);
         if (ensemble == MDB_BROWNIAN && advance) {
-            k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(-1, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed, e->ctl);
+            k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(-1, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed, e->ctl,
+                                                                          nullptr);
             e->stats.kernel_launches += 1;
         }
         if (reduce_now) enqueue_finalize(e, ensemble, dt, tau, 0, 0, 1);
@@ -992,7 +997,7 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
                     k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
                     g->stats.kernel_launches += 1;
                 }
-                if ((rc = group_force_phase<DIM, true>(G, ensemble, dt, tau, ktemp, dt, 1, 1, per_step_reduce))) return rc;
+                if ((rc = group_force_phase<DIM, true>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce))) return rc;
             } else {
                 if ((rc = group_force_phase<DIM, false>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce))) return rc;
             }

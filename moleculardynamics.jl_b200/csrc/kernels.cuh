@@ -64,6 +64,7 @@ struct DevCtl {
     int error;                    // sticky device-side error bits (see kErr*)
     double red[4];                // slab mode: local sums of U, W, n_pairs, |v|^2 awaiting the all-reduce
     double disp_in;               // displacement bound since the inner (tight) list was last refreshed
+    unsigned long long dref2_bits;  // Brownian: largest squared displacement from the positions of the last list build
     int inner_refresh;            // 1: the coming force evaluation re-derives the inner list from the outer one
     int max_nnbr_in;
     unsigned long long dmax2_bits;  // bit pattern of the largest squared displacement bound of the last move
@@ -629,14 +630,21 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
 template <int DIM>
 __global__ void __launch_bounds__(kForceBlock)
 k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
-             uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, uint32_t *__restrict__ ovf, DevCtl *ctl)
+             uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, uint32_t *__restrict__ ovf, DevCtl *ctl,
+             double *__restrict__ xref)
 {
-    const double4 *__restrict__ pos = ctl->st[ctl->cur].pos;
+    const StatePtrs st = ctl->st[ctl->cur];
+    const double4 *__restrict__ pos = st.pos;
     if (n < 0) n = ctl->n_own;
     int i = blockIdx.x * kForceBlock + threadIdx.x;
     int cnt = 0;
     if (i < n) {
         double4 pi = pos[i];
+        if (xref) {  // unwrapped position at build time: reference for the exact displacement test of Brownian runs
+            const double pk[3] = {pi.x, pi.y, pi.z};
+#pragma unroll
+            for (int k = 0; k < DIM; k++) xref[k * st.cap + i] = pk[k] + g.L[k] * (double)st.img[k * st.cap + i];
+        }
         int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
         int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
         int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
@@ -655,6 +663,7 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctl->list_valid = 1;
         ctl->disp = 0.0;
+        ctl->dref2_bits = 0ull;
     }
 }
 
@@ -1026,7 +1035,7 @@ k_kick_drift(int n, Grid g, double dt, DevCtl *__restrict__ ctl)
         st_pos(&s.pos[i], make_double4(x[0], x[1], x[2], p.w));
         vmax2 = fmax(vmax2, v2);
     }
-    double r[1] = {vmax2};
+    double r[1] = {vmax2 * (dt * dt)};  // squared displacement of this step: every mover reports the same quantity
     block_reduce<1, kStreamBlock, true>(r);
     // non-negative doubles order like their bit patterns; NaN (0x7ff8...) compares above everything and forces a rebuild
     if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
@@ -1061,18 +1070,19 @@ __global__ void k_flip(DevCtl *ctl, const uint32_t *__restrict__ n_new)
 // sigma = sqrt(2 dt), src/simulation.jl:212).  Noise keyed by (original particle id, RNG step).
 template <int DIM>
 __global__ void __launch_bounds__(kStreamBlock)
-k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, DevCtl *__restrict__ ctl)
+k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, DevCtl *__restrict__ ctl,
+           const double *__restrict__ xref)
 {
     const StatePtrs s = ctl->st[ctl->cur];
     const unsigned long long rng_step = ctl->rng_step;
     if (n < 0) n = ctl->n_own;
-    double dmax2 = 0.0;
+    double dmax2 = 0.0, dref2 = 0.0;
     for (int i = blockIdx.x * kStreamBlock + threadIdx.x; i < n; i += gridDim.x * kStreamBlock) {
         double noise[3];
         brownian_noise<DIM>(seed, rng_step, (uint32_t)s.id[i], noise);
         double4 p = ld_pos(&s.pos[i]);
         double x[3] = {p.x, p.y, p.z};
-        double d2 = 0.0;
+        double d2 = 0.0, r2 = 0.0;
 #pragma unroll
         for (int k = 0; k < DIM; k++) {
             double f = s.frc[k * s.cap + i];
@@ -1081,30 +1091,50 @@ k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, 
             d2 = (k == 0) ? del * del : d2 + del * del;
             double frac = g.invL[k] * xv;
             double ncr = floor(frac);
-            if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
             x[k] = g.L[k] * (frac - ncr);
+            if (xref) {
+                // a random walk moves far less than the sum of its per-step maxima: measure the true displacement from
+                // the positions the Verlet list was built for (unwrapped through the image counters)
+                int32_t im = s.img[k * s.cap + i];
+                if (ncr != 0.0) {
+                    im += (int32_t)ncr;
+                    s.img[k * s.cap + i] = im;
+                }
+                double dr = (x[k] + g.L[k] * (double)im) - xref[k * s.cap + i];
+                r2 = (k == 0) ? dr * dr : r2 + dr * dr;
+            } else if (ncr != 0.0) {
+                s.img[k * s.cap + i] += (int32_t)ncr;
+            }
         }
         st_pos(&s.pos[i], make_double4(x[0], x[1], x[2], p.w));
         dmax2 = fmax(dmax2, d2);
+        dref2 = fmax(dref2, r2);
     }
-    double r[1] = {dmax2};
-    block_reduce<1, kStreamBlock, true>(r);
-    if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
+    double r[2] = {dmax2, dref2};
+    block_reduce<2, kStreamBlock, true>(r);
+    if (threadIdx.x == 0) {
+        atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
+        if (xref) atomicMax(&ctl->dref2_bits, (unsigned long long)__double_as_longlong(r[1]));
+    }
 }
 
 #ifndef __CUDACC_RTC__
 // ------------------------------------------------------------------------------------------------
 // K-skin: consume the displacement bound of the move that just happened, decide whether the Verlet list must be
 // rebuilt before the coming force evaluation, and drive the conditional graph node.
-// dmax2 holds max |v|^2 (scale = dt) or max |dx|^2 (scale = 1).
+// dmax2 holds the largest squared displacement of the move that just happened (scale = 1).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_skin_check(double scale, double skin, double skin_in, int always, DevCtl *ctl, cudaGraphConditionalHandle handle,
-                             int use_handle)
+__global__ void k_skin_check(double scale, double skin, double skin_in, int always, int exact, DevCtl *ctl,
+                             cudaGraphConditionalHandle handle, int use_handle)
 {
     double m = __longlong_as_double((long long)ctl->dmax2_bits);
     ctl->dmax2_bits = 0ull;  // consumed
     double step = sqrt(m) * scale;
-    double disp = ctl->disp + step;
+    // exact: the mover measured the true largest displacement since the list build (Brownian); it replaces the running sum
+    // of per-step maxima and remains a valid starting point if later steps go back to accumulating bounds
+    const unsigned long long dref = ctl->dref2_bits;
+    double disp = (exact && dref != 0ull) ? sqrt(__longlong_as_double((long long)dref)) : ctl->disp + step;
+    if (!exact) ctl->dref2_bits = 0ull;  // a mover that does not measure it leaves the exact displacement unknown
     // NaN-safe: a non-finite bound forces a rebuild
     int need = always || !ctl->list_valid || !(2.0 * disp <= skin);
     ctl->disp = need ? 0.0 : disp;

@@ -228,3 +228,25 @@ def test_small_system_2d_polydisperse(md, orc):
     assert np.array_equal(t[:, 3], ot[:, 3]) and np.allclose(t[:, :3], ot[:, :3], rtol=1e-9)
     assert np.max(np.abs(x - ox)) < 1e-9 and np.array_equal(img, oi)
     e.close()
+
+
+def test_mixed_ensembles_keep_the_list_exact(md, orc):
+    """NVE, Brownian and stand-alone force calls interleaved on one engine: the displacement bookkeeping (running bound
+    for velocity Verlet, exact displacement for Brownian moves) must never let a pair slip out of the Verlet list"""
+    from mdjl_b200 import workloads
+    n = 8192
+    cfg = workloads.phs_fluid(n)
+    e = md.Engine(3, n, cfg["box"], 1.5, 0, seed=12, mode=md._capi.MODE_LIST)
+    e.upload(cfg["x"], cfg["diam"], velocities=workloads.velocities(n, 3, 1.4737))
+    e.run_nvt(1200, 1e-3, 1.4737, 0.1, thermo=False)
+    for rounds in range(6):
+        e.run_brownian(37, 2e-5, 1.4737, thermo=False)
+        e.run_nve(23, 1e-3, thermo=False)
+        t = e.run_brownian(11, 2e-5, 1.4737)
+        x = e.download()[0]
+        E, W, npairs = e.compute_forces()
+        ref = orc.forces(x, cfg["diam"], cfg["box"], 1.5, orc.POT_PHS)
+        assert npairs == ref["n_int"] and relerr(E, ref["E"]) <= 1e-12
+    st = e.stats()
+    assert st["rebuilds"] < 6 * 71      # far fewer rebuilds than steps
+    e.close()
