@@ -46,7 +46,6 @@ k_small_run(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParams pp
     extern __shared__ double4 spos[];
     __shared__ double red[5][kSmallBlock / 32];
     __shared__ double s_alpha;
-    __shared__ int s_rebuild;
     const StatePtrs s = ctl->st[ctl->cur];
     const int n = a.n, tid = threadIdx.x, G = gridDim.x;
     const int i = blockIdx.x * kSmallBlock + tid;
