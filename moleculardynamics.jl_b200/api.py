@@ -286,20 +286,40 @@ def initialize_velocities(ktemp, rng, n_particles, dimension):
     return np.ascontiguousarray(V.T)
 
 
-def lattice_positions(n_particles, box, dimension, rng, jitter=0.02):
+def lattice_positions(n_particles, box, dimension, rng, jitter=0.02, sigma=1.0):
     """Overlap-free start for random_init=True.  The reference packs random points with Packmol
-    (src/initialization.jl:20-30), a one-off host-side setup step that is out of scope here; a jittered lattice with
-    random vacancies gives the same kind of overlap-free input."""
-    box = np.asarray(box, dtype=np.float64)
-    m = int(math.ceil(n_particles ** (1.0 / dimension)))
-    while m ** dimension < n_particles:
-        m += 1
-    grid = np.stack(np.meshgrid(*[np.arange(m)] * dimension, indexing="ij"), axis=-1).reshape(-1, dimension)
-    keep = rng.permutation(grid.shape[0])[:n_particles]
+    (src/initialization.jl:20-30), a one-off host-side setup step that is out of scope here; this picks the lattice
+    (sc / bcc / fcc, or sc / centred-rectangular in 2-D) with the largest nearest-neighbour distance that offers at least
+    n_particles sites in the box, removes random sites down to n_particles and adds a small jitter that keeps
+    neighbours further apart than `sigma` whenever the lattice allows it."""
+    box = np.asarray(box, dtype=np.float64)[:dimension]
+    bases = {"sc": np.zeros((1, dimension)), "centred": np.array([[0.0] * dimension, [0.5] * dimension])}
+    if dimension == 3:
+        bases["fcc"] = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]], dtype=np.float64)
+    best = None
+    for kind, basis in bases.items():
+        nb = basis.shape[0]
+        # cell counts proportional to the box edges, grown until there are enough sites
+        scale = (n_particles / nb / np.prod(box)) ** (1.0 / dimension)
+        m = np.maximum(1, np.floor(box * scale).astype(int))
+        while nb * np.prod(m) < n_particles:
+            m[np.argmax(box / m)] += 1
+        a = box / m
+        seps = [a[k] for k in range(dimension)]
+        for bvec in basis[1:]:
+            seps.append(float(np.sqrt(np.sum((bvec * a) ** 2))))
+        nn = min(seps)
+        if best is None or nn > best[0]:
+            best = (nn, kind, m, basis)
+    nn, kind, m, basis = best
+    grid = np.stack(np.meshgrid(*[np.arange(mk) for mk in m], indexing="ij"), axis=-1).reshape(-1, dimension)
+    frac = (grid[:, None, :] + basis[None, :, :] + 0.25).reshape(-1, dimension) / m
+    keep = rng.permutation(frac.shape[0])[:n_particles]
     keep.sort()
-    spacing = box / m
-    pos = (grid[keep] + 0.5) * spacing
-    pos += rng.uniform(-jitter, jitter, size=pos.shape)
+    pos = frac[keep] * box
+    jit = min(jitter, max(0.0, 0.45 * (nn - sigma) / math.sqrt(dimension)))
+    pos += rng.uniform(-jit, jit, size=pos.shape) if jit > 0 else 0.0
+    pos -= box * np.floor(pos / box)
     return pos
 
 

@@ -346,6 +346,9 @@ static int alloc_neighbors(Engine *e)
     e->counts = e->start = e->tile_sums = nullptr; e->nl = nullptr; e->nl_in = nullptr;
     CU(cudaMalloc(&e->counts, sizeof(uint32_t) * (e->ncell + 1)));
     CU(cudaMalloc(&e->start, sizeof(uint32_t) * (e->ncell + 1)));
+    // the slab protocol packs boundary columns from `start` before the first rebuild has filled it: empty ranges, not garbage
+    CU(cudaMemset(e->start, 0, sizeof(uint32_t) * (e->ncell + 1)));
+    CU(cudaMemset(e->counts, 0, sizeof(uint32_t) * (e->ncell + 1)));
     e->ntiles = nblk(e->ncell, kScanTile);
     CU(cudaMalloc(&e->tile_sums, sizeof(uint32_t) * std::max(1, e->ntiles)));
     if (e->mode == MDB_MODE_LIST) {
@@ -375,7 +378,8 @@ static int alloc_slab(Engine *e)
 {
     free_slab(e);
     // capacities: leavers per rebuild are a thin layer (skin/2) of the two faces; a boundary column holds n/nxo particles
-    double per_col = (double)e->n / std::max(1, e->nxo);
+    // from GLOBAL quantities, so that every rank sizes its messages identically (columns may be split unevenly)
+    double per_col = (double)e->N / std::max(1, e->grid.nc[0]);
     e->mig_cap = (int)std::max(4096.0, 0.5 * per_col + 1024.0);
     e->ghost_cap = (int)std::max(4096.0, 2.0 * per_col + 1024.0);
     size_t nr = (size_t)e->nrows + 1;
@@ -756,6 +760,22 @@ __global__ void k_local_allreduce(PtrList pl, int count, int is_max)
 
 typedef std::vector<Engine *> Group;
 
+// MDB200_DEBUG_SYNC=1: synchronise after every phase of the slab protocol and name the phase that faulted
+static bool debug_sync()
+{
+    static int v = -1;
+    if (v < 0) v = getenv("MDB200_DEBUG_SYNC") ? 1 : 0;
+    return v == 1;
+}
+#define PHASE(e, name)                                                                                               \
+    do {                                                                                                             \
+        if (debug_sync()) {                                                                                          \
+            cudaError_t _e = cudaStreamSynchronize((e)->stream);                                                     \
+            if (_e == cudaSuccess) _e = cudaGetLastError();                                                          \
+            if (_e != cudaSuccess) return fail(e, MDB_ERR_CUDA, std::string("phase ") + name + ": " + cudaGetErrorString(_e)); \
+        }                                                                                                            \
+    } while (0)
+
 // ring exchange: every rank sends `to_left`/`to_right` and receives `from_left`/`from_right` (bytes each)
 template <class GetBuf>
 static int group_exchange(Group &G, size_t bytes, GetBuf buf)
@@ -827,23 +847,31 @@ static int group_rebuild(Group &G)
                                                                                    e->mig_send[0], e->mig_send[1], e->mig_cap);
         k_slab_mig_headers<<<1, 1, 0, s>>>(e->ctl, e->mig_send[0], e->mig_send[1], e->mig_cap);
         e->stats.kernel_launches += 2;
+        PHASE(e, "classify");
     }
     if ((rc = group_exchange(G, sizeof(MigRec) * (1 + (size_t)G[0]->mig_cap), mig_buf))) return rc;
     for (Engine *e : G) {
         cudaStream_t s = e->stream;
         const uint32_t *n_new = e->start + e->ncell;
+        PHASE(e, "migration exchange");
         k_slab_unpack<DIM><<<nblk(2 * e->mig_cap, kStreamBlock), kStreamBlock, 0, s>>>(e->ctl, e->grid, e->mig_recv[0], e->mig_recv[1],
                                                                                      e->cell_of, e->slot_of, e->counts, e->cap_own);
+        PHASE(e, "unpack");
         k_scan_tile_sums<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums);
         k_scan_tiles<<<1, 1024, 0, s>>>(e->ntiles, e->tile_sums);
         k_scan_apply<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums, e->start);
+        PHASE(e, "scan");
         k_fill<<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(-1, e->ctl, e->cell_of, e->slot_of, e->start, e->order);
+        PHASE(e, "fill");
         k_cellsort<<<nblk(e->ncell, kStreamBlock), kStreamBlock, 0, s>>>(e->ncell, e->start, e->order, 1, e->ctl);
+        PHASE(e, "cellsort");
         k_gather<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(-1, e->order, e->ctl, n_new);
+        PHASE(e, "gather");
         k_flip<<<1, 1, 0, s>>>(e->ctl, n_new);
         k_slab_rowcounts<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, s>>>(e->nrows, e->nxo, e->start, e->row_cnt[0], e->row_cnt[1]);
         k_slab_rowscan<<<1, 1024, 0, s>>>(e->nrows, e->row_cnt[0], e->rowoff[0], 0u, e->row_cnt[1], e->rowoff[1], 0u);
         e->stats.kernel_launches += 10;
+        PHASE(e, "rowscan");
     }
     if ((rc = group_exchange_ghosts<DIM>(G))) return rc;
     for (Engine *e : G) {
@@ -854,13 +882,16 @@ static int group_rebuild(Group &G)
         const double4 *gl = e->gpos_raw, *gr = e->gpos_raw + 1 + (size_t)e->ghost_cap;
         k_slab_ghost_count<DIM><<<nblk(2 * e->ghost_cap, kStreamBlock), kStreamBlock, 0, s>>>(e->grid, gl, gr, e->gcnt[0], e->gcnt[1]);
         uint32_t base_l = e->grid.g0 + 1u, base_r = e->grid.g0 + 1u + (uint32_t)e->ghost_cap + 1u;
+        PHASE(e, "ghost exchange");
         k_slab_rowscan<<<1, 1024, 0, s>>>(e->nrows, e->gcnt[0], e->gstart[0], base_l, e->gcnt[1], e->gstart[1], base_r);
         e->stats.kernel_launches += 2;
+        PHASE(e, "ghost cells");
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
             k_build_list<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
                                                                                   e->nnbr, e->ovf, e->ctl, nullptr);
             e->stats.kernel_launches += 1;
+            PHASE(e, "build list");
         }
     }
     return MDB_OK;
@@ -915,7 +946,9 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
         if ((rc = group_rebuild<DIM>(G))) return rc;
     }
     for (Engine *e : G) {
+        PHASE(e, "before force");
         enqueue_force_slab<DIM, KICK2>(e, dt);
+        PHASE(e, "force");
         if (ensemble == MDB_BROWNIAN && advance) {
             k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(-1, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed, e->ctl,
                                                                           nullptr);

@@ -95,3 +95,29 @@ def test_slab_errors(md):
         e.compute_forces()
     assert ei.value.code == _capi.ERR_STATE
     e.close()
+
+
+def test_2d_polydisperse_slabs(md, orc):
+    """2-D non-additive mixture (BASELINE config 2 family) cut into slabs: forces vs oracle, dynamics vs single domain"""
+    from mdjl_b200 import workloads
+    p = workloads.poly2d(4900)
+    e = md.Engine(2, 4900, p["box"], 1.5, md._capi.POT_POLY, (1.25, 0.2), seed=3, mode=md._capi.MODE_LIST)
+    e.upload(p["x"], p["diam"], velocities=np.zeros((4900, 2)))
+    e.fire_minimize(max_steps=300, tol=1e-3, dt_initial=1e-4, dt_max=5e-3)
+    x0 = e.download()[0]
+    v0 = workloads.velocities(4900, 2, 0.11)
+    e.upload(x0, p["diam"], velocities=v0)
+    ring = md.SlabRing.local(3, 2, 4900, p["box"], 1.5, md._capi.POT_POLY, (1.25, 0.2), seed=3)
+    ring.upload(x0, p["diam"], velocities=v0)
+    E, W, npairs = ring.compute_forces()
+    ref = orc.forces(x0, p["diam"], p["box"], 1.5, orc.POT_POLY, (1.25, 0.2))
+    assert npairs == ref["n_int"] and relerr(E, ref["E"]) <= 1e-12
+    assert force_error(ring.download()[2], ref["F"]) <= 1e-12
+    # the stand-alone evaluation primed the resident forces of the ring; start both runs from the same (unprimed) state,
+    # as the reference does not compute forces before step 0 (SURVEY Q6)
+    ring.upload(x0, p["diam"], velocities=v0)
+    a, b = e.run_nve(200, 1e-3), ring.run_nve(200, 1e-3)
+    assert np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a[:, :3], b[:, :3], rtol=1e-9)
+    assert np.max(np.abs(e.download()[0] - ring.download()[0])) < 1e-9
+    e.close()
+    ring.close()
