@@ -101,7 +101,12 @@ struct mdb_engine_s {
     int transport = 0;                     // 0 none, 1 in-process ring (tests / one-GPU emulation), 2 NCCL
     std::vector<mdb_engine_s *> *group = nullptr;  // in-process ring, shared by its members; [0] drives it
     bool stream_owned = true;
+    bool slab_graph_failed = false;
     ncclComm_t comm = nullptr;
+    // graph replay: NCCL keeps per-communicator capture state, and a graph captured in several segments (one per
+    // conditional node) needs a different communicator in every segment that communicates
+    ncclComm_t comm_seg[3] = {nullptr, nullptr, nullptr};
+    int comm_sel = 0;  // 0: comm, 1..3: comm_seg[sel-1]
 
     // ---- user-defined Potential compiled with NVRTC (mdb_set_user_potential) -----------------------
     cudaLibrary_t user_lib = nullptr;
@@ -380,8 +385,10 @@ static int alloc_slab(Engine *e)
     // capacities: leavers per rebuild are a thin layer (skin/2) of the two faces; a boundary column holds n/nxo particles
     // from GLOBAL quantities, so that every rank sizes its messages identically (columns may be split unevenly)
     double per_col = (double)e->N / std::max(1, e->grid.nc[0]);
-    e->mig_cap = (int)std::max(4096.0, 0.5 * per_col + 1024.0);
-    e->ghost_cap = (int)std::max(4096.0, 2.0 * per_col + 1024.0);
+    // a boundary column holds per_col particles (relative fluctuation ~ per_col^-1/2); leavers per rebuild are the
+    // particles within skin/2 of a face, about 0.1 per_col.  Messages always travel at full capacity.
+    e->mig_cap = (int)std::max(2048.0, 0.3 * per_col + 1024.0);
+    e->ghost_cap = (int)std::max(2048.0, 1.3 * per_col + 1024.0);
     size_t nr = (size_t)e->nrows + 1;
     for (int d = 0; d < 2; d++) {
         CU(cudaMalloc(&e->mig_send[d], sizeof(MigRec) * (1 + (size_t)e->mig_cap)));
@@ -701,6 +708,7 @@ struct NcclApi {
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -731,6 +739,7 @@ static bool load_nccl(std::string &why)
     LOADSYM(Send, "ncclSend")
     LOADSYM(Recv, "ncclRecv")
     LOADSYM(AllReduce, "ncclAllReduce")
+    LOADSYM(Broadcast, "ncclBroadcast")
     LOADSYM(GroupStart, "ncclGroupStart")
     LOADSYM(GroupEnd, "ncclGroupEnd")
     LOADSYM(GetErrorString, "ncclGetErrorString")
@@ -784,11 +793,12 @@ static int group_exchange(Group &G, size_t bytes, GetBuf buf)
     Engine *e = G[0];
     if (e->transport == 2) {
         int P = e->nranks, L = (e->rank + P - 1) % P, R = (e->rank + 1) % P;
+        ncclComm_t comm = e->comm_sel ? e->comm_seg[e->comm_sel - 1] : e->comm;
         NC(g_nccl.GroupStart());
-        NC(g_nccl.Send(buf(e, 0), bytes, ncclInt8, L, e->comm, e->stream));
-        NC(g_nccl.Send(buf(e, 1), bytes, ncclInt8, R, e->comm, e->stream));
-        NC(g_nccl.Recv(buf(e, 3), bytes, ncclInt8, R, e->comm, e->stream));
-        NC(g_nccl.Recv(buf(e, 2), bytes, ncclInt8, L, e->comm, e->stream));
+        NC(g_nccl.Send(buf(e, 0), bytes, ncclInt8, L, comm, e->stream));
+        NC(g_nccl.Send(buf(e, 1), bytes, ncclInt8, R, comm, e->stream));
+        NC(g_nccl.Recv(buf(e, 3), bytes, ncclInt8, R, comm, e->stream));
+        NC(g_nccl.Recv(buf(e, 2), bytes, ncclInt8, L, comm, e->stream));
         NC(g_nccl.GroupEnd());
     } else {
         int P = (int)G.size();
@@ -806,7 +816,8 @@ static int group_allreduce(Group &G, int count, bool is_max, GetPtr ptr)
 {
     Engine *e = G[0];
     if (e->transport == 2) {
-        NC(g_nccl.AllReduce(ptr(e), ptr(e), count, ncclDouble, is_max ? ncclMax : ncclSum, e->comm, e->stream));
+        ncclComm_t comm = e->comm_sel ? e->comm_seg[e->comm_sel - 1] : e->comm;
+        NC(g_nccl.AllReduce(ptr(e), ptr(e), count, ncclDouble, is_max ? ncclMax : ncclSum, comm, e->stream));
     } else {
         PtrList pl;
         pl.n = (int)G.size();
@@ -823,6 +834,18 @@ static inline void *ghost_buf(Engine *e, int which)
     return e->gpos_raw + (which == 2 ? 0 : 1 + (size_t)e->ghost_cap);  // left ghosts block, right ghosts block
 }
 
+static int group_send_ghosts(Group &G) { return group_exchange(G, sizeof(double4) * (1 + (size_t)G[0]->ghost_cap), ghost_buf); }
+
+static void group_pack_ghosts(Group &G)
+{
+    for (Engine *e : G) {
+        k_slab_pack_ghost<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->nxo, e->start, e->rowoff[0],
+                                                                                      e->rowoff[1], e->gh_send[0], e->gh_send[1],
+                                                                                      e->ghost_cap, e->ctl);
+        e->stats.kernel_launches += 1;
+    }
+}
+
 template <int DIM>
 static int group_exchange_ghosts(Group &G)
 {
@@ -837,9 +860,27 @@ static int group_exchange_ghosts(Group &G)
 
 // the neighbour rebuild of a slab ring: migration, counting sort of the owned set, ghost columns, Verlet list
 template <int DIM>
+static int rebuild_part1(Group &G);
+template <int DIM>
+static int rebuild_part2(Group &G);
+template <int DIM>
+static int rebuild_part3(Group &G);
+
+template <int DIM>
 static int group_rebuild(Group &G)
 {
     int rc;
+    if ((rc = rebuild_part1<DIM>(G))) return rc;
+    if ((rc = group_exchange(G, sizeof(MigRec) * (1 + (size_t)G[0]->mig_cap), mig_buf))) return rc;
+    if ((rc = rebuild_part2<DIM>(G))) return rc;
+    if ((rc = group_send_ghosts(G))) return rc;
+    return rebuild_part3<DIM>(G);
+}
+
+// part 1: leavers -> migration buffers
+template <int DIM>
+static int rebuild_part1(Group &G)
+{
     for (Engine *e : G) {
         cudaStream_t s = e->stream;
         CU(cudaMemsetAsync(e->counts, 0, sizeof(uint32_t) * (e->ncell + 1), s));
@@ -849,7 +890,13 @@ static int group_rebuild(Group &G)
         e->stats.kernel_launches += 2;
         PHASE(e, "classify");
     }
-    if ((rc = group_exchange(G, sizeof(MigRec) * (1 + (size_t)G[0]->mig_cap), mig_buf))) return rc;
+    return MDB_OK;
+}
+
+// part 2: arrivals appended, counting sort of the owned set, boundary columns packed
+template <int DIM>
+static int rebuild_part2(Group &G)
+{
     for (Engine *e : G) {
         cudaStream_t s = e->stream;
         const uint32_t *n_new = e->start + e->ncell;
@@ -873,7 +920,14 @@ static int group_rebuild(Group &G)
         e->stats.kernel_launches += 10;
         PHASE(e, "rowscan");
     }
-    if ((rc = group_exchange_ghosts<DIM>(G))) return rc;
+    group_pack_ghosts(G);
+    return MDB_OK;
+}
+
+// part 3: ghost cell ranges from the received columns, Verlet list
+template <int DIM>
+static int rebuild_part3(Group &G)
+{
     for (Engine *e : G) {
         cudaStream_t s = e->stream;
         size_t nr = (size_t)e->nrows + 1;
@@ -922,29 +976,27 @@ static void enqueue_force_slab(Engine *e, double dt)
     e->stats.kernel_launches += force_kernel_count(e);
 }
 
-// make every rank's ghosts and neighbour structure current, then evaluate forces and the global thermo scalars.
-// `moved_scale`: factor turning the pending displacement bound into a length (dt for |v|, 1 for |dx|).
-template <int DIM, bool KICK2>
-static int group_force_phase(Group &G, int ensemble, double dt, double tau, double ktemp, double moved_scale, int thermo, int advance,
-                             bool reduce_now = true)
+// head of a slab force evaluation: ghosts current on every rank, global displacement bound, rebuild decision
+template <int DIM>
+static int slab_head(Group &G, CondHandles hs)
 {
     int rc;
-    Engine *lead = G[0];
     if ((rc = group_exchange_ghosts<DIM>(G))) return rc;
     if ((rc = group_allreduce(G, 1, true, [](Engine *e) { return (double *)&e->ctl->dmax2_bits; }))) return rc;
     for (Engine *e : G) {
         int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
-        k_skin_check<<<1, 1, 0, e->stream>>>(moved_scale, e->skin, e->skin_in, always, 0, e->ctl, 0, 0);
+        // every rank reaches the same decision (same all-reduced bound); the first one drives the conditional node
+        k_skin_check<<<1, 1, 0, e->stream>>>(1.0, e->skin, e->skin_in, always, 0, e->ctl, 0, 0, e == G[0] ? hs : CondHandles{{0, 0, 0}, 0});
         e->stats.kernel_launches += 1;
     }
-    {
-        Engine *e = lead;
-        CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-    }
-    if (lead->h_ctl->need_rebuild) {
-        if ((rc = group_rebuild<DIM>(G))) return rc;
-    }
+    return MDB_OK;
+}
+
+// tail: forces (+ Brownian move), thermo scalars
+template <int DIM, bool KICK2>
+static int slab_tail(Group &G, int ensemble, double dt, double tau, double ktemp, int thermo, int advance, bool reduce_now)
+{
+    int rc;
     for (Engine *e : G) {
         PHASE(e, "before force");
         enqueue_force_slab<DIM, KICK2>(e, dt);
@@ -964,6 +1016,115 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
         enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 2);
         e->stats.kernel_launches += 1;
     }
+    return MDB_OK;
+}
+
+// make every rank's ghosts and neighbour structure current, then evaluate forces and the global thermo scalars (eager:
+// the rebuild decision is read back by the host)
+template <int DIM, bool KICK2>
+static int group_force_phase(Group &G, int ensemble, double dt, double tau, double ktemp, double, int thermo, int advance,
+                             bool reduce_now = true)
+{
+    int rc;
+    Engine *lead = G[0];
+    if ((rc = slab_head<DIM>(G, CondHandles{{0, 0, 0}, 0}))) return rc;
+    {
+        Engine *e = lead;
+        CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    if (lead->h_ctl->need_rebuild) {
+        if ((rc = group_rebuild<DIM>(G))) return rc;
+    }
+    return slab_tail<DIM, KICK2>(G, ensemble, dt, tau, ktemp, thermo, advance, reduce_now);
+}
+
+// One slab step as a CUDA graph.  NCCL calls cannot live inside conditional bodies (instantiation rejects them), so the
+// rebuild is cut at its two exchanges into three conditional bodies that share one decision; the exchanges themselves
+// run every step (with "nobody leaves" headers and an unchanged ghost set when there is no rebuild):
+//   kick-drift, pack, ghost exchange, all-reduce(max), decision | IF part1 | migration exchange | IF part2 |
+//   ghost exchange | IF part3 | forces, thermo.
+// Every rank replays the same graph; the all-reduced displacement bound makes the decision identical everywhere.
+template <int DIM>
+static int build_graph_slab(Group &G, const GraphKey &key, bool per_step_reduce)
+{
+    Engine *e = G[0];
+    drop_graph(e);
+    cudaStream_t s = e->stream;
+    CU(cudaGraphCreate(&e->graph, 0));
+    const bool conditional = (e->mode == MDB_MODE_LIST);
+    CondHandles hs{{0, 0, 0}, 0};
+    if (conditional) {
+        for (int q = 0; q < 3; q++) CU(cudaGraphConditionalHandleCreate(&hs.h[q], e->graph, 0, cudaGraphCondAssignDefault));
+        hs.n = 3;
+    }
+    int rc = MDB_OK;
+    cudaGraph_t g2 = nullptr;
+    auto abort_capture = [&](int code, const char *what = nullptr) {
+        cudaError_t last = cudaGetLastError();
+        if (what) e->err = std::string(what) + ": " + cudaGetErrorString(last);
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &st);
+        if (st != cudaStreamCaptureStatusNone) cudaStreamEndCapture(s, &g2);
+        cudaGetLastError();
+        drop_graph(e);
+        return code;
+    };
+    // close the current capture segment, hang a conditional node with `body` behind it, reopen the capture after it
+    auto conditional_section = [&](cudaGraphConditionalHandle h, int (*body)(Group &)) -> int {
+        if (!conditional) return body(G);
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t *d = nullptr;
+        size_t nd = 0;
+        if (cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &d, &nd) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamGetCaptureInfo");
+        std::vector<cudaGraphNode_t> deps(d, d + nd);
+        if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture");
+        cudaGraphNodeParams cp = {};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = h;
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        cudaGraphNode_t cnode;
+        if (cudaGraphAddNode(&cnode, e->graph, deps.data(), deps.size(), &cp) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaGraphAddNode");
+        cudaGraph_t bodyg = cp.conditional.phGraph_out[0];
+        if (cudaStreamBeginCaptureToGraph(s, bodyg, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+            return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph(body)");
+        int r = body(G);
+        if (r) return abort_capture(r);
+        if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture(body)");
+        if (cudaStreamBeginCaptureToGraph(s, e->graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+            return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph");
+        return MDB_OK;
+    };
+    CU(cudaStreamBeginCaptureToGraph(s, e->graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    if (key.ensemble != MDB_BROWNIAN)
+        for (Engine *g : G) k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, key.dt, g->ctl);
+    if ((rc = slab_head<DIM>(G, hs))) return abort_capture(rc);
+    for (Engine *g : G) k_slab_zero_headers<<<1, 1, 0, g->stream>>>(g->mig_send[0], g->mig_send[1]);
+    const bool multi_comm = e->transport == 2 && e->comm_seg[0] != nullptr;
+    if (e->transport == 2 && conditional && !multi_comm) return abort_capture(MDB_ERR_NCCL, nullptr);
+    auto select = [&](int which) {
+        for (Engine *g : G) g->comm_sel = multi_comm ? which : 0;
+    };
+    if ((rc = conditional_section(hs.h[0], rebuild_part1<DIM>))) return rc;
+    select(1);
+    rc = group_exchange(G, sizeof(MigRec) * (1 + (size_t)G[0]->mig_cap), mig_buf);
+    select(0);
+    if (rc) return abort_capture(rc);
+    if ((rc = conditional_section(hs.h[1], rebuild_part2<DIM>))) return rc;
+    select(2);
+    rc = group_send_ghosts(G);
+    select(0);
+    if (rc) return abort_capture(rc);
+    if ((rc = conditional_section(hs.h[2], rebuild_part3<DIM>))) return rc;
+    select(3);
+    if (key.ensemble != MDB_BROWNIAN) rc = slab_tail<DIM, true>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, per_step_reduce);
+    else rc = slab_tail<DIM, false>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, per_step_reduce);
+    select(0);
+    if (rc) return abort_capture(rc);
+    if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture");
+    if (cudaGraphInstantiate(&e->gexec, e->graph, 0) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaGraphInstantiate");
+    e->gkey = key;
     return MDB_OK;
 }
 
@@ -1012,8 +1173,26 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
     if (ensemble == MDB_NVT && (!ktemp_per_step || !(tau > 0))) return fail(lead, MDB_ERR_INVALID_ARG, "NVT needs ktemp_per_step and tau > 0");
     if (ensemble == MDB_BROWNIAN && !(ktemp > 0)) return fail(lead, MDB_ERR_INVALID_ARG, "Brownian needs ktemp > 0");
     cudaStream_t s = lead->stream;
-    CU(cudaEventRecord(lead->ev0, s));
     int rc;
+    // graph replay of the slab step (conditional rebuild with the NCCL exchanges captured inside): opt-in until validated
+    // on more systems; any failure to capture falls back to eager launches
+    bool use_graph = !lead->slab_graph_failed && getenv("MDB200_SLAB_GRAPH") != nullptr && !debug_sync();
+    if (use_graph) {
+        GraphKey key;
+        key.ensemble = ensemble; key.dt = dt; key.tau = tau; key.ktemp = ktemp; key.thermo = 1;
+        if (!(lead->gexec && lead->gkey == key)) {
+            int grc = build_graph_slab<DIM>(G, key, ensemble == MDB_NVT);
+            if (grc != MDB_OK) {
+                lead->slab_graph_failed = true;
+                use_graph = false;
+                for (int q = 0; q < 4; q++) cudaGetLastError();  // a failed capture must not poison the eager path
+            }
+            if (getenv("MDB200_VERBOSE"))
+                fprintf(stderr, "[mdb200] rank %d: slab step graph %s%s\n", lead->rank, grc == MDB_OK ? "captured" : "NOT captured, eager launches: ",
+                        grc == MDB_OK ? "" : lead->err.c_str());
+        }
+    }
+    CU(cudaEventRecord(lead->ev0, s));
     int64_t done = 0;
     while (done < nsteps) {
         int64_t m = std::min(lead->chunk, nsteps - done);
@@ -1024,6 +1203,9 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
         }
         // only the thermostat needs the global kinetic energy inside the step
         const bool per_step_reduce = (ensemble == MDB_NVT);
+        if (use_graph) {
+            for (int64_t q = 0; q < m; q++) CU(cudaGraphLaunch(lead->gexec, s));
+        } else
         for (int64_t q = 0; q < m; q++) {
             if (ensemble != MDB_BROWNIAN) {
                 for (Engine *g : G) {
@@ -1350,6 +1532,8 @@ MDB_EXPORT int mdb_destroy(mdb_handle e)
     free_stage(e);
     free_slab(e);
     if (e->user_lib) cudaLibraryUnload(e->user_lib);
+    for (int q = 0; q < 3; q++)
+        if (e->comm_seg[q] && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm_seg[q]);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->group) {
         // the ring is shared: detach this member; the last one out frees it
@@ -1448,6 +1632,7 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     if ((rc = ensure_stage(e, std::max<int64_t>(n_res, 1)))) return rc;
     if ((rc = alloc_neighbors(e))) return rc;
     if (e->slab && (rc = alloc_slab(e))) return rc;
+    if (e->group && (*e->group)[0]) drop_graph((*e->group)[0]);  // a captured ring step holds every member's buffers
     if (e->dim == 3) query_occupancy<3>(e);
     else query_occupancy<2>(e);
     cudaStream_t s = e->stream;
@@ -2022,6 +2207,17 @@ MDB_EXPORT int mdb_comm_init(mdb_handle e, const char *id)
     memcpy(&uid, id, sizeof(uid));
     NC(g_nccl.CommInitRank(&e->comm, e->nranks, uid, e->rank));
     e->transport = 2;
+    if (getenv("MDB200_SLAB_GRAPH")) {
+        // three more communicators for the later capture segments of the step graph; their ids travel over the first one
+        ncclUniqueId ids[3];
+        if (e->rank == 0)
+            for (int q = 0; q < 3; q++) NC(g_nccl.GetUniqueId(&ids[q]));
+        CU(cudaMemcpyAsync(e->d_thermo, ids, sizeof(ids), cudaMemcpyHostToDevice, e->stream));
+        NC(g_nccl.Broadcast(e->d_thermo, e->d_thermo, sizeof(ids), ncclInt8, 0, e->comm, e->stream));
+        CU(cudaMemcpyAsync(ids, e->d_thermo, sizeof(ids), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        for (int q = 0; q < 3; q++) NC(g_nccl.CommInitRank(&e->comm_seg[q], e->nranks, ids[q], e->rank));
+    }
     return MDB_OK;
 }
 

@@ -1124,8 +1124,12 @@ k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, 
 // rebuilt before the coming force evaluation, and drive the conditional graph node.
 // dmax2 holds the largest squared displacement of the move that just happened (scale = 1).
 // ------------------------------------------------------------------------------------------------
+struct CondHandles {  // a rebuild split into several conditional graph nodes (slab protocol) shares one decision
+    cudaGraphConditionalHandle h[3];
+    int n;
+};
 __global__ void k_skin_check(double scale, double skin, double skin_in, int always, int exact, DevCtl *ctl,
-                             cudaGraphConditionalHandle handle, int use_handle)
+                             cudaGraphConditionalHandle handle, int use_handle, CondHandles extra = CondHandles{{0, 0, 0}, 0})
 {
     double m = __longlong_as_double((long long)ctl->dmax2_bits);
     ctl->dmax2_bits = 0ull;  // consumed
@@ -1146,6 +1150,7 @@ __global__ void k_skin_check(double scale, double skin, double skin_in, int alwa
     ctl->disp_in = need_in ? 0.0 : disp_in;
     ctl->inner_refresh = need_in;
     if (use_handle) cudaGraphSetConditional(handle, need ? 1u : 0u);
+    for (int q = 0; q < extra.n; q++) cudaGraphSetConditional(extra.h[q], need ? 1u : 0u);
 }
 
 #endif  // !__CUDACC_RTC__

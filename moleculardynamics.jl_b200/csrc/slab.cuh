@@ -70,6 +70,13 @@ __global__ void k_slab_classify(DevCtl *ctl, Grid g, uint32_t *__restrict__ cell
     (dir == 0 ? out_l : out_r)[1 + k] = r;
 }
 
+// graph replay exchanges the migration buffers every step: without a rebuild they must say "nobody leaves"
+__global__ void k_slab_zero_headers(MigRec *out_l, MigRec *out_r)
+{
+    out_l[0].p.x = 0.0;
+    out_r[0].p.x = 0.0;
+}
+
 __global__ void k_slab_mig_headers(DevCtl *ctl, MigRec *out_l, MigRec *out_r, int mig_cap)
 {
     out_l[0].p.x = (double)min(ctl->mig_count[0], mig_cap);
