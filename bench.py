@@ -269,6 +269,9 @@ def main_slabs(args, rank, world, local_rank):
                           "algorithmic_bytes_per_particle_step": BYTES_STEP_3D},
         "cpu_baseline": None,
         "owned_per_rank": int(st1["n_owned"]),
+        "slab_phases_ms": ({"head_kick_pack_exchange_allreduce": st1["prof_kick_ms"] / max(st1["prof_steps"], 1),
+                            "tail_forces_thermo": st1["prof_force_ms"] / max(st1["prof_steps"], 1),
+                            "rebuild_per_step": st1["prof_rebuild_ms"] / max(st1["prof_steps"], 1)} if st1["prof_steps"] else None),
         "rebuilds_in_timed_region": int(st1["rebuilds"] - st0["rebuilds"]),
         "physics": {"T_mean": float(np.mean(2 * t_thermo[:, 2] / nf)), "U_per_particle": float(np.mean(t_thermo[:, 0]) / n),
                     "E_drift_rel": float((E.max() - E.min()) / abs(E[0])) if args.ensemble == "nve" else None,

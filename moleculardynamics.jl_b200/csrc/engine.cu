@@ -479,7 +479,7 @@ static ListView list_view(const Engine *e)
 }
 
 // kernels of a user-defined Potential live in an NVRTC-built library; same signatures as the templates in kernels.cuh
-static void launch_user_force(Engine *e, int n, int kick2, bool slab, double dt, int blocks)
+static void launch_user_force(Engine *e, int n, int kick2, bool slab, double dt, int blocks, int guard = 0)
 {
     cudaStream_t s = e->stream;
     ForceOut out{e->part};
@@ -496,13 +496,13 @@ static void launch_user_force(Engine *e, int n, int kick2, bool slab, double dt,
     } else if (e->mode == MDB_MODE_LIST) {
         ListView lv = list_view(e);
         double rwrap = e->r_grid + e->skin;
-        void *args[] = {&n, &ctl, &g, &lv, &cutoff2, &rwrap, &pot, &pp, &dt, &out};
+        void *args[] = {&n, &ctl, &g, &lv, &cutoff2, &rwrap, &pot, &pp, &dt, &out, &guard};
         cudaLaunchKernel((const void *)e->user_list[kick2][slab ? 1 : 0], dim3(blocks), dim3(kForceBlock), args, 0, s);
         int slot0 = blocks;
-        void *args2[] = {&cctl, &g, &start, &ovf, &cutoff2, &pot, &pp, &dt, &out, &slot0};
+        void *args2[] = {&cctl, &g, &start, &ovf, &cutoff2, &pot, &pp, &dt, &out, &slot0, &guard};
         cudaLaunchKernel((const void *)e->user_overflow[kick2], dim3(kOverflowGrid), dim3(kForceBlock), args2, 0, s);
     } else {
-        void *args[] = {&n, &cctl, &g, &start, &cutoff2, &pot, &pp, &dt, &out};
+        void *args[] = {&n, &cctl, &g, &start, &cutoff2, &pot, &pp, &dt, &out, &guard};
         cudaLaunchKernel((const void *)e->user_cells[kick2], dim3(blocks), dim3(kForceBlock), args, 0, s);
     }
 }
@@ -524,11 +524,11 @@ static void enqueue_force(Engine *e, double dt)
             k_force_brute<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->cutoff2, pot, e->pp, dt, out);
         else if (e->mode == MDB_MODE_LIST) {
             k_force_list<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
-                                                                       pot, e->pp, dt, out);
+                                                                       pot, e->pp, dt, out, 0);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
-                                                                                  e->pp, dt, out, blocks);
+                                                                                  e->pp, dt, out, blocks, 0);
         } else
-            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out);
+            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out, 0);
     });
 }
 template <int DIM>
@@ -579,11 +579,11 @@ static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHand
     k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, e->skin_in, always, exact, e->ctl, handle, use_handle);
 }
 
-static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance, int stage = 0)
+static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance, int stage = 0, int guard = 0)
 {
     double nf = e->dim * ((double)e->N - 1.0);  // src/initialization.jl:124
     k_finalize<<<1, kStreamBlock, 0, e->stream>>>(force_slots(e), e->part, ensemble, nf, dt, tau, e->d_ktemp, e->cfg.seed,
-                                                  thermo ? e->d_thermo : nullptr, advance, e->ctl, stage);
+                                                  thermo ? e->d_thermo : nullptr, advance, e->ctl, stage, guard);
 }
 
 // the part of one step before the (conditional) rebuild
@@ -615,7 +615,7 @@ static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, do
         if (prof) cudaEventRecord(e->evp[3], e->stream);
         if (prof) cudaEventRecord(e->evp[0], e->stream);
         k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed,
-                                                                      e->ctl, (e->mode == MDB_MODE_LIST && !e->brute) ? e->xref : nullptr);
+                                                                      e->ctl, (e->mode == MDB_MODE_LIST && !e->brute) ? e->xref : nullptr, 0);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
     }
@@ -952,13 +952,13 @@ static int rebuild_part3(Group &G)
 }
 
 template <int DIM, bool KICK2>
-static void enqueue_force_slab(Engine *e, double dt)
+static void enqueue_force_slab(Engine *e, double dt, int guard = 0)
 {
     cudaStream_t s = e->stream;
     ForceOut out{e->part};
     int blocks = force_grid(e);
     if (e->cfg.potential == MDB_POT_USER) {
-        launch_user_force(e, -1, KICK2 ? 1 : 0, true, dt, blocks);
+        launch_user_force(e, -1, KICK2 ? 1 : 0, true, dt, blocks, guard);
         e->stats.kernel_launches += force_kernel_count(e);
         return;
     }
@@ -966,11 +966,11 @@ static void enqueue_force_slab(Engine *e, double dt)
         typedef decltype(pot) Pot;
         if (e->mode == MDB_MODE_LIST) {
             k_force_list<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
-                                                                       pot, e->pp, dt, out);
+                                                                       pot, e->pp, dt, out, guard);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
-                                                                                  e->pp, dt, out, blocks);
+                                                                                  e->pp, dt, out, blocks, guard);
         } else {
-            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out);
+            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out, guard);
         }
     });
     e->stats.kernel_launches += force_kernel_count(e);
@@ -994,26 +994,27 @@ static int slab_head(Group &G, CondHandles hs)
 
 // tail: forces (+ Brownian move), thermo scalars
 template <int DIM, bool KICK2>
-static int slab_tail(Group &G, int ensemble, double dt, double tau, double ktemp, int thermo, int advance, bool reduce_now)
+static int slab_tail(Group &G, int ensemble, double dt, double tau, double ktemp, int thermo, int advance, bool reduce_now, int guard = 0)
 {
     int rc;
     for (Engine *e : G) {
         PHASE(e, "before force");
-        enqueue_force_slab<DIM, KICK2>(e, dt);
+        enqueue_force_slab<DIM, KICK2>(e, dt, guard);
         PHASE(e, "force");
         if (ensemble == MDB_BROWNIAN && advance) {
             k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(-1, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed, e->ctl,
-                                                                          nullptr);
+                                                                          nullptr, guard);
             e->stats.kernel_launches += 1;
         }
-        if (reduce_now) enqueue_finalize(e, ensemble, dt, tau, 0, 0, 1);
-        else enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 0);  // rank-local row; the chunk is all-reduced later
+        if (reduce_now) enqueue_finalize(e, ensemble, dt, tau, 0, 0, 1, guard);
+        else enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 0, guard);  // rank-local row; the chunk is all-reduced later
         e->stats.kernel_launches += 1;
     }
     if (!reduce_now) return MDB_OK;
+    // the collective itself always runs (every rank enqueues it); under a pending rebuild it moves stale numbers nobody reads
     if ((rc = group_allreduce(G, 4, false, [](Engine *e) { return e->ctl->red; }))) return rc;
     for (Engine *e : G) {
-        enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 2);
+        enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 2, guard);
         e->stats.kernel_launches += 1;
     }
     return MDB_OK;
@@ -1028,15 +1029,40 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
     int rc;
     Engine *lead = G[0];
     if ((rc = slab_head<DIM>(G, CondHandles{{0, 0, 0}, 0}))) return rc;
-    {
-        Engine *e = lead;
-        CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-    }
-    if (lead->h_ctl->need_rebuild) {
+    // The rebuild decision is read back by the host, but the GPU is not left idle meanwhile: the tail is enqueued
+    // speculatively behind the decision, guarded on the device (a pending rebuild turns its kernels into no-ops).  In
+    // the common case (no rebuild) the host returns from the read-back with the forces already running and goes on to
+    // enqueue the next step; otherwise it rebuilds and enqueues the tail again, unguarded.
+    static const bool slab_prof = getenv("MDB200_SLAB_PROF") != nullptr;  // per-phase CUDA-event totals, one sync per phase
+    const bool speculate = !debug_sync() && !slab_prof;
+    Engine *e = lead;
+    auto lap = [&](int a, int b, double &acc) -> int {  // close the phase [evp[a], evp[b]] and add its time to acc
+        float t = 0;
+        CU(cudaEventRecord(e->evp[b], e->stream));
+        CU(cudaEventSynchronize(e->evp[b]));
+        CU(cudaEventElapsedTime(&t, e->evp[a], e->evp[b]));
+        acc += t;
+        return MDB_OK;
+    };
+    // evp[5] was recorded at the start of the step: kick-drift + pack + ghost exchange + all-reduce + decision
+    if (slab_prof && (rc = lap(5, 1, e->stats.prof_kick_ms))) return rc;
+    CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(e->evp[0], e->stream));
+    if (speculate && (rc = slab_tail<DIM, KICK2>(G, ensemble, dt, tau, ktemp, thermo, advance, reduce_now, 1))) return rc;
+    CU(cudaEventSynchronize(e->evp[0]));
+    if (!e->h_ctl->need_rebuild && speculate) return MDB_OK;
+    if (e->h_ctl->need_rebuild) {
+        if (slab_prof) CU(cudaEventRecord(e->evp[2], e->stream));
         if ((rc = group_rebuild<DIM>(G))) return rc;
+        if (slab_prof && (rc = lap(2, 3, e->stats.prof_rebuild_ms))) return rc;
     }
-    return slab_tail<DIM, KICK2>(G, ensemble, dt, tau, ktemp, thermo, advance, reduce_now);
+    if (slab_prof) CU(cudaEventRecord(e->evp[2], e->stream));
+    if ((rc = slab_tail<DIM, KICK2>(G, ensemble, dt, tau, ktemp, thermo, advance, reduce_now, 0))) return rc;
+    if (slab_prof) {
+        if ((rc = lap(2, 3, e->stats.prof_force_ms))) return rc;
+        e->stats.prof_steps += 1;
+    }
+    return MDB_OK;
 }
 
 // One slab step as a CUDA graph.  NCCL calls cannot live inside conditional bodies (instantiation rejects them), so the
@@ -1174,6 +1200,8 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
     if (ensemble == MDB_BROWNIAN && !(ktemp > 0)) return fail(lead, MDB_ERR_INVALID_ARG, "Brownian needs ktemp > 0");
     cudaStream_t s = lead->stream;
     int rc;
+    lead->stats.prof_kick_ms = lead->stats.prof_force_ms = lead->stats.prof_rebuild_ms = 0.0;
+    lead->stats.prof_steps = 0;
     // graph replay of the slab step (conditional rebuild with the NCCL exchanges captured inside): opt-in until validated
     // on more systems; any failure to capture falls back to eager launches
     bool use_graph = !lead->slab_graph_failed && getenv("MDB200_SLAB_GRAPH") != nullptr && !debug_sync();
@@ -1207,6 +1235,7 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
             for (int64_t q = 0; q < m; q++) CU(cudaGraphLaunch(lead->gexec, s));
         } else
         for (int64_t q = 0; q < m; q++) {
+            CU(cudaEventRecord(lead->evp[5], s));
             if (ensemble != MDB_BROWNIAN) {
                 for (Engine *g : G) {
                     k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);

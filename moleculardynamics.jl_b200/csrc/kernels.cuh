@@ -564,8 +564,10 @@ __device__ __forceinline__ void cta_epilogue(const ThreadSums &acc, ForceOut out
 template <int DIM, class Pot, bool KICK2>
 __global__ void __launch_bounds__(kForceBlock)
 k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, double cutoff2, Pot pot, PotParams pp, double dt,
-              ForceOut out)
+              ForceOut out, int guard)
 {
+    // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
+    if (guard && ctl->need_rebuild) return;
     __shared__ uint32_t queue[kQueue][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
@@ -733,8 +735,10 @@ struct ListView {
 template <int DIM, class Pot, bool KICK2, bool SLAB>
 __global__ void __launch_bounds__(kForceBlock, MDB_FORCE_MIN_CTAS)
 k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt,
-             ForceOut out)
+             ForceOut out, int guard)
 {
+    // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
+    if (guard && ctl->need_rebuild) return;
     __shared__ uint32_t queue[kQueue][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
@@ -883,8 +887,9 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
 template <int DIM, class Pot, bool KICK2>
 __global__ void __launch_bounds__(kForceBlock)
 k_force_overflow(const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, const uint32_t *__restrict__ ovf,
-                 double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out, int slot0)
+                 double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out, int slot0, int guard)
 {
+    if (guard && ctl->need_rebuild) return;
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     const int novf = ctl->n_overflow;
@@ -1071,8 +1076,9 @@ __global__ void k_flip(DevCtl *ctl, const uint32_t *__restrict__ n_new)
 template <int DIM>
 __global__ void __launch_bounds__(kStreamBlock)
 k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, DevCtl *__restrict__ ctl,
-           const double *__restrict__ xref)
+           const double *__restrict__ xref, int guard)
 {
+    if (guard && ctl->need_rebuild) return;
     const StatePtrs s = ctl->st[ctl->cur];
     const unsigned long long rng_step = ctl->rng_step;
     if (n < 0) n = ctl->n_own;
@@ -1162,8 +1168,9 @@ __global__ void k_skin_check(double scale, double skin, double skin_in, int alwa
 // ------------------------------------------------------------------------------------------------
 __global__ void k_finalize(int nslots, const double *__restrict__ part, int ensemble, double nf, double dt, double tau,
                            const double *__restrict__ ktemp, uint64_t seed, double *__restrict__ thermo, int advance, DevCtl *ctl,
-                           int stage)
+                           int stage, int guard)
 {
+    if (guard && ctl->need_rebuild) return;
     // stage 0: single domain.  Slabs: stage 1 leaves this rank's sums in ctl->red for the all-reduce,
     // stage 2 continues from the globally summed ctl->red (identical on every rank).
     double r[4] = {0.0, 0.0, 0.0, 0.0};
