@@ -38,6 +38,9 @@ CUTOFF = 1.5
 BYTES_STEP_3D = 176.0
 # dominant kernel = K4 pair forces with fused second kick: reads x 24 + sigma 8 + v 24, writes f 24 + v 24
 BYTES_FORCE_KERNEL_3D = 104.0
+# fused NVE step (default in list mode): the same kernel also does the next step's kick-drift-wrap:
+# reads x 24 + sigma 8 + v 24, writes f 24 + v 24 + x 24 + sigma 8 (image counters only on a crossing)
+BYTES_FORCE_FUSED_3D = 136.0
 # K5 kick-drift-wrap: reads x 24 + sigma 8 (same 32 B record) + v 24 + f 24 + img 12, writes x 24 (+8) + v 24 + img 12
 BYTES_KICK_KERNEL_3D = 144.0
 
@@ -370,12 +373,15 @@ def main():
         rebuild_per_step = s2["prof_rebuild_ms"] / ksteps
         prof = {"kick_drift_ms": kick, "pair_force_ms": force, "rebuild_ms_per_step": rebuild_per_step,
                 "eager_steps": ksteps}
-        if force >= kick:
+        fused = st1["mode"] == 2 and args.ensemble == "nve" and not os.environ.get("MDB200_NO_FUSE")
+        if force >= kick and fused:
+            name, dur, bts = "k_force_list<KICK2=2>(pair forces + second kick + next step's kick-drift-wrap)", force, BYTES_FORCE_FUSED_3D
+        elif force >= kick:
             name, dur, bts = "k_force_list(pair forces + second kick)" if st1["mode"] == 2 else "k_force_cells", force, BYTES_FORCE_KERNEL_3D
         else:
             name, dur, bts = "k_kick_drift", kick, BYTES_KICK_KERNEL_3D
         achieved = bts * n / (dur * 1e-3) / 1e9
-        traffic = measured_traffic("k_kick_drift" if name == "k_kick_drift" else "k_force_list", n)
+        traffic = measured_traffic("k_kick_drift" if name == "k_kick_drift" else ("k_force_list_fused" if bts == BYTES_FORCE_FUSED_3D else "k_force_list"), n)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                     "traffic_source": "ncu --set full capture in profiles/ (dram read+write per launch)",
                     "kernel": name, "kernel_ms": dur, "algorithmic_bytes_per_particle": bts, "peak_source": peak_src}

@@ -79,7 +79,8 @@ typedef struct mdb_config {
     int32_t use_graph;      /* 1: replay each step as a CUDA graph (conditional rebuild node); 0: eager launches */
     int32_t rank;           /* slab decomposition along x: this handle owns x in [rank, rank+1) * Lx / nranks */
     int32_t nranks;         /* 1 = single domain */
-    int32_t reserved0;
+    int32_t no_fuse;        /* 0 (default): NVE runs in list mode fuse the next step's kick-drift into the force kernel
+                               (bit-identical results, one sweep less per step); 1: keep the reference's kernel order */
     double skin_inner;      /* skin of the inner (tight) list derived from the Verlet list; <= 0 picks a default */
     int32_t reserved[2];
 } mdb_config;

@@ -31,7 +31,7 @@ struct MdbConfig
     use_graph::Int32
     rank::Int32
     nranks::Int32
-    reserved0::Int32
+    no_fuse::Int32
     skin_inner::Float64
     reserved::NTuple{2,Int32}
 end

@@ -39,7 +39,7 @@ class Config(C.Structure):
     _fields_ = [("dim", C.c_int32), ("potential", C.c_int32), ("n_particles", C.c_int64), ("unitcell", C.c_double * 9),
                 ("cutoff", C.c_double), ("pot_params", C.c_double * 8), ("seed", C.c_uint64), ("device", C.c_int32),
                 ("mode", C.c_int32), ("skin", C.c_double), ("use_graph", C.c_int32), ("rank", C.c_int32),
-                ("nranks", C.c_int32), ("reserved0", C.c_int32), ("skin_inner", C.c_double), ("reserved", C.c_int32 * 2)]
+                ("nranks", C.c_int32), ("no_fuse", C.c_int32), ("skin_inner", C.c_double), ("reserved", C.c_int32 * 2)]
 
 
 class Stats(C.Structure):
@@ -142,7 +142,7 @@ class Engine:
     """Thin object wrapper over one mdb_handle (one GPU, one host thread)."""
 
     def __init__(self, dim, n_particles, box, cutoff, potential, pot_params=(), seed=0, device=0, mode=MODE_AUTO,
-                 skin=0.0, use_graph=True, rank=0, nranks=1, skin_inner=0.0):
+                 skin=0.0, use_graph=True, rank=0, nranks=1, skin_inner=0.0, no_fuse=False):
         L = load()
         cfg = Config()
         cfg.dim = dim
@@ -168,6 +168,7 @@ class Engine:
         cfg.skin = skin or 0.0
         cfg.skin_inner = skin_inner or 0.0
         cfg.use_graph = 1 if use_graph else 0
+        cfg.no_fuse = 1 if no_fuse else 0
         cfg.rank = rank
         cfg.nranks = nranks
         self._lib = L

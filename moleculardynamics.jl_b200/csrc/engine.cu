@@ -29,9 +29,10 @@ struct GraphKey {
     int ensemble = -1;
     double dt = 0, tau = 0, ktemp = 0;
     int thermo = 0;
+    int fused = 0;  // NVE with the next step's kick-drift fused into the force kernel (see kStepFused)
     bool operator==(const GraphKey &o) const
     {
-        return ensemble == o.ensemble && dt == o.dt && tau == o.tau && ktemp == o.ktemp && thermo == o.thermo;
+        return ensemble == o.ensemble && dt == o.dt && tau == o.tau && ktemp == o.ktemp && thermo == o.thermo && fused == o.fused;
     }
 };
 
@@ -81,6 +82,10 @@ struct mdb_engine_s {
 
     cudaGraphExec_t gexec = nullptr;
     cudaGraph_t graph = nullptr;
+    // fused NVE schedule: [1] = the last step of a run (no leading kick-drift, plain second kick); gexec/graph then
+    // hold the fused middle step
+    cudaGraphExec_t gexec_last = nullptr;
+    cudaGraph_t graph_last = nullptr;
     GraphKey gkey;
     int graph_kernels_fixed = 0, graph_kernels_rebuild = 0;
 
@@ -216,7 +221,9 @@ static void drop_graph(Engine *e)
 {
     if (e->gexec) cudaGraphExecDestroy(e->gexec);
     if (e->graph) cudaGraphDestroy(e->graph);
-    e->gexec = nullptr; e->graph = nullptr; e->gkey = GraphKey{};
+    if (e->gexec_last) cudaGraphExecDestroy(e->gexec_last);
+    if (e->graph_last) cudaGraphDestroy(e->graph_last);
+    e->gexec = nullptr; e->graph = nullptr; e->gexec_last = nullptr; e->graph_last = nullptr; e->gkey = GraphKey{};
 }
 
 // choose grid + neighbour strategy for the resident particle set
@@ -507,7 +514,8 @@ static void launch_user_force(Engine *e, int n, int kick2, bool slab, double dt,
     }
 }
 
-template <int DIM, bool KICK2>
+// KICK2: 0 forces only, 1 + second half kick, 2 + second half kick and the next step's kick-drift (list mode only)
+template <int DIM, int KICK2>
 static void enqueue_force(Engine *e, double dt)
 {
     cudaStream_t s = e->stream;
@@ -515,20 +523,20 @@ static void enqueue_force(Engine *e, double dt)
     ForceOut out{e->part};
     int blocks = force_grid(e);
     if (e->cfg.potential == MDB_POT_USER) {
-        launch_user_force(e, n, KICK2 ? 1 : 0, false, dt, blocks);
+        launch_user_force(e, n, KICK2 ? 1 : 0, false, dt, blocks);  // fused_step() excludes user potentials: KICK2 <= 1 here
         return;
     }
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         if (e->brute)
-            k_force_brute<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->cutoff2, pot, e->pp, dt, out);
+            k_force_brute<DIM, Pot, KICK2 != 0><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->cutoff2, pot, e->pp, dt, out);
         else if (e->mode == MDB_MODE_LIST) {
             k_force_list<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
                                                                        pot, e->pp, dt, out, 0);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
                                                                                   e->pp, dt, out, blocks, 0);
         } else
-            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out, 0);
+            k_force_cells<DIM, Pot, KICK2 != 0><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out, 0);
     });
 }
 template <int DIM>
@@ -551,10 +559,15 @@ static void query_occupancy(Engine *e)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_brute<DIM, Pot, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_brute<DIM, Pot, false>, kForceBlock, 0);
         } else if (e->mode == MDB_MODE_LIST) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, true, false>, kForceBlock, 0);
-            if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, true, true>, kForceBlock, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, false, false>, kForceBlock, 0);
-            if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, false, true>, kForceBlock, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, 1, false>, kForceBlock, 0);
+            if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, 1, true>, kForceBlock, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, 0, false>, kForceBlock, 0);
+            if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, 0, true>, kForceBlock, 0);
+            if (!e->slab) {
+                int c2 = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, false>, kForceBlock, 0);
+                a = std::min(a, c2);
+            }
         } else {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_cells<DIM, Pot, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_cells<DIM, Pot, false>, kForceBlock, 0);
@@ -579,20 +592,34 @@ static void enqueue_skin_check(Engine *e, double scale, cudaGraphConditionalHand
     k_skin_check<<<1, 1, 0, e->stream>>>(scale, e->skin, e->skin_in, always, exact, e->ctl, handle, use_handle);
 }
 
-static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance, int stage = 0, int guard = 0)
+static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int thermo, int advance, int stage = 0, int guard = 0,
+                             int swap_pos = 0)
 {
     double nf = e->dim * ((double)e->N - 1.0);  // src/initialization.jl:124
     k_finalize<<<1, kStreamBlock, 0, e->stream>>>(force_slots(e), e->part, ensemble, nf, dt, tau, e->d_ktemp, e->cfg.seed,
-                                                  thermo ? e->d_thermo : nullptr, advance, e->ctl, stage, guard);
+                                                  thermo ? e->d_thermo : nullptr, advance, e->ctl, stage, guard, swap_pos);
+}
+
+// Step schedules.  kStepFull is the reference's loop body (src/simulation.jl:88-108): kick-drift, [rebuild], forces + second
+// kick, thermo.  NVE runs in list mode rotate it: one kick-drift in front of the run, then kStepFused steps whose force
+// kernel also performs the NEXT step's kick-drift (KICK2 = 2, no K5 sweep at all), and a kStepLast that ends the run
+// with the plain second kick -- the state after n steps is bit-identical to n kStepFull steps.
+enum StepKind { kStepFull = 0, kStepFused = 1, kStepLast = 2 };
+static bool fused_step(const Engine *e, int ensemble)
+{
+    static const bool off = getenv("MDB200_NO_FUSE") != nullptr;
+    return ensemble == MDB_NVE && e->mode == MDB_MODE_LIST && !e->brute && !e->slab && e->cfg.potential != MDB_POT_USER &&
+           !e->cfg.no_fuse && !off;
 }
 
 // the part of one step before the (conditional) rebuild
 template <int DIM>
-static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphConditionalHandle handle, int use_handle, bool prof = false)
+static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphConditionalHandle handle, int use_handle, bool prof = false,
+                              int kind = kStepFull)
 {
     if (ensemble != MDB_BROWNIAN) {
         if (prof) cudaEventRecord(e->evp[0], e->stream);
-        k_kick_drift<DIM><<<kick_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl);
+        if (kind == kStepFull) k_kick_drift<DIM><<<kick_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, e->ctl);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_skin_check(e, 1.0, handle, use_handle);
     } else {
@@ -602,16 +629,18 @@ static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphCondi
 }
 // the part of one step after the rebuild
 template <int DIM>
-static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, double ktemp, int thermo, bool prof = false)
+static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, double ktemp, int thermo, bool prof = false,
+                              int kind = kStepFull)
 {
     if (ensemble != MDB_BROWNIAN) {
         if (prof) cudaEventRecord(e->evp[2], e->stream);
-        enqueue_force<DIM, true>(e, dt);
+        if (kind == kStepFused) enqueue_force<DIM, 2>(e, dt);
+        else enqueue_force<DIM, 1>(e, dt);
         if (prof) cudaEventRecord(e->evp[3], e->stream);
-        enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
+        enqueue_finalize(e, ensemble, dt, tau, thermo, 1, 0, 0, kind == kStepFused ? 1 : 0);
     } else {
         if (prof) cudaEventRecord(e->evp[2], e->stream);
-        enqueue_force<DIM, false>(e, dt);
+        enqueue_force<DIM, 0>(e, dt);
         if (prof) cudaEventRecord(e->evp[3], e->stream);
         if (prof) cudaEventRecord(e->evp[0], e->stream);
         k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed,
@@ -623,17 +652,32 @@ static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, do
 static int step_fixed_kernels(const Engine *e, int ensemble) { return 3 + force_kernel_count(e) + (ensemble == MDB_BROWNIAN ? 0 : 0); }
 
 template <int DIM>
+static int build_one_graph(Engine *e, const GraphKey &key, int kind, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out);
+template <int DIM>
 static int build_graph(Engine *e, const GraphKey &key)
 {
     drop_graph(e);
+    int rc;
+    if (key.fused) {
+        if ((rc = build_one_graph<DIM>(e, key, kStepFused, &e->graph, &e->gexec))) return rc;
+        if ((rc = build_one_graph<DIM>(e, key, kStepLast, &e->graph_last, &e->gexec_last))) return rc;
+    } else if ((rc = build_one_graph<DIM>(e, key, kStepFull, &e->graph, &e->gexec)))
+        return rc;
+    e->gkey = key;
+    return MDB_OK;
+}
+template <int DIM>
+static int build_one_graph(Engine *e, const GraphKey &key, int kind, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out)
+{
     cudaStream_t s = e->stream;
-    CU(cudaGraphCreate(&e->graph, 0));
+    cudaGraph_t &graph = *graph_out;
+    CU(cudaGraphCreate(&graph, 0));
     const bool conditional = (e->mode == MDB_MODE_LIST) && !e->brute;
     cudaGraphConditionalHandle handle = 0;
-    if (conditional) CU(cudaGraphConditionalHandleCreate(&handle, e->graph, 0, cudaGraphCondAssignDefault));
+    if (conditional) CU(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
     // head
-    CU(cudaStreamBeginCaptureToGraph(s, e->graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    enqueue_step_head<DIM>(e, key.ensemble, key.dt, handle, conditional ? 1 : 0);
+    CU(cudaStreamBeginCaptureToGraph(s, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    enqueue_step_head<DIM>(e, key.ensemble, key.dt, handle, conditional ? 1 : 0, false, kind);
     std::vector<cudaGraphNode_t> deps;
     if (conditional) {
         cudaStreamCaptureStatus status;
@@ -649,22 +693,21 @@ static int build_graph(Engine *e, const GraphKey &key)
         cp.conditional.type = cudaGraphCondTypeIf;
         cp.conditional.size = 1;
         cudaGraphNode_t cnode;
-        CU(cudaGraphAddNode(&cnode, e->graph, deps.data(), deps.size(), &cp));
+        CU(cudaGraphAddNode(&cnode, graph, deps.data(), deps.size(), &cp));
         cudaGraph_t body = cp.conditional.phGraph_out[0];
         CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
         enqueue_rebuild<DIM>(e);
         CU(cudaStreamEndCapture(s, &g2));
-        CU(cudaStreamBeginCaptureToGraph(s, e->graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
-        enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo);
+        CU(cudaStreamBeginCaptureToGraph(s, graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+        enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo, false, kind);
         CU(cudaStreamEndCapture(s, &g2));
     } else {
         enqueue_rebuild<DIM>(e);
-        enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo);
+        enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo, false, kind);
         cudaGraph_t g2 = nullptr;
         CU(cudaStreamEndCapture(s, &g2));
     }
-    CU(cudaGraphInstantiate(&e->gexec, e->graph, 0));
-    e->gkey = key;
+    CU(cudaGraphInstantiate(exec_out, graph, 0));
     return MDB_OK;
 }
 
@@ -1379,6 +1422,8 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
     cudaStream_t s = e->stream;
     GraphKey key;
     key.ensemble = ensemble; key.dt = dt; key.tau = tau; key.ktemp = ktemp; key.thermo = thermo ? 1 : 0;
+    const bool fused = fused_step(e, ensemble);
+    key.fused = fused ? 1 : 0;
     if (e->cfg.use_graph && !(e->gexec && e->gkey == key)) {
         int rc = build_graph<DIM>(e, key);
         if (rc) return rc;
@@ -1399,11 +1444,20 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
             CU(cudaMemcpyAsync(e->d_ktemp, ktemp_per_step + done, sizeof(double) * m, cudaMemcpyHostToDevice, s));
         CU(cudaMemsetAsync(&e->ctl->step, 0, sizeof(unsigned long long), s));
         for (int64_t q = 0; q < m; q++) {
+            // fused NVE schedule: the run's only stand-alone kick-drift, then fused steps, then a plain last step
+            int kind = kStepFull;
+            if (fused) {
+                kind = (done + q == nsteps - 1) ? kStepLast : kStepFused;
+                if (done + q == 0) {
+                    k_kick_drift<DIM><<<kick_grid(e), kStreamBlock, 0, s>>>(e->n, e->grid, dt, e->ctl);
+                    e->stats.kernel_launches += 1;
+                }
+            }
             if (e->cfg.use_graph) {
-                CU(cudaGraphLaunch(e->gexec, s));
+                CU(cudaGraphLaunch(kind == kStepLast ? e->gexec_last : e->gexec, s));
             } else {
                 // eager mode doubles as the profiling mode: CUDA events around each kernel group, one sync per step
-                enqueue_step_head<DIM>(e, ensemble, dt, 0, 0, true);
+                enqueue_step_head<DIM>(e, ensemble, dt, 0, 0, true, kind);
                 bool rebuilt = true;
                 if (e->mode == MDB_MODE_LIST && !e->brute) {
                     CU(cudaMemcpyAsync(&e->h_ctl->need_rebuild, &e->ctl->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1413,7 +1467,7 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
                 CU(cudaEventRecord(e->evp[4], s));
                 if (rebuilt) enqueue_rebuild<DIM>(e);
                 CU(cudaEventRecord(e->evp[5], s));
-                enqueue_step_tail<DIM>(e, ensemble, dt, tau, ktemp, key.thermo, true);
+                enqueue_step_tail<DIM>(e, ensemble, dt, tau, ktemp, key.thermo, true, kind);
                 CU(cudaStreamSynchronize(s));
                 float t = 0;
                 CU(cudaEventElapsedTime(&t, e->evp[0], e->evp[1]));
@@ -1450,7 +1504,7 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
     unsigned long long nreb = e->h_ctl->rebuilds - rebuilds0;
     e->stats.steps += nsteps;
     e->stats.rebuilds = (int64_t)e->h_ctl->rebuilds;
-    e->stats.kernel_launches += nsteps * step_fixed_kernels(e, ensemble) + (int64_t)nreb * rebuild_kernel_count(e);
+    e->stats.kernel_launches += nsteps * (step_fixed_kernels(e, ensemble) - (fused ? 1 : 0)) + (int64_t)nreb * rebuild_kernel_count(e);
     e->stats.max_neighbors = e->h_ctl->max_nnbr;
     e->rng_step = e->h_ctl->rng_step;
     if (e->mode == MDB_MODE_LIST && (e->h_ctl->max_nnbr > e->kmax || e->h_ctl->max_nnbr_in > e->kmax_in)) {
@@ -2158,10 +2212,10 @@ MDB_EXPORT int mdb_set_user_potential(mdb_handle e, const char *body, const doub
     const std::string D = std::to_string(e->dim);
     std::vector<std::string> names;
     for (int k = 0; k < 2; k++) {
-        std::string kk = k ? "true" : "false";
-        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + kk + ", false>");
-        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + kk + ", true>");
-        names.push_back("mdb::k_force_overflow<" + D + ", mdb::PotUser, " + kk + ">");
+        std::string kk = k ? "true" : "false", ki = k ? "1" : "0";
+        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + ki + ", false>");
+        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + ki + ", true>");
+        names.push_back("mdb::k_force_overflow<" + D + ", mdb::PotUser, " + ki + ">");
         names.push_back("mdb::k_force_cells<" + D + ", mdb::PotUser, " + kk + ">");
         names.push_back("mdb::k_force_brute<" + D + ", mdb::PotUser, " + kk + ">");
     }

@@ -543,6 +543,43 @@ __device__ __forceinline__ void particle_epilogue(int i, const double (&F)[3], c
     }
 }
 
+// Fused NVE step (KICK2 == 2): second half kick of this step, then the NEXT step's first half kick, drift and wrap
+// (k_kick_drift's arithmetic, operation for operation: src/integrate.jl:8-38, src/boundary.jl:7-17) while F, v and x are
+// still in registers.  The moved position goes to the other position buffer (neighbours still read this step's
+// positions from the live one); k_finalize swaps the two pointers afterwards.  Saves the whole K5 sweep of the next step.
+template <int DIM>
+__device__ __forceinline__ void leap_epilogue(int i, const double (&F)[3], const double (&vel)[3], const double4 &pi, const StatePtrs &s,
+                                              double4 *__restrict__ pos_next, const Grid &g, double dt, double &ke2, double &vmax2)
+{
+    double x[3] = {pi.x, pi.y, pi.z};
+    double v2 = 0.0, w2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        const double h = (F[k] * dt) * 0.5;
+        double v = vel[k] + h;  // v(t + dt): the kinetic energy of this step (src/thermostat.jl:50-60)
+        v2 = (k == 0) ? v * v : v2 + v * v;
+        v += h;                 // next step's first half kick (alpha == 1 in NVE)
+        s.vel[k * s.cap + i] = v;
+        w2 = (k == 0) ? v * v : w2 + v * v;
+        double xv = x[k] + v * dt;
+        double frac = g.invL[k] * xv;
+        double ncr = floor(frac);
+        if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
+        x[k] = g.L[k] * (frac - ncr);
+    }
+    st_pos(&pos_next[i], make_double4(x[0], x[1], x[2], pi.w));
+    ke2 += v2;
+    vmax2 = fmax(vmax2, w2);
+}
+// displacement bound of the fused move, folded like k_kick_drift does
+template <int BLOCK>
+__device__ __forceinline__ void leap_report(double vmax2, double dt, DevCtl *ctl)
+{
+    double r[1] = {vmax2 * (dt * dt)};
+    block_reduce<1, BLOCK, true>(r);
+    if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
+}
+
 // one deterministic CTA reduction at the end of the persistent loop
 __device__ __forceinline__ void cta_epilogue(const ThreadSums &acc, ForceOut out, int slot)
 {
@@ -732,7 +769,8 @@ struct ListView {
 };
 
 // SLAB: neighbour indices >= g.g0 address the ghost buffer of an x-slab (single domain: no such indices, no select)
-template <int DIM, class Pot, bool KICK2, bool SLAB>
+// KICK2: 0 forces only, 1 + second half kick, 2 + second half kick and the next step's kick-drift-wrap (leap_epilogue)
+template <int DIM, class Pot, int KICK2, bool SLAB>
 __global__ void __launch_bounds__(kForceBlock, MDB_FORCE_MIN_CTAS)
 k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt,
              ForceOut out, int guard)
@@ -742,6 +780,8 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     __shared__ uint32_t queue[kQueue][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
+    double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 == 2 only
+    double vmax2 = 0.0;
     const bool refresh = ctl->inner_refresh != 0;  // uniform over the grid
     const uint32_t *__restrict__ nl = refresh ? lv.nl : lv.nl_in;
     const int32_t *__restrict__ nnbr = refresh ? lv.nnbr : lv.nnbr_in;
@@ -860,7 +900,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         if (active) {
 #pragma unroll
             for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
-            if (KICK2) {
+            if (KICK2 == 1) {
                 double v2 = 0.0;
 #pragma unroll
                 for (int k = 0; k < DIM; k++) {
@@ -871,8 +911,10 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 }
                 acc.v2 += v2;
             }
+            if (KICK2 == 2) leap_epilogue<DIM>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
         }
     }
+    if (KICK2 == 2) leap_report<kForceBlock>(vmax2, dt, ctl);
     if (refresh) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) max_in = max(max_in, __shfl_xor_sync(0xffffffffu, max_in, o));
@@ -884,15 +926,17 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
 // list overflow (more than kmax neighbours within r_list): exact fallback through the stale-but-conservative
 // build-time cells.  Slot order is the build-time cell order, so the home cell is found by bisection on `start`.
 // One warp-lane per overflowing particle; normally the overflow list is empty and this kernel exits at once.
-template <int DIM, class Pot, bool KICK2>
+template <int DIM, class Pot, int KICK2>
 __global__ void __launch_bounds__(kForceBlock)
-k_force_overflow(const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, const uint32_t *__restrict__ ovf,
+k_force_overflow(DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ start, const uint32_t *__restrict__ ovf,
                  double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out, int slot0, int guard)
 {
     if (guard && ctl->need_rebuild) return;
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     const int novf = ctl->n_overflow;
+    double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 == 2 only
+    double vmax2 = 0.0;
     ThreadSums acc;
     for (int q = blockIdx.x * kForceBlock + threadIdx.x; q < novf; q += gridDim.x * kForceBlock) {
         const int i = (int)ovf[q];
@@ -913,8 +957,18 @@ k_force_overflow(const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restr
             if (d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj.w))
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
         });
-        particle_epilogue<DIM, KICK2>(i, F, s, dt, acc);
+        if (KICK2 == 2) {
+            double vel[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                s.frc[k * s.cap + i] = F[k];
+                vel[k] = s.vel[k * s.cap + i];
+            }
+            leap_epilogue<DIM>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
+        } else
+            particle_epilogue<DIM, KICK2 != 0>(i, F, s, dt, acc);
     }
+    if (KICK2 == 2 && novf > 0) leap_report<kForceBlock>(vmax2, dt, ctl);  // novf is grid-uniform
     cta_epilogue(acc, out, slot0 + blockIdx.x);
 }
 
@@ -1168,9 +1222,15 @@ __global__ void k_skin_check(double scale, double skin, double skin_in, int alwa
 // ------------------------------------------------------------------------------------------------
 __global__ void k_finalize(int nslots, const double *__restrict__ part, int ensemble, double nf, double dt, double tau,
                            const double *__restrict__ ktemp, uint64_t seed, double *__restrict__ thermo, int advance, DevCtl *ctl,
-                           int stage, int guard)
+                           int stage, int guard, int swap_pos = 0)
 {
     if (guard && ctl->need_rebuild) return;
+    // fused NVE step: the force kernels wrote the moved positions into the other buffer; make it the live one
+    if (swap_pos && threadIdx.x == 0) {
+        double4 *t = ctl->st[0].pos;
+        ctl->st[0].pos = ctl->st[1].pos;
+        ctl->st[1].pos = t;
+    }
     // stage 0: single domain.  Slabs: stage 1 leaves this rank's sums in ctl->red for the all-reduce,
     // stage 2 continues from the globally summed ctl->red (identical on every rank).
     double r[4] = {0.0, 0.0, 0.0, 0.0};

@@ -53,6 +53,30 @@ def test_graph_and_eager_are_bit_identical(md, orc):
     assert out[0][2]["rebuilds"] == out[1][2]["rebuilds"] > 1
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_nve_step_is_bit_identical_to_reference_order(md, orc, use_graph):
+    """NVE list-mode runs fold the next step's kick-drift into the force kernel (no K5 sweep); positions, velocities,
+    forces, images and every thermo row must equal the reference's kernel order (no_fuse) bit for bit, for any split of
+    the run into calls (1-step calls exercise first-step == last-step), across list rebuilds."""
+    from mdjl_b200 import workloads
+    n = 4096
+    cfg = workloads.phs_fluid(n)
+    v0 = workloads.velocities(n, 3, 1.4737)
+    out = []
+    for no_fuse in (True, False):
+        e = md.Engine(3, n, cfg["box"], 1.5, md._capi.POT_PSEUDOHS, seed=99, mode=md._capi.MODE_LIST, use_graph=use_graph, no_fuse=no_fuse)
+        e.upload(cfg["x"], cfg["diam"], velocities=v0)
+        rows = [e.run_nve(k, 1e-3) for k in (1, 2, 1, 157, 40)]
+        out.append((np.concatenate(rows), e.download(), e.stats()))
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    assert out[0][2]["rebuilds"] == out[1][2]["rebuilds"] > 1
+    # one kick-drift launch per run call instead of one per step
+    assert out[1][2]["kernel_launches"] < out[0][2]["kernel_launches"]
+
+
 def test_list_mode_equals_cell_mode(md, orc):
     """same pair set every step: pair counts identical, energies to rounding, over several list rebuilds"""
     res = {}
