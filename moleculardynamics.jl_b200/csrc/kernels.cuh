@@ -493,25 +493,42 @@ __device__ __forceinline__ const double4 *nbr_ptr(const Grid &g, const double4 *
 
 // per-pair update: src/pairwise.jl:26-39 (one side of it: the gather evaluates each pair from both ends,
 // the antisymmetric halves are bit-exact negatives, energy/virial/pair-count totals are halved at the end)
+// pair_force: the vector s = f*r/d of one pair and its energy / virial / count terms
+template <int DIM, class Pot>
+__device__ __forceinline__ void pair_force(const Pot &pot, const PotParams &pp, double dx, double dy, double dz, double d2, double si,
+                                           double sj, double &sx, double &sy, double &sz, double &e, double &w, double &np)
+{
+    double d = sqrt(d2);
+    double u, f;
+    bool in;
+    sz = 0.0;
+    if constexpr (has_rcp_eval<Pot>::value) {
+        const double r = rcp_refined(d);  // (f*r_k)/d and sigma/d share one reciprocal: same bits as four IEEE divisions
+        in = pot.eval_rcp(pp, d, r, si, sj, u, f);
+        sx = div_by(f * dx, d, r);
+        sy = div_by(f * dy, d, r);
+        if (DIM == 3) sz = div_by(f * dz, d, r);
+    } else {
+        in = pot.eval(pp, d, si, sj, u, f);
+        sx = (f * dx) / d;
+        sy = (f * dy) / d;
+        if (DIM == 3) sz = (f * dz) / d;
+    }
+    double dot = sx * dx + sy * dy;
+    if (DIM == 3) dot += sz * dz;
+    w += dot;
+    e += u;
+    np += in ? 1.0 : 0.0;
+}
 template <int DIM, class Pot>
 __device__ __forceinline__ void pair_accumulate(const Pot &pot, const PotParams &pp, double dx, double dy, double dz, double d2,
                                                 double si, double sj, double (&F)[3], double &e, double &w, double &np)
 {
-    double d = sqrt(d2);
-    double u, f;
-    bool in = pot.eval(pp, d, si, sj, u, f);
-    double sx = (f * dx) / d, sy = (f * dy) / d;
-    double dot = sx * dx + sy * dy;
+    double sx, sy, sz;
+    pair_force<DIM>(pot, pp, dx, dy, dz, d2, si, sj, sx, sy, sz, e, w, np);
     F[0] += sx;
     F[1] += sy;
-    if (DIM == 3) {
-        double sz = (f * dz) / d;
-        dot += sz * dz;
-        F[2] += sz;
-    }
-    w += dot;
-    e += u;
-    np += in ? 1.0 : 0.0;
+    if (DIM == 3) F[2] += sz;
 }
 
 struct ForceOut {
@@ -742,12 +759,17 @@ __device__ __forceinline__ double separation_plain(const double4 &pi, const doub
 }
 
 #ifndef MDB_UNROLL
-#define MDB_UNROLL 4  // tools/tune_force.py on B200: 4 -> 80 regs, 6 CTAs/SM; 8 -> 128 regs and 35% slower
+#define MDB_UNROLL 2  // tools/tune_force.py on B200: the inner list holds ~2 candidates; 2 -> no spills at 72 registers
+                      // (4 spilled 176 B per thread and the spills missed L1: ncu saw more local than global L2 sectors)
 #endif
 #ifndef MDB_FORCE_MIN_CTAS
-#define MDB_FORCE_MIN_CTAS 6  // 80 registers (a few spilled words) and 24 warps/SM beat 122 registers and 16 warps/SM by 7%
+#define MDB_FORCE_MIN_CTAS 7  // 72 registers, 28 warps/SM
 #endif
 constexpr int kUnroll = MDB_UNROLL;  // independent neighbour gathers in flight per thread
+#ifndef MDB_PARK
+#define MDB_PARK 1    // 0: evaluate every hit where the list walk finds it (no queue, no second gather)
+#endif
+
 
 // Two-level Verlet list + software pipelining.
 //  * outer list (radius r_search + skin): built from the cells, ~8 candidates per particle for PseudoHS at phi = 0.47;
@@ -777,7 +799,8 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
 {
     // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
     if (guard && ctl->need_rebuild) return;
-    __shared__ uint32_t queue[kQueue][kForceBlock];
+    constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0);  // park hits in a queue, or evaluate them where they are found
+    __shared__ uint32_t queue[kPark ? kQueue : 1][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 == 2 only
@@ -792,20 +815,24 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
     int max_in = 0;
     // prologue: first tile's operands
+    // grid-strided tiles: CTAs that run at the same time work on adjacent tiles, so one SM's gathers are another's L2
+    // hits (a contiguous range of tiles per CTA measured 24% slower)
     int tile = blockIdx.x;
+    const int tile_end = ntiles;
+    const int tile_step = gridDim.x;
     int i = tile * kForceBlock + threadIdx.x;
     double4 pi_n = make_double4(0, 0, 0, 1);
     int cnt_n = 0;
     uint32_t jn[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; u++) jn[u] = 0;
-    if (tile < ntiles && i < n) {
+    if (tile < tile_end && i < n) {
         pi_n = pos[i];
         cnt_n = nnbr[i];
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)u * stride + i];  // rows < kUnroll always exist
     }
-    for (; tile < ntiles; tile += gridDim.x) {
+    for (; tile < tile_end; tile += tile_step) {
         i = tile * kForceBlock + threadIdx.x;
         bool active = i < n;
         const double4 pi = pi_n;
@@ -820,10 +847,10 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
             for (int k = 0; k < DIM; k++) vel[k] = s.vel[k * s.cap + i];
         }
         {
-            const int tn = tile + gridDim.x;
+            const int tn = tile + tile_step;
             const int in = tn * kForceBlock + threadIdx.x;
             cnt_n = 0;
-            if (tn < ntiles && in < n) {
+            if (tn < tile_end && in < n) {
                 pi_n = pos[in];
                 cnt_n = nnbr[in];
 #pragma unroll
@@ -849,12 +876,14 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
         bool wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
         if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
+        const bool wrap_any = __any_sync(0xffffffffu, wrap);  // warp-uniform: the wrapped separation is exact for every pair
         auto drain_one = [&]() {
             if (nq > 0) {
                 int j = (int)queue[--nq][threadIdx.x];
                 double4 pj = ldg_pos(SLAB ? nbr_ptr(g, pos, (uint32_t)j) : pos + j);
-                double dx, dy, dz;
-                double d2 = wrap ? separation_wrap<DIM>(g, pi, pj, dx, dy, dz) : separation_plain<DIM>(pi, pj, dx, dy, dz);
+                double dx, dy, dz, d2;
+                if (wrap_any) d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
+                else d2 = separation_plain<DIM>(pi, pj, dx, dy, dz);
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
         };
@@ -863,8 +892,11 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
             uint32_t jc[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
-                jc[u] = (k0 + u < cnt) ? jj[u] : (uint32_t)i;
-                pj[u] = ldg_pos(SLAB ? nbr_ptr(g, pos, jc[u]) : pos + jc[u]);
+                // slots past the end of this particle's list issue no load at all: the kernel is bound by L1 wavefronts
+                // (ncu: 74% of the LSU data pipe), and a dummy gather costs a sector per lane like a real one
+                jc[u] = jj[u];
+                pj[u] = make_double4(0.0, 0.0, 0.0, 1.0);
+                if (k0 + u < cnt) pj[u] = ldg_pos(SLAB ? nbr_ptr(g, pos, jc[u]) : pos + jc[u]);
             }
             // next index chunk travels while the gathers above are in flight
             if (k0 + kUnroll < cnt) {
@@ -882,15 +914,15 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                     nin++;
                 }
                 if (valid && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
-                    if (Pot::kSparseHits) queue[nq++][threadIdx.x] = jc[u];
+                    if (kPark) queue[nq++][threadIdx.x] = jc[u];
                     else pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj[u].w, F, acc.e, acc.w, acc.np);
                 }
             }
-            if (Pot::kSparseHits && nq > kQueue - kUnroll) {
+            if (kPark && nq > kQueue - kUnroll) {
                 while (nq > 0) drain_one();
             }
         }
-        if (Pot::kSparseHits) {
+        if (kPark) {
             while (__any_sync(0xffffffffu, nq > 0)) drain_one();
         }
         if (write_inner && i < n) {
