@@ -293,7 +293,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 24)
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=1 << 24, help="under torchrun use --particles (--n is ambiguous to its parser)")
     ap.add_argument("--melt", type=int, default=1500)
     ap.add_argument("--mode", default="auto", choices=["auto", "cells", "list"])
     ap.add_argument("--skin", type=float, default=0.0)

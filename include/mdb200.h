@@ -41,7 +41,8 @@ enum mdb_status {
     MDB_ERR_NCCL = 7,
     MDB_ERR_STATE = 8,                 /* e.g. run before velocities were set */
     MDB_ERR_NONFINITE = 9,             /* overlap / blow-up detected: non-finite energy */
-    MDB_ERR_NVRTC = 10
+    MDB_ERR_NVRTC = 10,
+    MDB_ERR_IO = 11                    /* frame / checkpoint file could not be written or read */
 };
 
 /* Potential subtype -> device functor tag (src/potentials.jl, README.md:82-145) */
@@ -190,6 +191,35 @@ int mdb_comm_unique_id(char id[128]);
 int mdb_comm_init(mdb_handle h, const char id[128]);
 /* in-process ring of handles on the same device (tests / single-GPU emulation of the slab protocol; no NCCL) */
 int mdb_comm_init_local(mdb_handle *handles, int32_t count);
+
+/* ---- trajectory frames: the step after the path --------------------------------------- */
+/* Replaces the reads of positions and images by write_to_file_lammps (src/io.jl:78-170) at its call sites in the step loop
+ * (src/simulation.jl:139-171).  mdb_frame_capture packs, on the device and in ORIGINAL particle order, one record per
+ * particle {radius = diameter/2, x[dim] wrapped, xu[dim] = x + U*img (unwrapped, src/io.jl:62-70)} into frame slot
+ * `slot` (0 .. MDB_FRAME_SLOTS-1) and starts its copy to pinned host memory on a second stream; it returns without waiting,
+ * so the step loop continues while the frame travels (nranks == 1). */
+#define MDB_FRAME_SLOTS 2
+int mdb_frame_capture(mdb_handle h, int32_t slot);
+/* waits for the copy; *frame = library-owned pinned array [n_particles][*width], *width = 2*dim + 1; valid until the next
+ * capture into the slot */
+int mdb_frame_wait(mdb_handle h, int32_t slot, const double **frame, int32_t *width);
+/* queues the frame for a background thread of the library that formats it exactly like write_to_file_lammps (same header
+ * lines and "%lf" columns, src/io.jl:97-167; append != 0 is mode="a") and returns at once; a later capture into the slot
+ * waits until the file is written */
+int mdb_frame_write_lammps(mdb_handle h, int32_t slot, const char *path, int64_t step, int32_t append);
+/* blocks until every queued frame is on disk; reports the first I/O error (MDB_ERR_IO) */
+int mdb_frame_flush(mdb_handle h);
+
+/* ---- device-side set-up and exact restart: the step before the path -------------------- */
+/* state.velocities = initialize_velocities(ktemp, rng, N, dim) (src/initialization.jl:32-47) on the device: standard normals
+ * from the counter-based RNG keyed by (seed, original particle id, stream), centre-of-mass motion removed, rescaled so
+ * that sum(v^2) / ((N-1) dim) == ktemp (nranks == 1) */
+int mdb_init_velocities(mdb_handle h, double ktemp, uint64_t stream);
+/* Exact binary checkpoint: positions, velocities, forces, images and ids in device slot order plus the RNG step counter.
+ * Saving invalidates the resident Verlet list, so the saved run and a run restored with mdb_checkpoint_load on a handle
+ * created with the same mdb_config continue bit-identically (nranks == 1). */
+int mdb_checkpoint_save(mdb_handle h, const char *path);
+int mdb_checkpoint_load(mdb_handle h, const char *path);
 
 /* ---- introspection ------------------------------------------------------------------------------------ */
 int mdb_get_stats(mdb_handle h, mdb_stats *out);

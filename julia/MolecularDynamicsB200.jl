@@ -175,6 +175,15 @@ function run_chunk!(sys::GPUSystem, ens::Brownian, params, steps, first_step)
     return t
 end
 
+# initialize_velocities (src/initialization.jl:32-47) on the device; `stream` selects an independent set of draws
+init_velocities!(sys::GPUSystem, ktemp::Float64; stream::Integer=0) =
+    check(sys.handle, ccall((:mdb_init_velocities, libmdb), Cint, (Handle, Float64, UInt64), sys.handle, ktemp, UInt64(stream)))
+# exact binary restart: the saved run and a run restored from the file continue bit-identically
+save_checkpoint(sys::GPUSystem, path::String) =
+    check(sys.handle, ccall((:mdb_checkpoint_save, libmdb), Cint, (Handle, Cstring), sys.handle, path))
+load_checkpoint!(sys::GPUSystem, path::String) =
+    check(sys.handle, ccall((:mdb_checkpoint_load, libmdb), Cint, (Handle, Cstring), sys.handle, path))
+
 """
     run_simulation!(state::SimulationState{<:GPUSystem}, params, ensemble, total_steps, frequency, pathname; ...)
 
@@ -210,10 +219,16 @@ function MolecularDynamics.run_simulation!(state::SimulationState{<:GPUSystem}, 
                    W / (D * volume) + params.ρ * T + pressure_lrc(params.potential, N, volume))
         end
         open(io -> Printf.format(io, Printf.Format("%d %.6f %.6f %.6f\n"), row...), thermo_file, "a")
-        x, _, _, img = download(sys; velocities=false, forces=false)
-        write_to_file_lammps(trajectory_file, step, state.unitcell, N, x, img, state.diameters, D; mode="a")
+        # write_to_file_lammps (src/io.jl:78-170) without bringing the state back: the frame (unwrapped coordinates
+        # included) is packed on the device, copied on the engine's copy stream and written by its background thread
+        # while the next chunk of steps runs
+        slot = Int32(mod(fld(step, frequency), 2))
+        check(sys.handle, ccall((:mdb_frame_capture, libmdb), Cint, (Handle, Int32), sys.handle, slot))
+        check(sys.handle, ccall((:mdb_frame_write_lammps, libmdb), Cint, (Handle, Int32, Cstring, Int64, Int32),
+            sys.handle, slot, trajectory_file, step, 1))
     end
     done < total_steps && run_chunk!(sys, ensemble, params, done:(total_steps - 1), done)
+    check(sys.handle, ccall((:mdb_frame_flush, libmdb), Cint, (Handle,), sys.handle))
     _, v, _, img = download(sys; positions=false, forces=false)
     ensemble isa Brownian || (state.velocities = v)
     state.images = img

@@ -11,10 +11,10 @@ from . import _build
 
 # enum mdb_status
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED_POTENTIAL, ERR_UNSUPPORTED_CELL, ERR_BOX_TOO_SMALL = 0, 1, 2, 3, 4, 5
-ERR_NO_DEVICE, ERR_NCCL, ERR_STATE, ERR_NONFINITE, ERR_NVRTC = 6, 7, 8, 9, 10
+ERR_NO_DEVICE, ERR_NCCL, ERR_STATE, ERR_NONFINITE, ERR_NVRTC, ERR_IO = 6, 7, 8, 9, 10, 11
 STATUS_NAMES = {0: "MDB_OK", 1: "MDB_ERR_INVALID_ARG", 2: "MDB_ERR_CUDA", 3: "MDB_ERR_UNSUPPORTED_POTENTIAL",
                 4: "MDB_ERR_UNSUPPORTED_CELL", 5: "MDB_ERR_BOX_TOO_SMALL", 6: "MDB_ERR_NO_DEVICE", 7: "MDB_ERR_NCCL",
-                8: "MDB_ERR_STATE", 9: "MDB_ERR_NONFINITE", 10: "MDB_ERR_NVRTC"}
+                8: "MDB_ERR_STATE", 9: "MDB_ERR_NONFINITE", 10: "MDB_ERR_NVRTC", 11: "MDB_ERR_IO"}
 POT_PSEUDOHS, POT_LJ, POT_LJ_XPLOR, POT_POLY, POT_USER = 0, 1, 2, 3, 100
 NVE, NVT, BROWNIAN = 0, 1, 2
 MODE_AUTO, MODE_CELLS, MODE_LIST, MODE_SMALL = 0, 1, 2, 3
@@ -26,7 +26,10 @@ SYMBOLS = [
     "mdb_thermo", "mdb_fire_minimize", "mdb_bussi_scale_from", "mdb_bussi_noises", "mdb_get_rng_step",
     "mdb_set_rng_step", "mdb_set_user_potential", "mdb_comm_unique_id", "mdb_comm_init", "mdb_comm_init_local",
     "mdb_get_stats", "mdb_device_ptr", "mdb_stream", "mdb_synchronize",
+    "mdb_frame_capture", "mdb_frame_wait", "mdb_frame_write_lammps", "mdb_frame_flush",
+    "mdb_init_velocities", "mdb_checkpoint_save", "mdb_checkpoint_load",
 ]
+FRAME_SLOTS = 2
 
 
 class MdbError(RuntimeError):
@@ -105,6 +108,13 @@ def load():
     L.mdb_device_ptr.argtypes = [_H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.mdb_stream.argtypes = [_H, C.POINTER(C.c_void_p)]
     L.mdb_synchronize.argtypes = [_H]
+    L.mdb_frame_capture.argtypes = [_H, C.c_int32]
+    L.mdb_frame_wait.argtypes = [_H, C.c_int32, C.POINTER(_dp), C.POINTER(C.c_int32)]
+    L.mdb_frame_write_lammps.argtypes = [_H, C.c_int32, C.c_char_p, C.c_int64, C.c_int32]
+    L.mdb_frame_flush.argtypes = [_H]
+    L.mdb_init_velocities.argtypes = [_H, C.c_double, C.c_uint64]
+    L.mdb_checkpoint_save.argtypes = [_H, C.c_char_p]
+    L.mdb_checkpoint_load.argtypes = [_H, C.c_char_p]
     for name in SYMBOLS:
         if name not in ("mdb_last_error",):
             getattr(L, name).restype = C.c_int
@@ -261,6 +271,36 @@ class Engine:
         conv = C.c_int32()
         self._check(self._lib.mdb_fire_minimize(self._h, C.byref(p), _d(out), C.byref(conv)))
         return out[0], out[1], int(out[2]), bool(conv.value)
+
+    # ---- trajectory frames ----
+    def frame_capture(self, slot=0):
+        """pack {radius, x, unwrapped x} per particle on the device (original order) and start the copy to pinned host
+        memory on the copy stream; returns without waiting"""
+        self._check(self._lib.mdb_frame_capture(self._h, slot))
+
+    def frame_wait(self, slot=0):
+        """(n, 2*dim+1) view of the slot's pinned host frame once its copy has finished (valid until the next capture)"""
+        ptr, w = _dp(), C.c_int32()
+        self._check(self._lib.mdb_frame_wait(self._h, slot, C.byref(ptr), C.byref(w)))
+        return np.ctypeslib.as_array(ptr, shape=(self.n, w.value))
+
+    def frame_write_lammps(self, slot, path, step, append=True):
+        """queue the frame for the library's writer thread (write_to_file_lammps layout, src/io.jl:78-170)"""
+        self._check(self._lib.mdb_frame_write_lammps(self._h, slot, os.fsencode(path), int(step), 1 if append else 0))
+
+    def frame_flush(self):
+        self._check(self._lib.mdb_frame_flush(self._h))
+
+    # ---- device-side set-up and exact restart (SURVEY 8f row 4) ----
+    def init_velocities(self, ktemp, stream=0):
+        """initialize_velocities (src/initialization.jl:32-47) on the device"""
+        self._check(self._lib.mdb_init_velocities(self._h, float(ktemp), int(stream)))
+
+    def checkpoint_save(self, path):
+        self._check(self._lib.mdb_checkpoint_save(self._h, os.fsencode(path)))
+
+    def checkpoint_load(self, path):
+        self._check(self._lib.mdb_checkpoint_load(self._h, os.fsencode(path)))
 
     def bussi_scale_from(self, ke, ktemp, nf, dt, tau, r1, r2):
         s = C.c_double()

@@ -510,6 +510,16 @@ def run_simulation(state, params, ensemble, total_steps, frequency, pathname, tr
         all_thermo[done:upto] = t
         done = upto
 
+    frame_slot = 0
+
+    def emit_frame(path, step, append):
+        # write_to_file_lammps (src/io.jl:78-170): unwrapped coordinates formed and the frame packed on the device, copied
+        # on the engine's copy stream and formatted by its writer thread while the next chunk of steps runs
+        nonlocal frame_slot
+        engine.frame_capture(frame_slot)
+        engine.frame_write_lammps(frame_slot, path, step, append=append)
+        frame_slot = (frame_slot + 1) % _capi.FRAME_SLOTS
+
     for step in stops:
         advance(step + 1)
         U, W, KE, _ = all_thermo[step]
@@ -528,14 +538,12 @@ def run_simulation(state, params, ensemble, total_steps, frequency, pathname, tr
             with open(thermo_file, "a") as io:
                 io.write("%d %.6f %.6f %.6f\n" % row)
             if write_trajectory:
-                x, _, _, img = engine.download(velocities=False, forces=False)
-                write_to_file_lammps(traj_file, step, state.unitcell, n, x, img, state.diameters, dimension, mode="a")
+                emit_frame(traj_file, step, True)
         if log_times and snap_index < len(snapshot_times) and snapshot_times[snap_index] == step:
-            x, _, _, img = engine.download(velocities=False, forces=False)
-            write_to_file_lammps(os.path.join(pathname, "snapshot.%d" % step), step, state.unitcell, n, x, img,
-                                 state.diameters, dimension, mode="w")
+            emit_frame(os.path.join(pathname, "snapshot.%d" % step), step, False)
             snap_index += 1
     advance(total_steps)
+    engine.frame_flush()
     # finalize_simulation! (src/simulation.jl:11-36)
     write_to_file(os.path.join(pathname, "final.xyz"), total_steps, state.unitcell, n, state.system.positions,
                   state.diameters, dimension, mode="w")

@@ -5,7 +5,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -14,6 +18,7 @@
 #include "kernels.cuh"
 #include "slab.cuh"
 #include "small.cuh"
+#include "setup_io.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -36,6 +41,7 @@ struct GraphKey {
     }
 };
 
+struct FrameIO;
 struct mdb_engine_s {
     mdb_config cfg;
     int dim = 3;
@@ -107,6 +113,7 @@ struct mdb_engine_s {
     std::vector<mdb_engine_s *> *group = nullptr;  // in-process ring, shared by its members; [0] drives it
     bool stream_owned = true;
     bool slab_graph_failed = false;
+    bool prof_step_open = false;
     ncclComm_t comm = nullptr;
     // graph replay: NCCL keeps per-communicator capture state, and a graph captured in several segments (one per
     // conditional node) needs a different communicator in every segment that communicates
@@ -118,6 +125,9 @@ struct mdb_engine_s {
     cudaKernel_t user_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [KICK2][SLAB]
     cudaKernel_t user_overflow[2] = {nullptr, nullptr}, user_cells[2] = {nullptr, nullptr}, user_brute[2] = {nullptr, nullptr};
     double user_range = 0;
+
+    // ---- trajectory frames: device packing, copy stream, background writer ---------
+    FrameIO *fio = nullptr;
 
     // ---- K0-small: persistent single-CTA step loop for n <= kSmallMaxN ------------------------------
     bool small = false;
@@ -563,9 +573,10 @@ static void query_occupancy(Engine *e)
             if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, 1, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, 0, false>, kForceBlock, 0);
             if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_list<DIM, Pot, 0, true>, kForceBlock, 0);
-            if (!e->slab) {
+            {
                 int c2 = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, false>, kForceBlock, 0);
+                if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, true>, kForceBlock, 0);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, false>, kForceBlock, 0);
                 a = std::min(a, c2);
             }
         } else {
@@ -608,8 +619,7 @@ enum StepKind { kStepFull = 0, kStepFused = 1, kStepLast = 2 };
 static bool fused_step(const Engine *e, int ensemble)
 {
     static const bool off = getenv("MDB200_NO_FUSE") != nullptr;
-    return ensemble == MDB_NVE && e->mode == MDB_MODE_LIST && !e->brute && !e->slab && e->cfg.potential != MDB_POT_USER &&
-           !e->cfg.no_fuse && !off;
+    return ensemble == MDB_NVE && e->mode == MDB_MODE_LIST && !e->brute && e->cfg.potential != MDB_POT_USER && !e->cfg.no_fuse && !off;
 }
 
 // the part of one step before the (conditional) rebuild
@@ -994,7 +1004,7 @@ static int rebuild_part3(Group &G)
     return MDB_OK;
 }
 
-template <int DIM, bool KICK2>
+template <int DIM, int KICK2>
 static void enqueue_force_slab(Engine *e, double dt, int guard = 0)
 {
     cudaStream_t s = e->stream;
@@ -1013,7 +1023,7 @@ static void enqueue_force_slab(Engine *e, double dt, int guard = 0)
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
                                                                                   e->pp, dt, out, blocks, guard);
         } else {
-            k_force_cells<DIM, Pot, KICK2><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out, guard);
+            k_force_cells<DIM, Pot, KICK2 != 0><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, e->start, e->cutoff2, pot, e->pp, dt, out, guard);
         }
     });
     e->stats.kernel_launches += force_kernel_count(e);
@@ -1036,7 +1046,7 @@ static int slab_head(Group &G, CondHandles hs)
 }
 
 // tail: forces (+ Brownian move), thermo scalars
-template <int DIM, bool KICK2>
+template <int DIM, int KICK2>
 static int slab_tail(Group &G, int ensemble, double dt, double tau, double ktemp, int thermo, int advance, bool reduce_now, int guard = 0)
 {
     int rc;
@@ -1050,7 +1060,7 @@ static int slab_tail(Group &G, int ensemble, double dt, double tau, double ktemp
             e->stats.kernel_launches += 1;
         }
         if (reduce_now) enqueue_finalize(e, ensemble, dt, tau, 0, 0, 1, guard);
-        else enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 0, guard);  // rank-local row; the chunk is all-reduced later
+        else enqueue_finalize(e, ensemble, dt, tau, thermo, advance, 0, guard, KICK2 == 2 ? 1 : 0);  // rank-local row; the chunk is all-reduced later
         e->stats.kernel_launches += 1;
     }
     if (!reduce_now) return MDB_OK;
@@ -1065,7 +1075,7 @@ static int slab_tail(Group &G, int ensemble, double dt, double tau, double ktemp
 
 // make every rank's ghosts and neighbour structure current, then evaluate forces and the global thermo scalars (eager:
 // the rebuild decision is read back by the host)
-template <int DIM, bool KICK2>
+template <int DIM, int KICK2>
 static int group_force_phase(Group &G, int ensemble, double dt, double tau, double ktemp, double, int thermo, int advance,
                              bool reduce_now = true)
 {
@@ -1076,7 +1086,8 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
     // speculatively behind the decision, guarded on the device (a pending rebuild turns its kernels into no-ops).  In
     // the common case (no rebuild) the host returns from the read-back with the forces already running and goes on to
     // enqueue the next step; otherwise it rebuilds and enqueues the tail again, unguarded.
-    static const bool slab_prof = getenv("MDB200_SLAB_PROF") != nullptr;  // per-phase CUDA-event totals, one sync per phase
+    static const bool slab_prof_env = getenv("MDB200_SLAB_PROF") != nullptr;  // per-phase CUDA-event totals, one sync per phase
+    const bool slab_prof = slab_prof_env && lead->prof_step_open;                // (only inside a run step: evp[5] marks its start)
     const bool speculate = !debug_sync() && !slab_prof;
     Engine *e = lead;
     auto lap = [&](int a, int b, double &acc) -> int {  // close the phase [evp[a], evp[b]] and add its time to acc
@@ -1265,6 +1276,7 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
     }
     CU(cudaEventRecord(lead->ev0, s));
     int64_t done = 0;
+    const bool fused = !use_graph && fused_step(lead, ensemble);
     while (done < nsteps) {
         int64_t m = std::min(lead->chunk, nsteps - done);
         for (Engine *g : G) {
@@ -1279,15 +1291,23 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
         } else
         for (int64_t q = 0; q < m; q++) {
             CU(cudaEventRecord(lead->evp[5], s));
+            lead->prof_step_open = true;
             if (ensemble != MDB_BROWNIAN) {
-                for (Engine *g : G) {
-                    k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
-                    g->stats.kernel_launches += 1;
+                // fused NVE schedule (see StepKind): one stand-alone kick-drift per run, then the force kernel of every
+                // step but the last also moves the particles for the next one
+                const bool first = done + q == 0, last = done + q == nsteps - 1;
+                if (!fused || first) {
+                    for (Engine *g : G) {
+                        k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
+                        g->stats.kernel_launches += 1;
+                    }
                 }
-                if ((rc = group_force_phase<DIM, true>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce))) return rc;
-            } else {
-                if ((rc = group_force_phase<DIM, false>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce))) return rc;
-            }
+                if (fused && !last) rc = group_force_phase<DIM, 2>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce);
+                else rc = group_force_phase<DIM, 1>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce);
+            } else
+                rc = group_force_phase<DIM, 0>(G, ensemble, dt, tau, ktemp, 1.0, 1, 1, per_step_reduce);
+            lead->prof_step_open = false;
+            if (rc) return rc;
         }
         if (!per_step_reduce) {
             if ((rc = group_allreduce(G, (int)(4 * m), false, [](Engine *e) { return e->d_thermo; }))) return rc;
@@ -1605,11 +1625,13 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     return MDB_OK;
 }
 
+static void free_frames(Engine *e);
 MDB_EXPORT int mdb_destroy(mdb_handle e)
 {
     if (!e) return MDB_OK;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    free_frames(e);
     drop_graph(e);
     free_state(e);
     free_stage(e);
@@ -2367,5 +2389,433 @@ MDB_EXPORT int mdb_synchronize(mdb_handle e)
     if (!e) return MDB_ERR_INVALID_ARG;
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->stream));
+    return MDB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Trajectory frames.  Replaces the positions/images reads of write_to_file_lammps
+// (src/io.jl:78-170) at its two call sites in the step loop (src/simulation.jl:139-171): the frame is packed on the
+// device in the caller's particle order with the unwrapped coordinates already formed, copied to pinned host memory on
+// a second stream, and formatted by a background thread of the library, so the step loop goes on while a frame
+// is in flight.  Slots are double-buffered (MDB_FRAME_SLOTS); a slot is busy from capture until its file is written
+// (or, without a write request, until the next capture into it).
+// ------------------------------------------------------------------------------------------------
+struct FrameJob {
+    int slot;
+    std::string path;
+    int64_t step;
+    int append;
+};
+struct FrameIO {
+    double *d_frame[MDB_FRAME_SLOTS] = {};
+    double *h_frame[MDB_FRAME_SLOTS] = {};
+    cudaEvent_t copied[MDB_FRAME_SLOTS] = {};
+    bool captured[MDB_FRAME_SLOTS] = {};
+    int writing[MDB_FRAME_SLOTS] = {};  // jobs queued or running on the slot
+    cudaEvent_t packed = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int64_t n = 0;
+    int width = 0;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<FrameJob> jobs;
+    bool stop = false;
+    std::string io_error;
+    // what the writer needs of the engine
+    int device = 0, dim = 3;
+    double L[3] = {1, 1, 1};
+};
+
+// write_to_file_lammps for a diagonal cell: same header lines, same "%lf" columns (src/io.jl:97-167)
+static bool write_lammps_frame(const FrameIO *f, const FrameJob &job, std::string &err)
+{
+    FILE *fp = fopen(job.path.c_str(), job.append ? "a" : "w");
+    if (!fp) {
+        err = "cannot open " + job.path;
+        return false;
+    }
+    const int dim = f->dim, W = f->width;
+    const int64_t n = f->n;
+    fprintf(fp, "ITEM: TIMESTEP\n%lld\n", (long long)job.step);
+    fprintf(fp, "ITEM: NUMBER OF ATOMS\n%lld\n", (long long)n);
+    if (dim == 2) {
+        fprintf(fp, "ITEM: BOX BOUNDS xy pp pp\n");
+        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[0], 0.0);
+        fprintf(fp, "%lf %lf 0.0\n", 0.0, f->L[1]);
+        fprintf(fp, "%lf %lf 0.0\n", 0.0, 1.0);
+        fprintf(fp, "ITEM: ATOMS id type radius x y xu yu\n");
+    } else {
+        fprintf(fp, "ITEM: BOX BOUNDS xy xz yz pp pp pp\n");
+        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[0], 0.0);
+        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[1], 0.0);
+        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[2], 0.0);
+        fprintf(fp, "ITEM: ATOMS id type radius x y z xu yu zu\n");
+    }
+    // rows are formatted in parallel blocks and written in order
+    const double *fr = f->h_frame[job.slot];
+    const int nthr = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const int64_t block = 1 << 18;
+    std::vector<std::string> bufs(nthr);
+    bool ok = true;
+    for (int64_t b0 = 0; b0 < n && ok; b0 += block * nthr) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; t++) {
+            const int64_t lo = b0 + t * block, hi = std::min(n, lo + block);
+            bufs[t].clear();
+            if (lo >= hi) continue;
+            th.emplace_back([&, t, lo, hi]() {
+                std::string &out = bufs[t];
+                out.reserve((size_t)(hi - lo) * (16 + 14 * (size_t)W));
+                char line[512];
+                for (int64_t i = lo; i < hi; i++) {
+                    const double *r = fr + i * W;
+                    int len = snprintf(line, sizeof(line), "%lld %d", (long long)(i + 1), 1);
+                    for (int c = 0; c < W; c++) len += snprintf(line + len, sizeof(line) - len, " %lf", r[c]);
+                    line[len++] = '\n';
+                    out.append(line, (size_t)len);
+                }
+            });
+        }
+        for (auto &t : th) t.join();
+        for (int t = 0; t < nthr && ok; t++)
+            if (!bufs[t].empty() && fwrite(bufs[t].data(), 1, bufs[t].size(), fp) != bufs[t].size()) ok = false;
+    }
+    if (fclose(fp) != 0) ok = false;
+    if (!ok) err = "short write to " + job.path;
+    return ok;
+}
+
+static void frame_worker(FrameIO *f)
+{
+    cudaSetDevice(f->device);
+    for (;;) {
+        FrameJob job;
+        {
+            std::unique_lock<std::mutex> lk(f->mu);
+            f->cv.wait(lk, [&] { return f->stop || !f->jobs.empty(); });
+            if (f->jobs.empty()) return;  // stop requested and nothing left
+            job = f->jobs.front();
+            f->jobs.pop_front();
+        }
+        std::string err;
+        cudaError_t ce = cudaEventSynchronize(f->copied[job.slot]);
+        if (ce != cudaSuccess) err = std::string("frame copy: ") + cudaGetErrorString(ce);
+        else write_lammps_frame(f, job, err);
+        {
+            std::lock_guard<std::mutex> lk(f->mu);
+            if (!err.empty() && f->io_error.empty()) f->io_error = err;
+            f->writing[job.slot]--;
+        }
+        f->cv.notify_all();
+    }
+}
+
+static void free_frames(Engine *e)
+{
+    FrameIO *f = e->fio;
+    if (!f) return;
+    {
+        std::lock_guard<std::mutex> lk(f->mu);
+        f->stop = true;
+    }
+    f->cv.notify_all();
+    if (f->worker.joinable()) f->worker.join();
+    if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
+    for (int q = 0; q < MDB_FRAME_SLOTS; q++) {
+        cudaFree(f->d_frame[q]);
+        if (f->h_frame[q]) cudaFreeHost(f->h_frame[q]);
+        if (f->copied[q]) cudaEventDestroy(f->copied[q]);
+    }
+    if (f->packed) cudaEventDestroy(f->packed);
+    if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
+    delete f;
+    e->fio = nullptr;
+}
+
+static int ensure_frames(Engine *e)
+{
+    if (e->fio && e->fio->n == e->N && e->fio->dim == e->dim) return MDB_OK;
+    free_frames(e);
+    FrameIO *f = new FrameIO();
+    e->fio = f;
+    f->n = e->N;
+    f->dim = e->dim;
+    f->width = 2 * e->dim + 1;
+    f->device = e->cfg.device;
+    for (int k = 0; k < 3; k++) f->L[k] = e->L[k];
+    const size_t bytes = sizeof(double) * (size_t)f->n * f->width;
+    for (int q = 0; q < MDB_FRAME_SLOTS; q++) {
+        CU(cudaMalloc(&f->d_frame[q], bytes));
+        CU(cudaMallocHost(&f->h_frame[q], bytes));
+        CU(cudaEventCreateWithFlags(&f->copied[q], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&f->packed, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+    f->worker = std::thread(frame_worker, f);
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_frame_capture(mdb_handle e, int32_t slot)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= MDB_FRAME_SLOTS) return fail(e, MDB_ERR_INVALID_ARG, "frame slot out of range");
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: frames are assembled from mdb_download_owned of every rank");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = ensure_frames(e);
+    if (rc) return rc;
+    FrameIO *f = e->fio;
+    {
+        // the slot's host image must be on disk before it is overwritten
+        std::unique_lock<std::mutex> lk(f->mu);
+        f->cv.wait(lk, [&] { return f->writing[slot] == 0; });
+    }
+    cudaStream_t s = e->stream;
+    // (the previous copy out of this slot's device buffer was awaited above or by mdb_frame_wait; order it anyway)
+    if (f->captured[slot]) CU(cudaStreamWaitEvent(s, f->copied[slot], 0));
+    const int blocks = std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * 8));
+    if (e->dim == 3) k_pack_frame<3><<<blocks, kStreamBlock, 0, s>>>(e->n, e->ctl, e->grid, f->d_frame[slot]);
+    else k_pack_frame<2><<<blocks, kStreamBlock, 0, s>>>(e->n, e->ctl, e->grid, f->d_frame[slot]);
+    e->stats.kernel_launches += 1;
+    CU(cudaEventRecord(f->packed, s));
+    CU(cudaStreamWaitEvent(f->copy_stream, f->packed, 0));
+    CU(cudaMemcpyAsync(f->h_frame[slot], f->d_frame[slot], sizeof(double) * (size_t)f->n * f->width, cudaMemcpyDeviceToHost, f->copy_stream));
+    CU(cudaEventRecord(f->copied[slot], f->copy_stream));
+    f->captured[slot] = true;
+    CU(cudaGetLastError());
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_frame_wait(mdb_handle e, int32_t slot, const double **frame, int32_t *width)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= MDB_FRAME_SLOTS || !e->fio || !e->fio->captured[slot]) return fail(e, MDB_ERR_STATE, "no frame captured in this slot");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventSynchronize(e->fio->copied[slot]));
+    if (frame) *frame = e->fio->h_frame[slot];
+    if (width) *width = e->fio->width;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_frame_write_lammps(mdb_handle e, int32_t slot, const char *path, int64_t step, int32_t append)
+{
+    if (!e || !path) return MDB_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= MDB_FRAME_SLOTS || !e->fio || !e->fio->captured[slot]) return fail(e, MDB_ERR_STATE, "no frame captured in this slot");
+    FrameIO *f = e->fio;
+    {
+        std::lock_guard<std::mutex> lk(f->mu);
+        f->jobs.push_back(FrameJob{slot, std::string(path), step, append});
+        f->writing[slot]++;
+    }
+    f->cv.notify_all();
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_frame_flush(mdb_handle e)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    FrameIO *f = e->fio;
+    if (!f) return MDB_OK;
+    std::unique_lock<std::mutex> lk(f->mu);
+    f->cv.wait(lk, [&] {
+        for (int q = 0; q < MDB_FRAME_SLOTS; q++)
+            if (f->writing[q]) return false;
+        return true;
+    });
+    if (!f->io_error.empty()) {
+        std::string msg = f->io_error;
+        f->io_error.clear();
+        lk.unlock();
+        return fail(e, MDB_ERR_IO, msg);
+    }
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// initialize_velocities on the device (src/initialization.jl:32-47)
+// ------------------------------------------------------------------------------------------------
+MDB_EXPORT int mdb_init_velocities(mdb_handle e, double ktemp, uint64_t stream)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload first");
+    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: draw the velocities on one handle (or the host) and upload them");
+    if (!(ktemp > 0) || e->N < 2) return fail(e, MDB_ERR_INVALID_ARG, "ktemp must be > 0 and n_particles >= 2");
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const int64_t n = e->n;
+    const int blocks = std::max(1, std::min(std::min(nblk(n, kStreamBlock), e->nsm * 8), kMaxPartials));
+    for (int stage = 0; stage < 3; stage++) {
+        if (e->dim == 3) k_vel_init<3><<<blocks, kStreamBlock, 0, s>>>(stage, n, e->cfg.seed, stream, e->ctl, e->part);
+        else k_vel_init<2><<<blocks, kStreamBlock, 0, s>>>(stage, n, e->cfg.seed, stream, e->ctl, e->part);
+        if (stage < 2) k_vel_reduce<<<1, kStreamBlock, 0, s>>>(stage, blocks, e->part, (double)e->N, e->dim, ktemp, e->ctl);
+    }
+    e->stats.kernel_launches += 5;
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    e->have_vel = true;
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact binary checkpoint.  The file holds the state in DEVICE SLOT ORDER together with the RNG
+// step counter; saving also invalidates the resident Verlet list, so the next step of the run that was saved and the
+// first step of a run restored from the file start from the same rebuild of the same slot order: the continuation is
+// bit-identical (tests/test_gpu_setup_io.py).
+// ------------------------------------------------------------------------------------------------
+struct CkptHeader {
+    char magic[8];
+    uint32_t version;
+    int32_t dim;
+    int64_t n_particles;
+    double unitcell[9];
+    uint64_t seed;
+    uint64_t rng_step;
+    int32_t have_vel;
+    int32_t reserved[7];
+};
+static const char kCkptMagic[8] = {'M', 'D', 'B', '2', '0', '0', 'C', 'K'};
+
+struct CkptBuffers {
+    double4 *pos = nullptr;
+    double *vel = nullptr, *frc = nullptr;
+    int32_t *img = nullptr, *id = nullptr;
+    ~CkptBuffers()
+    {
+        cudaFree(pos); cudaFree(vel); cudaFree(frc); cudaFree(img); cudaFree(id);
+    }
+    cudaError_t alloc(int64_t n, int d)
+    {
+        cudaError_t ce;
+        if ((ce = cudaMalloc(&pos, sizeof(double4) * n)) != cudaSuccess) return ce;
+        if ((ce = cudaMalloc(&vel, sizeof(double) * n * d)) != cudaSuccess) return ce;
+        if ((ce = cudaMalloc(&frc, sizeof(double) * n * d)) != cudaSuccess) return ce;
+        if ((ce = cudaMalloc(&img, sizeof(int32_t) * n * d)) != cudaSuccess) return ce;
+        return cudaMalloc(&id, sizeof(int32_t) * n);
+    }
+};
+
+MDB_EXPORT int mdb_checkpoint_save(mdb_handle e, const char *path)
+{
+    if (!e || !path) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
+    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: checkpoint through mdb_download_owned of every rank");
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const int64_t n = e->n;
+    const int d = e->dim;
+    CkptBuffers b;
+    CU(b.alloc(n, d));
+    const int blocks = std::max(1, std::min(nblk(n, kStreamBlock), e->nsm * 8));
+    if (d == 3) k_ckpt_pack<3><<<blocks, kStreamBlock, 0, s>>>(n, e->ctl, b.pos, b.vel, b.frc, b.img, b.id);
+    else k_ckpt_pack<2><<<blocks, kStreamBlock, 0, s>>>(n, e->ctl, b.pos, b.vel, b.frc, b.img, b.id);
+    e->stats.kernel_launches += 1;
+    std::vector<double4> hpos(n);
+    std::vector<double> hvel((size_t)n * d), hfrc((size_t)n * d);
+    std::vector<int32_t> himg((size_t)n * d), hid(n);
+    CU(cudaMemcpyAsync(hpos.data(), b.pos, sizeof(double4) * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hvel.data(), b.vel, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hfrc.data(), b.frc, sizeof(double) * n * d, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(himg.data(), b.img, sizeof(int32_t) * n * d, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hid.data(), b.id, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    // both futures (this engine going on, an engine restored from the file) rebuild the list at their next step
+    CU(cudaMemsetAsync(&e->ctl->list_valid, 0, sizeof(int), s));
+    int rc = sync_ctl(e);
+    if (rc) return rc;
+    CkptHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, kCkptMagic, 8);
+    h.version = 1;
+    h.dim = d;
+    h.n_particles = e->N;
+    memcpy(h.unitcell, e->cfg.unitcell, sizeof(h.unitcell));
+    h.seed = e->cfg.seed;
+    h.rng_step = e->h_ctl->rng_step;
+    h.have_vel = e->have_vel ? 1 : 0;
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(e, MDB_ERR_IO, std::string("cannot open ") + path);
+    bool ok = fwrite(&h, sizeof(h), 1, fp) == 1 && fwrite(hpos.data(), sizeof(double4), n, fp) == (size_t)n &&
+              fwrite(hvel.data(), sizeof(double), (size_t)n * d, fp) == (size_t)n * d &&
+              fwrite(hfrc.data(), sizeof(double), (size_t)n * d, fp) == (size_t)n * d &&
+              fwrite(himg.data(), sizeof(int32_t), (size_t)n * d, fp) == (size_t)n * d &&
+              fwrite(hid.data(), sizeof(int32_t), n, fp) == (size_t)n;
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok) return fail(e, MDB_ERR_IO, std::string("short write to ") + path);
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_checkpoint_load(mdb_handle e, const char *path)
+{
+    if (!e || !path) return MDB_ERR_INVALID_ARG;
+    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: restore through mdb_upload");
+    CU(cudaSetDevice(e->cfg.device));
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(e, MDB_ERR_IO, std::string("cannot open ") + path);
+    CkptHeader h;
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0 || h.version != 1) {
+        fclose(fp);
+        return fail(e, MDB_ERR_IO, std::string(path) + " is not an mdb200 checkpoint");
+    }
+    if (h.dim != e->dim || h.n_particles != e->N || memcmp(h.unitcell, e->cfg.unitcell, sizeof(h.unitcell)) != 0) {
+        fclose(fp);
+        return fail(e, MDB_ERR_INVALID_ARG, "checkpoint was written for a different system (dimension, particle count or unit cell)");
+    }
+    const int64_t n = e->N;
+    const int d = e->dim;
+    std::vector<double4> hpos(n);
+    std::vector<double> hvel((size_t)n * d), hfrc((size_t)n * d);
+    std::vector<int32_t> himg((size_t)n * d), hid(n);
+    bool ok = fread(hpos.data(), sizeof(double4), n, fp) == (size_t)n && fread(hvel.data(), sizeof(double), (size_t)n * d, fp) == (size_t)n * d &&
+              fread(hfrc.data(), sizeof(double), (size_t)n * d, fp) == (size_t)n * d &&
+              fread(himg.data(), sizeof(int32_t), (size_t)n * d, fp) == (size_t)n * d && fread(hid.data(), sizeof(int32_t), n, fp) == (size_t)n;
+    fclose(fp);
+    if (!ok) return fail(e, MDB_ERR_IO, std::string("truncated checkpoint ") + path);
+    double smin = hpos[0].w, smax = hpos[0].w;
+    for (int64_t i = 1; i < n; i++) {
+        smin = std::min(smin, hpos[i].w);
+        smax = std::max(smax, hpos[i].w);
+    }
+    if (!(smin > 0) || !std::isfinite(smax)) return fail(e, MDB_ERR_IO, "checkpoint holds invalid diameters");
+    e->smin = smin; e->smax = smax;
+    int rc;
+    if ((rc = plan_neighbors(e))) return rc;
+    e->n = (int)n;
+    if (e->cap < n || !e->st[0].pos) {
+        if ((rc = alloc_state(e, n))) return rc;
+    }
+    if ((rc = ensure_stage(e, std::max<int64_t>(n, 1)))) return rc;
+    if ((rc = alloc_neighbors(e))) return rc;
+    drop_graph(e);
+    if (d == 3) query_occupancy<3>(e);
+    else query_occupancy<2>(e);
+    cudaStream_t s = e->stream;
+    CkptBuffers b;
+    CU(b.alloc(n, d));
+    CU(cudaMemcpyAsync(b.pos, hpos.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b.vel, hvel.data(), sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b.frc, hfrc.data(), sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b.img, himg.data(), sizeof(int32_t) * n * d, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b.id, hid.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    e->rng_step = h.rng_step;
+    DevCtl c;
+    memset(&c, 0, sizeof(c));
+    c.alpha = 1.0;
+    c.rng_step = e->rng_step;
+    c.n_own = (int)n;
+    c.n_tmp = (int)n;
+    c.st[0] = e->st[0];
+    c.st[1] = e->st[1];
+    *e->h_ctl = c;
+    CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
+    const int blocks = std::max(1, std::min(nblk(n, kStreamBlock), e->nsm * 8));
+    if (d == 3) k_ckpt_unpack<3><<<blocks, kStreamBlock, 0, s>>>(n, e->st[0], b.pos, b.vel, b.frc, b.img, b.id);
+    else k_ckpt_unpack<2><<<blocks, kStreamBlock, 0, s>>>(n, e->st[0], b.pos, b.vel, b.frc, b.img, b.id);
+    e->stats.kernel_launches += 1;
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    e->uploaded = true;
+    e->have_vel = h.have_vel != 0;
+    e->stats.n_owned = e->n;
     return MDB_OK;
 }

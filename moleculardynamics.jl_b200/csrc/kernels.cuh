@@ -71,6 +71,7 @@ struct DevCtl {
     unsigned long long rebuilds;
     StatePtrs st[2];
     double fire[8];               // FIRE scalars: dt, alpha, steps_since_neg, converged, P, vnorm2, fnorm2, energy
+    double scratch[4];            // initialize_velocities: mean per component, scale factor (setup_io.cuh)
 };
 
 

@@ -403,6 +403,8 @@ ORC_API double orc_bussi_scale(double kinetic_energy, double ktemp, double nf, d
  *   thermostat uniforms: ctr = (step_lo, step_hi, block, 0xB0551<<8|1), two u53_open per block
  *   Brownian noise     : ctr = (particle_id, step_lo, step_hi, 0xB12D<<8|block); block 0 gives
  *                        u_x=(w0,w1), u_y=(w2,w3); block 1 gives u_z=(w0,w1)
+ *   velocity normals   : ctr = (particle_id, stream_lo, stream_hi, 0x1E10C<<8|block), Box-Muller as above; block 0
+ *                        gives (v_x, v_y), block 1 gives v_z = r cos (orc_init_velocities)
  * ---------------------------------------------------------------------------------------- */
 ORC_API void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
@@ -537,6 +539,43 @@ ORC_API void orc_brownian_noise(uint64_t seed, uint64_t step, uint32_t id, int d
         orc_philox4x32_10(ctr, key, w);
         noise[2] = (2.0 * u53(w[0], w[1]) - 1.0) * sqthree;
     }
+}
+
+/* src/initialization.jl:32-47 initialize_velocities: V = randn(d, N); V .-= mean(V; dims=2);
+ * fs = sqrt(ktemp / (sum(abs2, V) / ((N-1) d))); V .*= fs.  The normals come from the counter-based generator:
+ *   velocity normals: ctr = (particle_id, stream_lo, stream_hi, 0x1E10C<<8 | block), Box-Muller on
+ *   (u53_open(w0,w1), u53(w2,w3)); block 0 gives (v_x, v_y) = (r cos, r sin), block 1 gives v_z = r cos.
+ * v is [n][dim] in particle order; sums are accumulated in long double. */
+#define ORC_TAG_VEL 0x1E10Cu
+ORC_API void orc_init_velocities(int dim, int64_t n, double ktemp, uint64_t seed, uint64_t stream, double *v)
+{
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, w[4];
+    long double mean[3] = {0, 0, 0};
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t ctr[4] = {(uint32_t)i, (uint32_t)stream, (uint32_t)(stream >> 32), (ORC_TAG_VEL << 8) | 0u};
+        orc_philox4x32_10(ctr, key, w);
+        double r = sqrt(-2.0 * log(u53_open(w[0], w[1])));
+        double th = 6.283185307179586 * u53(w[2], w[3]);
+        v[i * dim + 0] = r * cos(th);
+        v[i * dim + 1] = r * sin(th);
+        if (dim == 3) {
+            ctr[3] = (ORC_TAG_VEL << 8) | 1u;
+            orc_philox4x32_10(ctr, key, w);
+            double r2 = sqrt(-2.0 * log(u53_open(w[0], w[1])));
+            v[i * dim + 2] = r2 * cos(6.283185307179586 * u53(w[2], w[3]));
+        }
+        for (int k = 0; k < dim; k++) mean[k] += v[i * dim + k];
+    }
+    double m[3] = {0, 0, 0};
+    for (int k = 0; k < dim; k++) m[k] = (double)(mean[k] / (long double)n);
+    long double sum_v2 = 0;
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < dim; k++) {
+            v[i * dim + k] -= m[k];
+            sum_v2 += (long double)v[i * dim + k] * v[i * dim + k];
+        }
+    double fs = sqrt(ktemp / ((double)sum_v2 / (((double)n - 1.0) * dim)));
+    for (int64_t i = 0; i < n * dim; i++) v[i] *= fs;
 }
 
 /* src/integrate.jl:66-82 integrate_brownian! with the *intended* semantics:

@@ -63,6 +63,7 @@ def lib():
         _lib.orc_fire.restype = C.c_int64
         _lib.orc_fire.argtypes = [C.c_int, C.c_int64, _dp, _ip, _dp, _dp, C.c_double, C.c_int, _dp, C.c_int64] + [C.c_double] * 6 + \
             [C.c_int, _dp, C.POINTER(C.c_int), _dp]
+        _lib.orc_init_velocities.argtypes = [C.c_int, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, _dp]
         _lib.orc_threads.restype = C.c_int
         _lib.orc_run_timing.restype = C.c_int
         _lib.orc_run_timing.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, C.c_double, C.c_int,
@@ -159,6 +160,13 @@ def brownian_noise(seed, step, pid, dim):
     out = np.zeros(3)
     lib().orc_brownian_noise(seed, step, pid, dim, _d(out))
     return out[:dim]
+
+
+def init_velocities(dim, n, ktemp, seed, stream=0):
+    """src/initialization.jl:32-47 with the counter-based normals; returns (n, dim)"""
+    v = np.zeros((n, dim))
+    lib().orc_init_velocities(dim, n, float(ktemp), seed, stream, _d(v))
+    return v
 
 
 def run(ensemble, x, v, f, img, diam, box, cutoff, tag, params, dt, nsteps, ktemp=None, tau=1.0, nf=None, seed=0,

@@ -224,3 +224,30 @@ def test_timing_variant_matches_accurate_oracle(orc):
     ox, ov, of, oimg, th = orc.run(orc.NVE, g["x"], g["v"], g["f"], g["img"], g["diam"], g["box"], 1.5, orc.POT_PHS, (), 1e-3, 25)
     assert np.max(np.abs(x - ox)) < 1e-10 and np.array_equal(img, oimg)
     assert np.allclose(out, th[-1, :3], rtol=1e-10)
+
+
+def test_init_velocities_restatement(orc):
+    """src/initialization.jl:32-47: zero centre-of-mass velocity, exactly the requested temperature, unit-normal draws
+    from the documented Philox stream (checked against a Box-Muller recomputed here from the raw counter output)"""
+    import math
+    for dim, n in ((3, 20000), (2, 1200)):
+        v = orc.init_velocities(dim, n, 1.4737, 99, 5)
+        assert v.shape == (n, dim)
+        assert np.max(np.abs(v.mean(axis=0))) < 1e-15
+        assert abs(np.sum(v * v) / ((n - 1) * dim) - 1.4737) < 1e-13
+        if n * dim > 50000:
+            z = v / v.std()
+            assert abs(np.mean(z ** 3)) < 0.05 and abs(np.mean(z ** 4) - 3.0) < 0.1   # gaussian moments
+        assert np.array_equal(v, orc.init_velocities(dim, n, 1.4737, 99, 5))
+        assert not np.allclose(v, orc.init_velocities(dim, n, 1.4737, 99, 6))
+
+    def box_muller(pid):
+        w = orc.philox((pid, 5, 0, (0x1E10C << 8) | 0), (99, 0))
+        u1 = ((((w[0] << 32) | w[1]) >> 11) + 1) * 2.0 ** -53
+        u2 = (((w[2] << 32) | w[3]) >> 11) * 2.0 ** -53
+        r, th = math.sqrt(-2.0 * math.log(u1)), 6.283185307179586 * u2
+        return np.array([r * math.cos(th), r * math.sin(th)])
+    # two particles in 2-D: centring and scaling keep v0 - v1 parallel to the raw difference of their draws
+    pair = orc.init_velocities(2, 2, 1.0, 99, 5)
+    d_raw, d_out = box_muller(0) - box_muller(1), pair[0] - pair[1]
+    assert np.allclose(d_out / np.linalg.norm(d_out), d_raw / np.linalg.norm(d_raw), rtol=0, atol=1e-14)
