@@ -806,6 +806,12 @@ static bool load_nccl(std::string &why)
         if (_r != ncclSuccess) return fail(e, MDB_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(_r)); \
     } while (0)
 
+#define NC_G(eng, call)                                                                                             \
+    do {                                                                                                            \
+        ncclResult_t _r = (call);                                                                                   \
+        if (_r != ncclSuccess) return fail(eng, MDB_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
+
 struct PtrList {
     double *p[16];
     int n;
@@ -1034,8 +1040,13 @@ template <int DIM>
 static int slab_head(Group &G, CondHandles hs)
 {
     int rc;
+    // the ghost exchange and the all-reduce of the displacement bound are independent: under NCCL they go out as ONE
+    // group (one launch, one rendezvous of the ranks instead of two)
+    static const bool merged = getenv("MDB200_NO_MERGED_HEAD") == nullptr;
+    if (G[0]->transport == 2 && merged) NC_G(G[0], g_nccl.GroupStart());
     if ((rc = group_exchange_ghosts<DIM>(G))) return rc;
     if ((rc = group_allreduce(G, 1, true, [](Engine *e) { return (double *)&e->ctl->dmax2_bits; }))) return rc;
+    if (G[0]->transport == 2 && merged) NC_G(G[0], g_nccl.GroupEnd());
     for (Engine *e : G) {
         int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
         // every rank reaches the same decision (same all-reduced bound); the first one drives the conditional node
