@@ -386,6 +386,16 @@ def main():
                     "traffic_source": "ncu --set full capture in profiles/ (dram read+write per launch)",
                     "kernel": name, "kernel_ms": dur, "algorithmic_bytes_per_particle": bts, "peak_source": peak_src}
     step_gbs = BYTES_STEP_3D * n * args.steps / (ms * 1e-3) / 1e9
+    # FP64 pipe: DFMA peak measured live on this device; the dominant kernel's pipe utilisation comes from the committed
+    # ncu --set full capture (sm__pipe_fp64_cycles_active), like roofline.traffic
+    fp64 = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            cap = json.load(fh).get("k_force_list_fused", {})
+        fp64 = {"peak_tflops_measured": eng.measure_fp64_peak(), "dominant_kernel_pipe_active_pct_ncu": cap.get("fp64_pipe_active_pct"),
+                "source": "mdb_measure_fp64_peak (DFMA chains, best of 5) / profiles/r01_s9_fused_ncu.md"}
+    except Exception:
+        pass
 
     # end-to-end through the public host-buffer API: upload (pinned host) + K steps + download + thermo
     e2e = None
@@ -450,6 +460,7 @@ def main():
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm, "unit": "GB/s", "frac": step_gbs / hbm,
                           "algorithmic_bytes_per_particle_step": BYTES_STEP_3D},
         "cpu_baseline": cpu,
+        "fp64": fp64,
         "kernels": prof,
         "rebuilds_in_timed_region": int(rebuilds),
         "physics": {"T_mean": float(np.mean(2 * t_thermo[:, 2] / nf)), "U_per_particle": float(np.mean(t_thermo[:, 0]) / n),

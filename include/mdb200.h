@@ -229,6 +229,9 @@ int mdb_device_ptr(mdb_handle h, int32_t which, void **ptr, int64_t *stride);
 /* the CUDA stream the engine launches on (cudaStream_t), so callers can order their own work / events after it */
 int mdb_stream(mdb_handle h, void **stream);
 int mdb_synchronize(mdb_handle h);
+/* measured FP64 (DFMA) throughput of the device in TFLOP/s (8 independent FMA chains per thread, best of 5): the
+ * denominator bench.py uses next to ncu's FP64-pipe utilisation; not part of the path */
+int mdb_measure_fp64_peak(mdb_handle h, double *tflops);
 
 #ifdef __cplusplus
 }

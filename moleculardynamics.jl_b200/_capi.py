@@ -27,7 +27,7 @@ SYMBOLS = [
     "mdb_set_rng_step", "mdb_set_user_potential", "mdb_comm_unique_id", "mdb_comm_init", "mdb_comm_init_local",
     "mdb_get_stats", "mdb_device_ptr", "mdb_stream", "mdb_synchronize",
     "mdb_frame_capture", "mdb_frame_wait", "mdb_frame_write_lammps", "mdb_frame_flush",
-    "mdb_init_velocities", "mdb_checkpoint_save", "mdb_checkpoint_load",
+    "mdb_init_velocities", "mdb_checkpoint_save", "mdb_checkpoint_load", "mdb_measure_fp64_peak",
 ]
 FRAME_SLOTS = 2
 
@@ -115,6 +115,7 @@ def load():
     L.mdb_init_velocities.argtypes = [_H, C.c_double, C.c_uint64]
     L.mdb_checkpoint_save.argtypes = [_H, C.c_char_p]
     L.mdb_checkpoint_load.argtypes = [_H, C.c_char_p]
+    L.mdb_measure_fp64_peak.argtypes = [_H, _dp]
     for name in SYMBOLS:
         if name not in ("mdb_last_error",):
             getattr(L, name).restype = C.c_int
@@ -301,6 +302,12 @@ class Engine:
 
     def checkpoint_load(self, path):
         self._check(self._lib.mdb_checkpoint_load(self._h, os.fsencode(path)))
+
+    def measure_fp64_peak(self):
+        """measured DFMA throughput of the device, TFLOP/s"""
+        t = C.c_double()
+        self._check(self._lib.mdb_measure_fp64_peak(self._h, C.byref(t)))
+        return t.value
 
     def bussi_scale_from(self, ke, ktemp, nf, dt, tau, r1, r2):
         s = C.c_double()

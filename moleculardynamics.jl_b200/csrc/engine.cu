@@ -2830,3 +2830,28 @@ MDB_EXPORT int mdb_checkpoint_load(mdb_handle e, const char *path)
     e->stats.n_owned = e->n;
     return MDB_OK;
 }
+
+// measured FP64 (DFMA) throughput of this device in TFLOP/s: denominator for FP64-pipe utilisation
+MDB_EXPORT int mdb_measure_fp64_peak(mdb_handle e, double *tflops)
+{
+    if (!e || !tflops) return MDB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const int iters = 1 << 14, blocks = e->nsm * 8, threads = 256;
+    k_fp64_probe<<<blocks, threads, 0, s>>>(256, 1.0, e->d_scratch);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(e->evf0, s));
+        k_fp64_probe<<<blocks, threads, 0, s>>>(iters, 1.0, e->d_scratch);
+        CU(cudaEventRecord(e->evf1, s));
+        CU(cudaEventSynchronize(e->evf1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e->evf0, e->evf1));
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    e->stats.kernel_launches += 6;
+    CU(cudaGetLastError());
+    *tflops = best;
+    return MDB_OK;
+}

@@ -143,4 +143,23 @@ __global__ void k_ckpt_unpack(int64_t n, StatePtrs s, const double4 *__restrict_
     }
 }
 
+// DFMA throughput probe for the FP64-pipe figures in bench.py / BASELINE.md (not part of the path): 8 independent
+// dependent-FMA chains per thread so the pipe, not the latency, is what is measured
+__global__ void __launch_bounds__(256)
+k_fp64_probe(int iters, double seed, double *__restrict__ sink)
+{
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = seed + (double)(threadIdx.x + q);
+    const double m = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) a[q] = fma(a[q], m, c);
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) r += a[q];
+    if (r == 123.456) sink[0] = r;  // keeps the chains alive
+}
+
 }  // namespace mdb
