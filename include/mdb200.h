@@ -51,6 +51,8 @@ enum mdb_potential {
     MDB_POT_LJ = 1,       /* LennardJones: params = {epsilon, r_cut} (src/potentials.jl:160-164, 66-77) */
     MDB_POT_LJ_XPLOR = 2, /* LennardJonesXPLOR: params = {epsilon, r_on, r_cut} (src/potentials.jl:217-249) */
     MDB_POT_POLY = 3,     /* non-additive Polydisperse plugin: params = {rcut, non_additivity} (README.md:89-145) */
+    MDB_POT_SOFT = 4,     /* overlap-removal penalty u = k/2 (1 - r/tol)^2, r < tol: params = {k, tol}; stands in for Packmol's
+                             pack_monoatomic!(coordinates, maxs, tol) together with mdb_fire_minimize (src/initialization.jl:20-30) */
     MDB_POT_USER = 100    /* user CUDA-C `evaluate` body compiled with NVRTC (mdb_set_user_potential) */
 };
 
@@ -215,6 +217,11 @@ int mdb_frame_flush(mdb_handle h);
  * from the counter-based RNG keyed by (seed, original particle id, stream), centre-of-mass motion removed, rescaled so
  * that sum(v^2) / ((N-1) dim) == ktemp (nranks == 1) */
 int mdb_init_velocities(mdb_handle h, double ktemp, uint64_t stream);
+/* initialize_random (src/initialization.jl:20-30) on the device, first half: replaces the resident positions by uniform
+ * random points of the cell (counter-based RNG keyed by seed, particle id, stream), resets the images.  Second half: a
+ * handle created with MDB_POT_SOFT {k, tol} removes the overlaps with mdb_fire_minimize (zero energy <=> no pair closer
+ * than tol; check with mdb_count_pairs(h, tol)), which is what Packmol's pack_monoatomic! does on the host (nranks == 1). */
+int mdb_random_positions(mdb_handle h, uint64_t stream);
 /* Exact binary checkpoint: positions, velocities, forces, images and ids in device slot order plus the RNG step counter.
  * Saving invalidates the resident Verlet list, so the saved run and a run restored with mdb_checkpoint_load on a handle
  * created with the same mdb_config continue bit-identically (nranks == 1). */

@@ -178,6 +178,25 @@ end
 # initialize_velocities (src/initialization.jl:32-47) on the device; `stream` selects an independent set of draws
 init_velocities!(sys::GPUSystem, ktemp::Float64; stream::Integer=0) =
     check(sys.handle, ccall((:mdb_init_velocities, libmdb), Cint, (Handle, Float64, UInt64), sys.handle, ktemp, UInt64(stream)))
+# initialize_random (src/initialization.jl:20-30) on the GPU: uniform points of the cell, then FIRE on the penalty
+# potential MDB_POT_SOFT until no pair is closer than `tol` (what Packmol.pack_monoatomic! does on the host)
+function initialize_random_gpu(unitcell, npart::Int, dimension::Int; tol::Float64=1.0, seed::UInt64=rand(UInt64), device::Int=0)
+    cell = ntuple(k -> (k in (1, 5, 9) && cld(k, 4) <= dimension) ? Float64(unitcell[cld(k, 4), cld(k, 4)]) : 0.0, 9)
+    tp = 1.001 * tol
+    cfg = MdbConfig(dimension, Int32(4), npart, cell, tp, pad8((1.0, tp)), seed, device, 0, 0.0, 1, 0, 1, Int32(0), 0.0,
+                    ntuple(_ -> Int32(0), 2))
+    sys = dimension == 3 ? GPUSystem{3}(cfg) : GPUSystem{2}(cfg)
+    upload!(sys, [zeros(dimension) for _ in 1:npart], ones(npart); velocities=[zeros(dimension) for _ in 1:npart])
+    check(sys.handle, ccall((:mdb_random_positions, libmdb), Cint, (Handle, UInt64), sys.handle, UInt64(0)))
+    fp = Ref(FireParams(2000, 1e-12, 0.02, 0.2, 0.1, 1.2, 0.2, Int32(5), Int32(0)))
+    out, conv, close = zeros(3), Ref{Int32}(0), Ref{Int64}(1)
+    while close[] != 0
+        check(sys.handle, ccall((:mdb_fire_minimize, libmdb), Cint, (Handle, Ptr{FireParams}, Ptr{Float64}, Ptr{Int32}), sys.handle, fp, out, conv))
+        check(sys.handle, ccall((:mdb_count_pairs, libmdb), Cint, (Handle, Float64, Ptr{Int64}, Ptr{Int32}), sys.handle, tol, close, C_NULL))
+    end
+    x, _, _, _ = download(sys; velocities=false, forces=false, images=false)
+    return x
+end
 # exact binary restart: the saved run and a run restored from the file continue bit-identically
 save_checkpoint(sys::GPUSystem, path::String) =
     check(sys.handle, ccall((:mdb_checkpoint_save, libmdb), Cint, (Handle, Cstring), sys.handle, path))

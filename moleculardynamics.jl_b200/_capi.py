@@ -15,7 +15,7 @@ ERR_NO_DEVICE, ERR_NCCL, ERR_STATE, ERR_NONFINITE, ERR_NVRTC, ERR_IO = 6, 7, 8, 
 STATUS_NAMES = {0: "MDB_OK", 1: "MDB_ERR_INVALID_ARG", 2: "MDB_ERR_CUDA", 3: "MDB_ERR_UNSUPPORTED_POTENTIAL",
                 4: "MDB_ERR_UNSUPPORTED_CELL", 5: "MDB_ERR_BOX_TOO_SMALL", 6: "MDB_ERR_NO_DEVICE", 7: "MDB_ERR_NCCL",
                 8: "MDB_ERR_STATE", 9: "MDB_ERR_NONFINITE", 10: "MDB_ERR_NVRTC", 11: "MDB_ERR_IO"}
-POT_PSEUDOHS, POT_LJ, POT_LJ_XPLOR, POT_POLY, POT_USER = 0, 1, 2, 3, 100
+POT_PSEUDOHS, POT_LJ, POT_LJ_XPLOR, POT_POLY, POT_SOFT, POT_USER = 0, 1, 2, 3, 4, 100
 NVE, NVT, BROWNIAN = 0, 1, 2
 MODE_AUTO, MODE_CELLS, MODE_LIST, MODE_SMALL = 0, 1, 2, 3
 
@@ -27,7 +27,7 @@ SYMBOLS = [
     "mdb_set_rng_step", "mdb_set_user_potential", "mdb_comm_unique_id", "mdb_comm_init", "mdb_comm_init_local",
     "mdb_get_stats", "mdb_device_ptr", "mdb_stream", "mdb_synchronize",
     "mdb_frame_capture", "mdb_frame_wait", "mdb_frame_write_lammps", "mdb_frame_flush",
-    "mdb_init_velocities", "mdb_checkpoint_save", "mdb_checkpoint_load", "mdb_measure_fp64_peak",
+    "mdb_init_velocities", "mdb_random_positions", "mdb_checkpoint_save", "mdb_checkpoint_load", "mdb_measure_fp64_peak",
 ]
 FRAME_SLOTS = 2
 
@@ -113,6 +113,7 @@ def load():
     L.mdb_frame_write_lammps.argtypes = [_H, C.c_int32, C.c_char_p, C.c_int64, C.c_int32]
     L.mdb_frame_flush.argtypes = [_H]
     L.mdb_init_velocities.argtypes = [_H, C.c_double, C.c_uint64]
+    L.mdb_random_positions.argtypes = [_H, C.c_uint64]
     L.mdb_checkpoint_save.argtypes = [_H, C.c_char_p]
     L.mdb_checkpoint_load.argtypes = [_H, C.c_char_p]
     L.mdb_measure_fp64_peak.argtypes = [_H, _dp]
@@ -296,6 +297,10 @@ class Engine:
     def init_velocities(self, ktemp, stream=0):
         """initialize_velocities (src/initialization.jl:32-47) on the device"""
         self._check(self._lib.mdb_init_velocities(self._h, float(ktemp), int(stream)))
+
+    def random_positions(self, stream=0):
+        """uniform random positions in the cell, drawn on the device (src/initialization.jl:20-27)"""
+        self._check(self._lib.mdb_random_positions(self._h, int(stream)))
 
     def checkpoint_save(self, path):
         self._check(self._lib.mdb_checkpoint_save(self._h, os.fsencode(path)))

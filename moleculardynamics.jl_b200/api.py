@@ -286,9 +286,38 @@ def initialize_velocities(ktemp, rng, n_particles, dimension):
     return np.ascontiguousarray(V.T)
 
 
+def initialize_random(unitcell, npart, rng, dimension, tol=1.0, device=0, max_steps=400000, seed=None):
+    """initialize_random(unitcell, npart, rng, dimension; tol=1.0)  (src/initialization.jl:20-30) on the GPU: uniform random
+    points of the cell (mdb_random_positions), then the overlaps are removed -- the job Packmol's pack_monoatomic! does on
+    the host in the reference -- by FIRE minimisation (mdb_fire_minimize) of the penalty u = k/2 (1 - r/tol')^2 on a
+    scratch handle with MDB_POT_SOFT, tol' = 1.001 tol, until no pair is closer than tol (mdb_count_pairs).  Returns the
+    (npart, dimension) positions; raises if the density does not admit such a packing within max_steps."""
+    box = np.diag(to_unitcell(unitcell, dimension)).astype(np.float64)
+    if seed is None:
+        seed = int(rng.integers(0, 2 ** 63 - 1))
+    tol_pack = 1.001 * float(tol)
+    eng = _capi.Engine(dimension, npart, box, tol_pack, _capi.POT_SOFT, (1.0, tol_pack), seed=seed, device=device)
+    try:
+        eng.upload(np.zeros((npart, dimension)), np.ones(npart), velocities=np.zeros((npart, dimension)))
+        eng.random_positions(stream=0)
+        done = 0
+        while True:
+            _, _, steps, _ = eng.fire_minimize(max_steps=2000, tol=1e-12, dt_initial=0.02, dt_max=0.2)
+            done += steps
+            close = eng.count_pairs(float(tol))
+            if close == 0:
+                break
+            if done >= max_steps:
+                raise _capi.MdbError(_capi.ERR_STATE, "initialize_random: %d pairs still closer than tol = %g after %d FIRE "
+                                     "steps (density too high for this tolerance?)" % (close, tol, done))
+        return eng.download(velocities=False, forces=False, images=False)[0]
+    finally:
+        eng.close()
+
+
 def lattice_positions(n_particles, box, dimension, rng, jitter=0.02, sigma=1.0):
-    """Overlap-free start for random_init=True.  The reference packs random points with Packmol
-    (src/initialization.jl:20-30), a one-off host-side setup step that is out of scope here; this picks the lattice
+    """Deterministic overlap-free start (initialize_state(..., random_init="lattice")); random_init=True uses
+    initialize_random like the reference.  Picks the lattice
     (sc / bcc / fcc, or sc / centred-rectangular in 2-D) with the largest nearest-neighbour distance that offers at least
     n_particles sites in the box, removes random sites down to n_particles and adds a small jitter that keeps
     neighbours further apart than `sigma` whenever the lattice allows it."""
@@ -403,14 +432,16 @@ def initialize_state(params, pathname, from_file="", dimension=3, random_init=Fa
     elif os.path.isfile(from_file) or not random_init:
         unitcell, positions, diameters = read_file(from_file, dimension=dimension)
         n_particles = positions.shape[0]
-    elif unitcell is not None:
-        unitcell = to_unitcell(unitcell, dimension)
-        positions = lattice_positions(n_particles, np.diag(unitcell), dimension, rng)
-        diameters = np.ones(n_particles)
     else:
-        boxl = (n_particles / params.rho) ** (1.0 / dimension)
-        unitcell = to_unitcell(boxl, dimension)
-        positions = lattice_positions(n_particles, np.diag(unitcell), dimension, rng)
+        # initialize_simulation's random branch (src/initialization.jl:86-92): box from the density unless a cell is given
+        if unitcell is not None:
+            unitcell = to_unitcell(unitcell, dimension)
+        else:
+            unitcell = to_unitcell((n_particles / params.rho) ** (1.0 / dimension), dimension)
+        if random_init == "lattice":
+            positions = lattice_positions(n_particles, np.diag(unitcell), dimension, rng)
+        else:
+            positions = initialize_random(unitcell, n_particles, rng, dimension, device=device)
         diameters = np.ones(n_particles)
     diameters = np.ascontiguousarray(diameters, dtype=np.float64)
     if np.any(unitcell != np.diag(np.diag(unitcell))):

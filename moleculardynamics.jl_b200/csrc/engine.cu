@@ -170,6 +170,7 @@ static bool dispatch_pot(int tag, F &&f)
     case MDB_POT_LJ: f(PotLJ{}); return true;
     case MDB_POT_LJ_XPLOR: f(PotXPLOR{}); return true;
     case MDB_POT_POLY: f(PotPoly{}); return true;
+    case MDB_POT_SOFT: f(PotSoft{}); return true;
     }
     return false;
 }
@@ -181,6 +182,7 @@ static double pot_range(const Engine *e)
     case MDB_POT_LJ: return PotLJ::range(e->pp, e->smin, e->smax);
     case MDB_POT_LJ_XPLOR: return PotXPLOR::range(e->pp, e->smin, e->smax);
     case MDB_POT_POLY: return PotPoly::range(e->pp, e->smin, e->smax);
+    case MDB_POT_SOFT: return PotSoft::range(e->pp, e->smin, e->smax);
     case MDB_POT_USER: return e->user_range;
     }
     return e->cfg.cutoff;
@@ -1575,7 +1577,7 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
             if (r == c && !(v > 0)) return fail(nullptr, MDB_ERR_INVALID_ARG, "unit cell diagonal must be positive");
         }
     switch (cfg->potential) {
-    case MDB_POT_PSEUDOHS: case MDB_POT_LJ: case MDB_POT_LJ_XPLOR: case MDB_POT_POLY: break;
+    case MDB_POT_PSEUDOHS: case MDB_POT_LJ: case MDB_POT_LJ_XPLOR: case MDB_POT_POLY: case MDB_POT_SOFT: break;
     default: return fail(nullptr, MDB_ERR_UNSUPPORTED_POTENTIAL, "no device functor for this Potential subtype (no CPU fallback exists)");
     }
     if (cfg->nranks > 16 || (cfg->nranks > 1 && (cfg->rank < 0 || cfg->rank >= cfg->nranks)))
@@ -2666,6 +2668,24 @@ MDB_EXPORT int mdb_init_velocities(mdb_handle e, double ktemp, uint64_t stream)
     CU(cudaStreamSynchronize(s));
     CU(cudaGetLastError());
     e->have_vel = true;
+    return MDB_OK;
+}
+
+// initialize_random's first half (src/initialization.jl:20-27): uniform random positions in the cell, drawn on the
+// device.  The second half (Packmol's overlap removal) is mdb_fire_minimize on a handle created with MDB_POT_SOFT.
+MDB_EXPORT int mdb_random_positions(mdb_handle e, uint64_t stream)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload first (diameters; the positions passed there are replaced)");
+    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: draw the positions on one handle and upload them");
+    CU(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const int blocks = std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * 8));
+    if (e->dim == 3) k_random_positions<3><<<blocks, kStreamBlock, 0, s>>>(e->n, e->grid, e->cfg.seed, stream, e->ctl);
+    else k_random_positions<2><<<blocks, kStreamBlock, 0, s>>>(e->n, e->grid, e->cfg.seed, stream, e->ctl);
+    e->stats.kernel_launches += 1;
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
     return MDB_OK;
 }
 

@@ -143,6 +143,40 @@ __global__ void k_ckpt_unpack(int64_t n, StatePtrs s, const double4 *__restrict_
     }
 }
 
+// uniform positions in the cell keyed by (particle id, stream): ctr = (id, stream_lo, stream_hi, kTagPos<<8 | block);
+// block 0 gives u_x = (w0,w1), u_y = (w2,w3), block 1 gives u_z = (w0,w1); x_k = L_k * u53 (0 if that rounds up to L_k).
+// Images are reset and the neighbour structures invalidated.  (rand(rng, dim) .* (maxs .- mins) .+ mins with mins = 0,
+// src/initialization.jl:22-27)
+constexpr uint32_t kTagPos = 0x9051u;
+template <int DIM>
+__global__ void __launch_bounds__(kStreamBlock)
+k_random_positions(int64_t n, Grid g, uint64_t seed, uint64_t stream, DevCtl *__restrict__ ctl)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int64_t i = blockIdx.x * (int64_t)kStreamBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStreamBlock) {
+        const uint32_t id = (uint32_t)s.id[i];
+        Philox4 o = philox4x32_10(id, (uint32_t)stream, (uint32_t)(stream >> 32), (kTagPos << 8) | 0u, k0, k1);
+        double x[3] = {g.L[0] * u53(o.w[0], o.w[1]), g.L[1] * u53(o.w[2], o.w[3]), 0.0};
+        if (DIM == 3) {
+            Philox4 q = philox4x32_10(id, (uint32_t)stream, (uint32_t)(stream >> 32), (kTagPos << 8) | 1u, k0, k1);
+            x[2] = g.L[2] * u53(q.w[0], q.w[1]);
+        }
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            if (!(x[k] < g.L[k])) x[k] = 0.0;
+            s.img[k * s.cap + i] = 0;
+        }
+        const double w = s.pos[i].w;
+        s.pos[i] = make_double4(x[0], x[1], x[2], w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->list_valid = 0;
+        ctl->disp = 0.0;
+        ctl->disp_in = 0.0;
+    }
+}
+
 // DFMA throughput probe for the FP64-pipe figures in bench.py / BASELINE.md (not part of the path): 8 independent
 // dependent-FMA chains per thread so the pipe, not the latency, is what is measured
 __global__ void __launch_bounds__(256)

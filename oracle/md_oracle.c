@@ -29,7 +29,7 @@
 #define ORC_API __attribute__((visibility("default")))
 
 /* potential tags == include/mdb200.h MDB_POT_* */
-enum { ORC_POT_PHS = 0, ORC_POT_LJ = 1, ORC_POT_XPLOR = 2, ORC_POT_POLY = 3 };
+enum { ORC_POT_PHS = 0, ORC_POT_LJ = 1, ORC_POT_XPLOR = 2, ORC_POT_POLY = 3, ORC_POT_SOFT = 4 };
 
 /* ------------------------------------------------------------------------------------------
  * Potentials.  Each returns (u, f) like the reference's `evaluate`; the int return is 1 when the
@@ -122,6 +122,18 @@ static inline double ipow14(double x) { double x2 = x * x; return ipow12(x) * x2
 static inline double ipow16(double x) { double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4; return x8 * x8; }
 
 /* README.md:89-145: user plugin `Polydisperse` / poly_potential.  p[0]=rcut (1.25), p[1]=non_additivity (0.2). */
+/* overlap-removal penalty of the packer (stands in for Packmol.pack_monoatomic!, src/initialization.jl:20-30; the
+ * package is an un-vendored dependency): u = k/2 (1 - r/tol)^2 for r < tol, f = -du/dr; p = {k, tol} */
+static int pot_soft(const double *p, double r, double *u, double *f)
+{
+    double k = p[0], tol = p[1];
+    if (!(r < tol)) { *u = 0.0; *f = 0.0; return 0; }
+    double t = 1.0 - r / tol;
+    *u = 0.5 * k * (t * t);
+    *f = k * t / tol;
+    return 1;
+}
+
 static int pot_poly(const double *p, double r, double s1, double s2, double *u, double *f)
 {
     double r_cut = p[0], non_add = p[1];
@@ -154,6 +166,7 @@ ORC_API int orc_evaluate(int tag, const double *p, double r, double s1, double s
     case ORC_POT_LJ: return pot_lj(p, r, s1, s2, u, f);
     case ORC_POT_XPLOR: return pot_xplor(p, r, s1, s2, u, f);
     case ORC_POT_POLY: return pot_poly(p, r, s1, s2, u, f);
+    case ORC_POT_SOFT: return pot_soft(p, r, u, f);
     }
     *u = NAN; *f = NAN;
     return -1;
@@ -538,6 +551,28 @@ ORC_API void orc_brownian_noise(uint64_t seed, uint64_t step, uint32_t id, int d
         ctr[3] = (ORC_TAG_BROWN << 8) | 1u;
         orc_philox4x32_10(ctr, key, w);
         noise[2] = (2.0 * u53(w[0], w[1]) - 1.0) * sqthree;
+    }
+}
+
+/* src/initialization.jl:22-27 initialize_random, first half: rand(rng, dim) .* (maxs .- mins) .+ mins with mins = 0.
+ *   position uniforms: ctr = (particle_id, stream_lo, stream_hi, 0x9051<<8 | block); block 0 gives u_x = (w0,w1),
+ *   u_y = (w2,w3); block 1 gives u_z = (w0,w1); x_k = L_k * u53, or 0 if the product rounds up to L_k. */
+#define ORC_TAG_POS 0x9051u
+ORC_API void orc_random_positions(int dim, int64_t n, const double *box, uint64_t seed, uint64_t stream, double *x)
+{
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, w[4];
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t ctr[4] = {(uint32_t)i, (uint32_t)stream, (uint32_t)(stream >> 32), (ORC_TAG_POS << 8) | 0u};
+        orc_philox4x32_10(ctr, key, w);
+        x[i * dim + 0] = box[0] * u53(w[0], w[1]);
+        x[i * dim + 1] = box[1] * u53(w[2], w[3]);
+        if (dim == 3) {
+            ctr[3] = (ORC_TAG_POS << 8) | 1u;
+            orc_philox4x32_10(ctr, key, w);
+            x[i * dim + 2] = box[2] * u53(w[0], w[1]);
+        }
+        for (int k = 0; k < dim; k++)
+            if (!(x[i * dim + k] < box[k])) x[i * dim + k] = 0.0;
     }
 }
 

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libmdoracle.so")
 
-POT_PHS, POT_LJ, POT_XPLOR, POT_POLY = 0, 1, 2, 3
+POT_PHS, POT_LJ, POT_XPLOR, POT_POLY, POT_SOFT = 0, 1, 2, 3, 4
 NVE, NVT, BROWNIAN = 0, 1, 2
 
 
@@ -64,6 +64,7 @@ def lib():
         _lib.orc_fire.argtypes = [C.c_int, C.c_int64, _dp, _ip, _dp, _dp, C.c_double, C.c_int, _dp, C.c_int64] + [C.c_double] * 6 + \
             [C.c_int, _dp, C.POINTER(C.c_int), _dp]
         _lib.orc_init_velocities.argtypes = [C.c_int, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, _dp]
+        _lib.orc_random_positions.argtypes = [C.c_int, C.c_int64, _dp, C.c_uint64, C.c_uint64, _dp]
         _lib.orc_threads.restype = C.c_int
         _lib.orc_run_timing.restype = C.c_int
         _lib.orc_run_timing.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, C.c_double, C.c_int,
@@ -160,6 +161,14 @@ def brownian_noise(seed, step, pid, dim):
     out = np.zeros(3)
     lib().orc_brownian_noise(seed, step, pid, dim, _d(out))
     return out[:dim]
+
+
+def random_positions(dim, n, box, seed, stream=0):
+    """src/initialization.jl:22-27: uniform points of the cell from the counter-based generator; returns (n, dim)"""
+    x = np.zeros((n, dim))
+    b = np.ascontiguousarray(np.asarray(box, dtype=np.float64) * np.ones(3))
+    lib().orc_random_positions(dim, n, _d(b), seed, stream, _d(x))
+    return x
 
 
 def init_velocities(dim, n, ktemp, seed, stream=0):

@@ -141,3 +141,44 @@ def test_checkpoint_errors(md, tmp_path):
     assert ei.value.code == md._capi.ERR_INVALID_ARG
     other.close()
     e.close()
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_random_positions_match_oracle(md, orc, dim):
+    n, box = 5000, (9.0, 11.0, 13.0)[:dim]
+    e = md.Engine(dim, n, np.array(box), 1.0, md._capi.POT_SOFT, (1.0, 1.0), seed=77)
+    e.upload(np.zeros((n, dim)), np.ones(n))
+    e.random_positions(stream=9)
+    x, _, _, img = e.download(velocities=False, forces=False)
+    assert np.array_equal(x, orc.random_positions(dim, n, np.array(box + (1.0,) * (3 - dim)), 77, 9))   # same bits
+    assert np.all(x >= 0) and np.all(x < np.array(box)) and not np.any(img)
+    e.close()
+
+
+def test_soft_penalty_forces_match_oracle(md, orc):
+    from conftest import force_error, relerr
+    n, box = 4000, 14.0
+    x = orc.random_positions(3, n, box, 3, 0)
+    diam = np.ones(n)
+    e = md.Engine(3, n, box, 1.2, md._capi.POT_SOFT, (2.0, 1.2), seed=1)
+    e.upload(x, diam)
+    E, W, npairs = e.compute_forces()
+    F = e.download()[2]
+    ref = orc.forces(x, diam, np.full(3, box), 1.2, orc.POT_SOFT, (2.0, 1.2))
+    assert npairs == ref["n_int"] > 1000
+    assert relerr(E, ref["E"]) <= 1e-12 and relerr(W, ref["W"]) <= 1e-12 and force_error(F, ref["F"]) <= 1e-12
+    e.close()
+
+
+@pytest.mark.parametrize("dim,n,rho", [(3, 4096, 0.8976338790382897), (3, 1024, 0.8976338790382897), (2, 1200, 0.6)])
+def test_initialize_random_removes_every_overlap(md, orc, dim, n, rho):
+    """initialize_random (src/initialization.jl:20-30): random points, then no pair closer than tol -- what Packmol's
+    pack_monoatomic! delivers in the reference -- checked by an independent O(N^2)-free recount in the oracle"""
+    box = (n / rho) ** (1.0 / dim)
+    x = md.initialize_random(box, n, np.random.default_rng(4), dim, tol=1.0)
+    assert x.shape == (n, dim) and np.all(x >= 0) and np.all(x < box)
+    ref = orc.forces(x, np.ones(n), np.full(3, box), 1.0, orc.POT_SOFT, (1.0, 1.0))
+    assert ref["n_int"] == 0                                             # nobody within tol of anybody
+    # and it is a disordered configuration, not a lattice: nearest-neighbour distances are spread out
+    ref2 = orc.forces(x, np.ones(n), np.full(3, box), 1.3, orc.POT_SOFT, (1.0, 1.3))
+    assert ref2["n_int"] > n // 2
