@@ -178,6 +178,27 @@ end
 # initialize_velocities (src/initialization.jl:32-47) on the device; `stream` selects an independent set of draws
 init_velocities!(sys::GPUSystem, ktemp::Float64; stream::Integer=0) =
     check(sys.handle, ccall((:mdb_init_velocities, libmdb), Cint, (Handle, Float64, UInt64), sys.handle, ktemp, UInt64(stream)))
+# mdb_fire_params (include/mdb200.h) and the FIRE minimiser, second caller of the force path (src/minimize.jl:31-135)
+struct FireParams
+    max_steps::Int64
+    tol::Float64
+    dt_initial::Float64
+    dt_max::Float64
+    alpha0::Float64
+    f_inc::Float64
+    f_dec::Float64
+    n_min::Int32
+    reserved::Int32
+end
+"returns (energy, F_rms, steps_done, converged) like fire_minimize! reports them (src/minimize.jl:127-135)"
+function fire_minimize!(sys::GPUSystem; max_steps::Int=10_000, tol::Float64=1e-6, dt_initial::Float64=0.01, dt_max::Float64=0.1,
+                        alpha0::Float64=0.1, f_inc::Float64=1.2, f_dec::Float64=0.2, n_min::Int=5)
+    fp = Ref(FireParams(max_steps, tol, dt_initial, dt_max, alpha0, f_inc, f_dec, Int32(n_min), Int32(0)))
+    out, conv = zeros(3), Ref{Int32}(0)
+    check(sys.handle, ccall((:mdb_fire_minimize, libmdb), Cint, (Handle, Ptr{FireParams}, Ptr{Float64}, Ptr{Int32}), sys.handle, fp, out, conv))
+    return out[1], out[2], Int(out[3]), conv[] != 0
+end
+
 # initialize_random (src/initialization.jl:20-30) on the GPU: uniform points of the cell, then FIRE on the penalty
 # potential MDB_POT_SOFT until no pair is closer than `tol` (what Packmol.pack_monoatomic! does on the host)
 function initialize_random_gpu(unitcell, npart::Int, dimension::Int; tol::Float64=1.0, seed::UInt64=rand(UInt64), device::Int=0)
