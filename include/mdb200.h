@@ -35,7 +35,8 @@ enum mdb_status {
     MDB_ERR_INVALID_ARG = 1,
     MDB_ERR_CUDA = 2,
     MDB_ERR_UNSUPPORTED_POTENTIAL = 3, /* Potential subtype without a device functor (src/types.jl:4-6 errors likewise) */
-    MDB_ERR_UNSUPPORTED_CELL = 4,      /* non-diagonal unit cell (to_unitcell matrix branch, src/initialization.jl:13-15) */
+    MDB_ERR_UNSUPPORTED_CELL = 4,      /* a feature that needs a diagonal unit cell (slab decomposition, user potentials) was
+                                          asked for with a general one (to_unitcell matrix branch, src/initialization.jl:13-15) */
     MDB_ERR_BOX_TOO_SMALL = 5,         /* cutoff >= L/2 in a periodic direction */
     MDB_ERR_NO_DEVICE = 6,
     MDB_ERR_NCCL = 7,
@@ -72,7 +73,9 @@ typedef struct mdb_config {
     int32_t dim;            /* 2 or 3                       (initialize_state(dimension=...), src/initialization.jl:116) */
     int32_t potential;      /* enum mdb_potential           (Parameters.potential, src/types.jl:12) */
     int64_t n_particles;    /* global particle count        (Parameters.n_particles, src/types.jl:10) */
-    double unitcell[9];     /* row-major 3x3, upper-left dim x dim used; must be diagonal (SimulationState.unitcell) */
+    double unitcell[9];     /* row-major 3x3, upper-left dim x dim used: the matrix of SimulationState.unitcell, lattice vectors
+                               in its columns (x = U*frac, src/boundary.jl:7-17); diagonal (per-axis arithmetic) or general /
+                               triclinic (fractional-coordinate wrap, nearest image and cell grid) */
     double cutoff;          /* neighbour cutoff             (initialize_state(cutoff=1.5), src/initialization.jl:118) */
     double pot_params[8];   /* see enum mdb_potential */
     uint64_t seed;          /* key of the counter-based RNG (replaces SimulationState.rng, src/types.jl:21) */

@@ -202,7 +202,7 @@ end
 # initialize_random (src/initialization.jl:20-30) on the GPU: uniform points of the cell, then FIRE on the penalty
 # potential MDB_POT_SOFT until no pair is closer than `tol` (what Packmol.pack_monoatomic! does on the host)
 function initialize_random_gpu(unitcell, npart::Int, dimension::Int; tol::Float64=1.0, seed::UInt64=rand(UInt64), device::Int=0)
-    cell = ntuple(k -> (k in (1, 5, 9) && cld(k, 4) <= dimension) ? Float64(unitcell[cld(k, 4), cld(k, 4)]) : 0.0, 9)
+    cell = ntuple(q -> (r = (q - 1) ÷ 3 + 1; c = (q - 1) % 3 + 1; (r <= dimension && c <= dimension) ? Float64(unitcell[r, c]) : 0.0), 9)
     tp = 1.001 * tol
     cfg = MdbConfig(dimension, Int32(4), npart, cell, tp, pad8((1.0, tp)), seed, device, 0, 0.0, 1, 0, 1, Int32(0), 0.0,
                     ntuple(_ -> Int32(0), 2))

@@ -292,7 +292,8 @@ def initialize_random(unitcell, npart, rng, dimension, tol=1.0, device=0, max_st
     the host in the reference -- by FIRE minimisation (mdb_fire_minimize) of the penalty u = k/2 (1 - r/tol')^2 on a
     scratch handle with MDB_POT_SOFT, tol' = 1.001 tol, until no pair is closer than tol (mdb_count_pairs).  Returns the
     (npart, dimension) positions; raises if the density does not admit such a packing within max_steps."""
-    box = np.diag(to_unitcell(unitcell, dimension)).astype(np.float64)
+    cell = np.asarray(to_unitcell(unitcell, dimension), dtype=np.float64)
+    box = cell if np.any(cell != np.diag(np.diag(cell))) else np.diag(cell).copy()   # general cells go in as matrices
     if seed is None:
         seed = int(rng.integers(0, 2 ** 63 - 1))
     tol_pack = 1.001 * float(tol)
@@ -444,8 +445,7 @@ def initialize_state(params, pathname, from_file="", dimension=3, random_init=Fa
             positions = initialize_random(unitcell, n_particles, rng, dimension, device=device)
         diameters = np.ones(n_particles)
     diameters = np.ascontiguousarray(diameters, dtype=np.float64)
-    if np.any(unitcell != np.diag(np.diag(unitcell))):
-        raise _capi.MdbError(_capi.ERR_UNSUPPORTED_CELL, "only diagonal (orthorhombic) unit cells are supported")
+    triclinic = bool(np.any(unitcell != np.diag(np.diag(unitcell))))   # full matrix: lattice vectors in the columns
     pot = params.potential
     if pot.tag is None:
         # no device functor: mirror the reference's `error("evaluate not implemented ...")` (src/types.jl:4-6)
@@ -454,7 +454,7 @@ def initialize_state(params, pathname, from_file="", dimension=3, random_init=Fa
     if seed is None:
         seed = int(rng.integers(0, 2 ** 63 - 1))
     user = isinstance(pot, UserPotential)
-    engine = _capi.Engine(dimension, n_particles, np.diag(unitcell), float(cutoff), _capi.POT_PSEUDOHS if user else pot.tag,
+    engine = _capi.Engine(dimension, n_particles, np.asarray(unitcell) if triclinic else np.diag(unitcell), float(cutoff), _capi.POT_PSEUDOHS if user else pot.tag,
                           () if user else pot.params(), seed=seed, device=device, mode=modes[mode], skin=skin or 0.0,
                           use_graph=use_graph)
     if user:

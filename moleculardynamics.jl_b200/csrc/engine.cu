@@ -48,7 +48,10 @@ struct mdb_engine_s {
     int64_t N = 0;  // global particle count
     int n = 0;      // particles resident on this handle
     int64_t cap = 0;
-    double L[3] = {1, 1, 1};
+    double L[3] = {1, 1, 1};   // cell edge lengths; for a general (triclinic) cell: its perpendicular widths
+    bool tri = false;          // unit cell with off-diagonal entries (x = U frac, src/boundary.jl:7-17)
+    double U[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Ui[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double volume = 1.0;
     double smin = 1, smax = 1;
     double r_search = 0, skin = 0, r_grid = 0, cutoff2 = 0;
     int mode = MDB_MODE_CELLS;  // resolved: CELLS, LIST; brute = tiny-box all-pairs
@@ -238,6 +241,19 @@ static void drop_graph(Engine *e)
     e->gexec = nullptr; e->graph = nullptr; e->gexec_last = nullptr; e->graph_last = nullptr; e->gkey = GraphKey{};
 }
 
+// inverse of the 3x3 cell matrix by the adjugate (same formula, same operation order as oracle/md_oracle.c
+// orc_cell_inverse, so host, device and oracle work with identical U^-1); returns the determinant
+static double cell_inverse(const double *U, double *Ui)
+{
+    const double a = U[0], b = U[1], c = U[2], d = U[3], e = U[4], f = U[5], g = U[6], h = U[7], i = U[8];
+    const double A = e * i - f * h, B = f * g - d * i, C = d * h - e * g;
+    const double det = a * A + b * B + c * C;
+    Ui[0] = A / det;             Ui[1] = (c * h - b * i) / det; Ui[2] = (b * f - c * e) / det;
+    Ui[3] = B / det;             Ui[4] = (a * i - c * g) / det; Ui[5] = (c * d - a * f) / det;
+    Ui[6] = C / det;             Ui[7] = (b * g - a * h) / det; Ui[8] = (a * e - b * d) / det;
+    return det;
+}
+
 // choose grid + neighbour strategy for the resident particle set
 static int plan_neighbors(Engine *e)
 {
@@ -247,10 +263,8 @@ static int plan_neighbors(Engine *e)
     e->cutoff2 = e->cfg.cutoff * e->cfg.cutoff;
     for (int k = 0; k < d; k++)
         if (!(e->r_search < 0.5 * e->L[k]))
-            return fail(e, MDB_ERR_BOX_TOO_SMALL, "search radius must be < L/2 in every periodic direction");
-    double volume = 1.0;
-    for (int k = 0; k < d; k++) volume *= e->L[k];
-    double rho = (double)e->N / volume;
+            return fail(e, MDB_ERR_BOX_TOO_SMALL, "search radius must be < L/2 (half the perpendicular width of the cell) in every periodic direction");
+    double rho = (double)e->N / e->volume;
     double skin = e->cfg.skin > 0 ? e->cfg.skin : 0.25 * e->r_search;
     auto cells_for = [&](double r, int nc[3]) {
         bool ok = true;
@@ -297,6 +311,9 @@ static int plan_neighbors(Engine *e)
         g.hL[k] = 0.5 * e->L[k];
         g.cinv[k] = (double)nc[k] / e->L[k];
     }
+    g.tri = e->tri ? 1 : 0;
+    memcpy(g.U, e->U, sizeof(g.U));
+    memcpy(g.Ui, e->Ui, sizeof(g.Ui));
     e->ncell = (int64_t)nc[0] * nc[1] * nc[2];
     g.slab = 0;
     g.c0 = 0;
@@ -338,7 +355,7 @@ static int plan_neighbors(Engine *e)
     // mdb_compute_forces / mdb_count_pairs / mdb_fire_minimize
     // measured on B200 (tools/small_probe.py): 15 / 20 / 41 us per step at N = 256 / 1024 / 4096 against 30 / 31 / 32 us for
     // the graph-replayed multi-kernel step, so MDB_MODE_AUTO switches over at 2048 particles
-    e->small = !e->slab && e->cfg.potential != MDB_POT_USER &&
+    e->small = !e->slab && !e->tri && e->cfg.potential != MDB_POT_USER &&
                ((want == MDB_MODE_AUTO && e->N <= 2048) || (want == MDB_MODE_SMALL && e->N <= kSmallMaxN));
     if (e->small) {
         e->small_skin = std::max(e->cfg.skin > 0 ? e->cfg.skin : 0.0, 0.4 * e->r_search);
@@ -480,8 +497,12 @@ static void enqueue_rebuild(Engine *e)
         k_flip<<<1, 1, 0, s>>>(e->ctl, nullptr);
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
-            k_build_list<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
-                                                                         e->nnbr, e->ovf, e->ctl, e->xref);
+            if (e->tri)
+                k_build_list<DIM, true><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
+                                                                                   e->nnbr, e->ovf, e->ctl, nullptr);
+            else
+                k_build_list<DIM, false><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
+                                                                                    e->nnbr, e->ovf, e->ctl, e->xref);
         }
     }
 }
@@ -543,8 +564,12 @@ static void enqueue_force(Engine *e, double dt)
         if (e->brute)
             k_force_brute<DIM, Pot, KICK2 != 0><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, e->cutoff2, pot, e->pp, dt, out);
         else if (e->mode == MDB_MODE_LIST) {
-            k_force_list<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
-                                                                       pot, e->pp, dt, out, 0);
+            if (e->tri)
+                k_force_list<DIM, Pot, KICK2, false, true><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                     e->r_grid + e->skin, pot, e->pp, dt, out, 0);
+            else
+                k_force_list<DIM, Pot, KICK2, false, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                      e->r_grid + e->skin, pot, e->pp, dt, out, 0);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
                                                                                   e->pp, dt, out, blocks, 0);
         } else
@@ -580,6 +605,14 @@ static void query_occupancy(Engine *e)
                 if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, true>, kForceBlock, 0);
                 else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, false>, kForceBlock, 0);
                 a = std::min(a, c2);
+                if (e->tri) {
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, false, true>, kForceBlock, 0);
+                    a = std::min(a, c2);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 1, false, true>, kForceBlock, 0);
+                    a = std::min(a, c2);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 0, false, true>, kForceBlock, 0);
+                    b = std::min(b, c2);
+                }
             }
         } else {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_cells<DIM, Pot, true>, kForceBlock, 0);
@@ -636,7 +669,7 @@ static void enqueue_step_head(Engine *e, int ensemble, double dt, cudaGraphCondi
         enqueue_skin_check(e, 1.0, handle, use_handle);
     } else {
         // Brownian: the mover measured the true displacement since the list build (exact test, list mode only)
-        enqueue_skin_check(e, 1.0, handle, use_handle, (e->mode == MDB_MODE_LIST && !e->brute) ? 1 : 0);
+        enqueue_skin_check(e, 1.0, handle, use_handle, (e->mode == MDB_MODE_LIST && !e->brute && !e->tri) ? 1 : 0);
     }
 }
 // the part of one step after the rebuild
@@ -656,7 +689,7 @@ static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, do
         if (prof) cudaEventRecord(e->evp[3], e->stream);
         if (prof) cudaEventRecord(e->evp[0], e->stream);
         k_brownian<DIM><<<stream_grid(e), kStreamBlock, 0, e->stream>>>(e->n, e->grid, dt, ktemp, std::sqrt(2.0 * dt), e->cfg.seed,
-                                                                      e->ctl, (e->mode == MDB_MODE_LIST && !e->brute) ? e->xref : nullptr, 0);
+                                                                      e->ctl, (e->mode == MDB_MODE_LIST && !e->brute && !e->tri) ? e->xref : nullptr, 0);
         if (prof) cudaEventRecord(e->evp[1], e->stream);
         enqueue_finalize(e, ensemble, dt, tau, thermo, 1);
     }
@@ -1570,12 +1603,25 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     if (cfg->dim != 2 && cfg->dim != 3) return fail(nullptr, MDB_ERR_INVALID_ARG, "dim must be 2 or 3");
     if (cfg->n_particles < 1 || cfg->n_particles > (1ll << 27)) return fail(nullptr, MDB_ERR_INVALID_ARG, "n_particles out of range (1 .. 2^27 per handle)");
     if (!(cfg->cutoff > 0)) return fail(nullptr, MDB_ERR_INVALID_ARG, "cutoff must be > 0");
+    bool tri = false;
     for (int r = 0; r < cfg->dim; r++)
         for (int c = 0; c < cfg->dim; c++) {
             double v = cfg->unitcell[3 * r + c];
-            if (r != c && v != 0.0) return fail(nullptr, MDB_ERR_UNSUPPORTED_CELL, "only diagonal (orthorhombic) unit cells are supported");
-            if (r == c && !(v > 0)) return fail(nullptr, MDB_ERR_INVALID_ARG, "unit cell diagonal must be positive");
+            if (!std::isfinite(v)) return fail(nullptr, MDB_ERR_INVALID_ARG, "unit cell must be finite");
+            if (r != c && v != 0.0) tri = true;
         }
+    double U9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Ui9[9];
+    for (int r = 0; r < cfg->dim; r++)
+        for (int c = 0; c < cfg->dim; c++) U9[3 * r + c] = cfg->unitcell[3 * r + c];
+    const double det = cell_inverse(U9, Ui9);
+    if (!tri) {
+        for (int r = 0; r < cfg->dim; r++)
+            if (!(cfg->unitcell[4 * r] > 0)) return fail(nullptr, MDB_ERR_INVALID_ARG, "unit cell diagonal must be positive");
+    } else {
+        if (!(std::fabs(det) > 0) || !std::isfinite(1.0 / det)) return fail(nullptr, MDB_ERR_INVALID_ARG, "unit cell is singular");
+        if (cfg->nranks > 1)
+            return fail(nullptr, MDB_ERR_UNSUPPORTED_CELL, "slab decomposition (nranks > 1) needs a diagonal unit cell");
+    }
     switch (cfg->potential) {
     case MDB_POT_PSEUDOHS: case MDB_POT_LJ: case MDB_POT_LJ_XPLOR: case MDB_POT_POLY: case MDB_POT_SOFT: break;
     default: return fail(nullptr, MDB_ERR_UNSUPPORTED_POTENTIAL, "no device functor for this Potential subtype (no CPU fallback exists)");
@@ -1595,6 +1641,15 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     e->rank = cfg->nranks > 1 ? cfg->rank : 0;
     e->slab = e->nranks > 1;
     for (int k = 0; k < 3; k++) e->L[k] = (k < cfg->dim) ? cfg->unitcell[4 * k] : 1.0;
+    e->tri = tri;
+    memcpy(e->U, U9, sizeof(U9));
+    memcpy(e->Ui, Ui9, sizeof(Ui9));
+    e->volume = std::fabs(det);
+    if (tri) {
+        // perpendicular width along lattice direction k = 1 / |row k of U^-1| (the reciprocal vector)
+        for (int k = 0; k < cfg->dim; k++)
+            e->L[k] = 1.0 / std::sqrt(Ui9[3 * k] * Ui9[3 * k] + Ui9[3 * k + 1] * Ui9[3 * k + 1] + Ui9[3 * k + 2] * Ui9[3 * k + 2]);
+    }
     memcpy(e->pp.p, cfg->pot_params, sizeof(e->pp.p));
     memset(&e->stats, 0, sizeof(e->stats));
     memset(&e->grid, 0, sizeof(e->grid));
@@ -2221,6 +2276,7 @@ MDB_EXPORT int mdb_set_user_potential(mdb_handle e, const char *body, const doub
 {
     if (!e || !body) return MDB_ERR_INVALID_ARG;
     if (e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_set_user_potential must be called before mdb_upload");
+    if (e->tri) return fail(e, MDB_ERR_UNSUPPORTED_CELL, "user-defined potentials need a diagonal unit cell");
     if (n_params < 0 || n_params > 7 || (n_params > 0 && !params)) return fail(e, MDB_ERR_INVALID_ARG, "at most 7 parameters (p[7] is reserved)");
     if (!(range > 0)) return fail(e, MDB_ERR_INVALID_ARG, "range must be > 0");
     std::string why;
@@ -2248,8 +2304,8 @@ MDB_EXPORT int mdb_set_user_potential(mdb_handle e, const char *body, const doub
     std::vector<std::string> names;
     for (int k = 0; k < 2; k++) {
         std::string kk = k ? "true" : "false", ki = k ? "1" : "0";
-        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + ki + ", false>");
-        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + ki + ", true>");
+        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + ki + ", false, false>");
+        names.push_back("mdb::k_force_list<" + D + ", mdb::PotUser, " + ki + ", true, false>");
         names.push_back("mdb::k_force_overflow<" + D + ", mdb::PotUser, " + ki + ">");
         names.push_back("mdb::k_force_cells<" + D + ", mdb::PotUser, " + kk + ">");
         names.push_back("mdb::k_force_brute<" + D + ", mdb::PotUser, " + kk + ">");
@@ -2438,7 +2494,7 @@ struct FrameIO {
     std::string io_error;
     // what the writer needs of the engine
     int device = 0, dim = 3;
-    double L[3] = {1, 1, 1};
+    double U[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // cell matrix, lattice vectors in the columns
 };
 
 // write_to_file_lammps for a diagonal cell: same header lines, same "%lf" columns (src/io.jl:97-167)
@@ -2453,17 +2509,20 @@ static bool write_lammps_frame(const FrameIO *f, const FrameJob &job, std::strin
     const int64_t n = f->n;
     fprintf(fp, "ITEM: TIMESTEP\n%lld\n", (long long)job.step);
     fprintf(fp, "ITEM: NUMBER OF ATOMS\n%lld\n", (long long)n);
+    // box bounds = norms of the lattice vectors (columns), tilt factors xy = U[1,2], xz = U[1,3], yz = U[2,3] (src/io.jl:104-128)
+    const double *U = f->U;
+    auto coln = [&](int c) { return std::sqrt(U[c] * U[c] + U[3 + c] * U[3 + c] + U[6 + c] * U[6 + c]); };
     if (dim == 2) {
         fprintf(fp, "ITEM: BOX BOUNDS xy pp pp\n");
-        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[0], 0.0);
-        fprintf(fp, "%lf %lf 0.0\n", 0.0, f->L[1]);
+        fprintf(fp, "%lf %lf %lf\n", 0.0, std::sqrt(U[0] * U[0] + U[3] * U[3]), U[1]);
+        fprintf(fp, "%lf %lf 0.0\n", 0.0, std::sqrt(U[1] * U[1] + U[4] * U[4]));
         fprintf(fp, "%lf %lf 0.0\n", 0.0, 1.0);
         fprintf(fp, "ITEM: ATOMS id type radius x y xu yu\n");
     } else {
         fprintf(fp, "ITEM: BOX BOUNDS xy xz yz pp pp pp\n");
-        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[0], 0.0);
-        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[1], 0.0);
-        fprintf(fp, "%lf %lf %lf\n", 0.0, f->L[2], 0.0);
+        fprintf(fp, "%lf %lf %lf\n", 0.0, coln(0), U[1]);
+        fprintf(fp, "%lf %lf %lf\n", 0.0, coln(1), U[5]);
+        fprintf(fp, "%lf %lf %lf\n", 0.0, coln(2), U[2]);
         fprintf(fp, "ITEM: ATOMS id type radius x y z xu yu zu\n");
     }
     // rows are formatted in parallel blocks and written in order
@@ -2557,7 +2616,8 @@ static int ensure_frames(Engine *e)
     f->dim = e->dim;
     f->width = 2 * e->dim + 1;
     f->device = e->cfg.device;
-    for (int k = 0; k < 3; k++) f->L[k] = e->L[k];
+    memcpy(f->U, e->U, sizeof(f->U));
+    if (e->dim == 2) f->U[8] = 0.0;  // the writer's 3x3 boxmat of a 2-D cell has an empty third column (src/io.jl:101-102)
     const size_t bytes = sizeof(double) * (size_t)f->n * f->width;
     for (int q = 0; q < MDB_FRAME_SLOTS; q++) {
         CU(cudaMalloc(&f->d_frame[q], bytes));

@@ -34,7 +34,100 @@ struct Grid {
     uint32_t g0;                     // neighbour indices >= g0 address ghosts: gpos_m[j]
     const uint32_t *gstart_l, *gstart_r;  // [ny*nz + 1] ghost index ranges per (cz,cy) row
     const double4 *gpos_m;           // ghost positions, biased so that gpos_m[g0 + k] is ghost record k
+    // general (triclinic) unit cell, x = U frac with the lattice vectors in the columns of U (src/boundary.jl:7-17,
+    // src/initialization.jl:7-18), row-major 3x3 (a 2-D cell is embedded with U[2][2] = 1).  tri == 0: diagonal cell,
+    // the per-axis arithmetic above is used and U, Ui are ignored.  With tri != 0 the cell grid lives in fractional
+    // coordinates (nc cells per lattice direction) and L holds the perpendicular widths of the cell.
+    int tri;
+    double U[9], Ui[9];
 };
+
+// o = M v, every row summed left to right (the oracle's order, oracle/md_oracle.c "general unit cells")
+__device__ __forceinline__ void mat3_mul(const double *M, const double (&v)[3], double (&o)[3])
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++) o[r] = M[3 * r] * v[0] + M[3 * r + 1] * v[1] + M[3 * r + 2] * v[2];
+}
+// wrap_to_box (src/boundary.jl:7-17): frac = U^-1 x; n = floor(frac); x = U (frac - n).  ncr receives n (the image update).
+// TRI template argument of the geometry helpers: -1 decide at run time from g.tri, 0 / 1 decided at compile time (the hot
+// kernels are instantiated per cell type so the diagonal-cell code carries nothing of the general one)
+template <int DIM, int TRI = -1>
+__device__ __forceinline__ void wrap_point(const Grid &g, double (&x)[3], double (&ncr)[3])
+{
+    const bool tri = (TRI < 0) ? (g.tri != 0) : (TRI != 0);
+    if (!tri) {
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double frac = g.invL[k] * x[k];
+            ncr[k] = floor(frac);
+            x[k] = g.L[k] * (frac - ncr[k]);
+        }
+        if (DIM == 2) ncr[2] = 0.0;
+    } else {
+        double fr[3];
+        if (DIM == 2) x[2] = 0.0;
+        mat3_mul(g.Ui, x, fr);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            ncr[k] = (k < DIM) ? floor(fr[k]) : 0.0;
+            fr[k] = (k < DIM) ? fr[k] - ncr[k] : 0.0;
+        }
+        mat3_mul(g.U, fr, x);
+    }
+}
+// unwrapped(p, img, boxmat) = p + boxmat * img (src/io.jl:62-70)
+template <int DIM>
+__device__ __forceinline__ void unwrap_point(const Grid &g, const double (&x)[3], const int32_t (&im)[3], double (&xu)[3])
+{
+    if (!g.tri) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) xu[k] = (k < DIM) ? x[k] + g.L[k] * (double)im[k] : 0.0;
+    } else {
+        const double iv[3] = {(double)im[0], (double)im[1], (DIM == 3) ? (double)im[2] : 0.0};
+        double sh[3];
+        mat3_mul(g.U, iv, sh);
+#pragma unroll
+        for (int k = 0; k < 3; k++) xu[k] = (k < DIM) ? x[k] + sh[k] : 0.0;
+    }
+}
+// minimum image of a separation vector: k = nearbyint(d / L) per axis, or k = nearbyint(U^-1 d), d -= U k
+template <int DIM, int TRI = -1>
+__device__ __forceinline__ void min_image(const Grid &g, double &dx, double &dy, double &dz)
+{
+    const bool tri = (TRI < 0) ? (g.tri != 0) : (TRI != 0);
+    if (!tri) {
+        dx = dx - nearbyint(dx * g.invL[0]) * g.L[0];
+        dy = dy - nearbyint(dy * g.invL[1]) * g.L[1];
+        if (DIM == 3) dz = dz - nearbyint(dz * g.invL[2]) * g.L[2];
+    } else {
+        const double d[3] = {dx, dy, (DIM == 3) ? dz : 0.0};
+        double fr[3], sh[3];
+        mat3_mul(g.Ui, d, fr);
+        const double kk[3] = {nearbyint(fr[0]), nearbyint(fr[1]), (DIM == 3) ? nearbyint(fr[2]) : 0.0};
+        mat3_mul(g.U, kk, sh);
+        dx = dx - sh[0];
+        dy = dy - sh[1];
+        if (DIM == 3) dz = dz - sh[2];
+    }
+}
+// Cartesian shift of the periodic image (kx, ky, kz) of the cell
+template <int DIM, int TRI = -1>
+__device__ __forceinline__ void image_shift(const Grid &g, int kx, int ky, int kz, double &sx, double &sy, double &sz)
+{
+    const bool tri = (TRI < 0) ? (g.tri != 0) : (TRI != 0);
+    if (!tri) {
+        sx = kx * g.L[0];
+        sy = ky * g.L[1];
+        sz = (DIM == 3) ? kz * g.L[2] : 0.0;
+    } else {
+        const double kk[3] = {(double)kx, (double)ky, (DIM == 3) ? (double)kz : 0.0};
+        double sh[3];
+        mat3_mul(g.U, kk, sh);
+        sx = sh[0];
+        sy = sh[1];
+        sz = (DIM == 3) ? sh[2] : 0.0;
+    }
+}
 
 struct StatePtrs {
     double4 *pos;
@@ -157,6 +250,24 @@ __device__ __forceinline__ int cell_coord(double x, double cinv, int nc)
     int c = (int)(x * cinv);
     return c < nc - 1 ? (c < 0 ? 0 : c) : nc - 1;
 }
+// cell of a (wrapped) position: per axis for a diagonal cell, from the fractional coordinates otherwise
+template <int DIM, int TRI = -1>
+__device__ __forceinline__ void cell_of_point(const Grid &g, const double4 &p, int &cx, int &cy, int &cz)
+{
+    const bool tri = (TRI < 0) ? (g.tri != 0) : (TRI != 0);
+    if (!tri) {
+        cx = cell_coord(p.x, g.cinv[0], g.nc[0]);
+        cy = cell_coord(p.y, g.cinv[1], g.nc[1]);
+        cz = (DIM == 3) ? cell_coord(p.z, g.cinv[2], g.nc[2]) : 0;
+    } else {
+        const double x[3] = {p.x, p.y, (DIM == 3) ? p.z : 0.0};
+        double fr[3];
+        mat3_mul(g.Ui, x, fr);
+        cx = cell_coord(fr[0], (double)g.nc[0], g.nc[0]);
+        cy = cell_coord(fr[1], (double)g.nc[1], g.nc[1]);
+        cz = (DIM == 3) ? cell_coord(fr[2], (double)g.nc[2], g.nc[2]) : 0;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // K0  upload: AoS host image -> device layout, with wrap_to_box (src/boundary.jl:7-17)
@@ -172,17 +283,26 @@ __global__ void k_import(int64_t n, const double *__restrict__ x, const double *
     int32_t m[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < DIM; k++) {
-        double xv = x[i * DIM + k];
-        int32_t iv = im ? im[i * DIM + k] : 0;
-        double invL = g.invL[k];
-        if (xv < 0.0 || xv >= g.L[k]) {
-            double frac = invL * xv;
-            double ncr = floor(frac);
-            iv += (int32_t)ncr;
-            xv = g.L[k] * (frac - ncr);
+        p[k] = x[i * DIM + k];
+        m[k] = im ? im[i * DIM + k] : 0;
+    }
+    if (!g.tri) {
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double xv = p[k];
+            if (xv < 0.0 || xv >= g.L[k]) {
+                double frac = g.invL[k] * xv;
+                double ncr = floor(frac);
+                m[k] += (int32_t)ncr;
+                xv = g.L[k] * (frac - ncr);
+            }
+            p[k] = xv;
         }
-        p[k] = xv;
-        m[k] = iv;
+    } else {  // a general cell is always passed through wrap_to_box (wrapping a point inside the cell leaves n = 0)
+        double ncr[3];
+        wrap_point<DIM>(g, p, ncr);
+#pragma unroll
+        for (int k = 0; k < DIM; k++) m[k] += (int32_t)ncr[k];
     }
     s.pos[i] = make_double4(p[0], p[1], p[2], diam[i]);
 #pragma unroll
@@ -238,9 +358,8 @@ __global__ void k_hash(int64_t n, const DevCtl *__restrict__ ctl, Grid g, uint32
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double4 p = ctl->st[ctl->cur].pos[i];
-    int cx = cell_coord(p.x, g.cinv[0], g.nc[0]);
-    int cy = cell_coord(p.y, g.cinv[1], g.nc[1]);
-    int cz = (DIM == 3) ? cell_coord(p.z, g.cinv[2], g.nc[2]) : 0;
+    int cx, cy, cz;
+    cell_of_point<DIM>(g, p, cx, cy, cz);
     uint32_t c = ((uint32_t)cz * g.nc[1] + cy) * g.nxo + (cx - g.c0);
     cell_of[i] = c;
     slot_of[i] = atomicAdd(&counts[c], 1u);
@@ -402,7 +521,7 @@ __global__ void k_gather(int64_t n, const uint32_t *__restrict__ order, const De
 // (same value as the oracle's k = nearbyint(dx/L) for every pair within the search radius).
 // visit(j, dx, dy, dz, d2, sigma_j, code) is called for every candidate j != i with d2 <= r2.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, class Visit>
+template <int DIM, int TRI = -1, class Visit>
 __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__restrict__ start,
                                                const double4 *__restrict__ pos, int i, const double4 &pi, int cx, int cy,
                                                int cz, double r2, Visit &&visit)
@@ -468,7 +587,8 @@ __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__
                         if (d2 <= r2 && (int)j != i) visit((int)j, dx, dy_, dz_, d2, pj.w, code);
                     }
                 } else {
-                    const double sx = kx * g.L[0], sy = ky * g.L[1], sz = (DIM == 3) ? kz * g.L[2] : 0.0;
+                    double sx, sy, sz;
+                    image_shift<DIM, TRI>(g, kx, ky, kz, sx, sy, sz);
                     for (uint32_t j = jb; j < je; j++) {
                         double4 pj = ldg_pos(&src[j]);
                         double dx = (pi.x - pj.x) - sx, dy_ = (pi.y - pj.y) - sy;
@@ -565,7 +685,7 @@ __device__ __forceinline__ void particle_epilogue(int i, const double (&F)[3], c
 // (k_kick_drift's arithmetic, operation for operation: src/integrate.jl:8-38, src/boundary.jl:7-17) while F, v and x are
 // still in registers.  The moved position goes to the other position buffer (neighbours still read this step's
 // positions from the live one); k_finalize swaps the two pointers afterwards.  Saves the whole K5 sweep of the next step.
-template <int DIM>
+template <int DIM, int TRI = -1>
 __device__ __forceinline__ void leap_epilogue(int i, const double (&F)[3], const double (&vel)[3], const double4 &pi, const StatePtrs &s,
                                               double4 *__restrict__ pos_next, const Grid &g, double dt, double &ke2, double &vmax2)
 {
@@ -579,12 +699,13 @@ __device__ __forceinline__ void leap_epilogue(int i, const double (&F)[3], const
         v += h;                 // next step's first half kick (alpha == 1 in NVE)
         s.vel[k * s.cap + i] = v;
         w2 = (k == 0) ? v * v : w2 + v * v;
-        double xv = x[k] + v * dt;
-        double frac = g.invL[k] * xv;
-        double ncr = floor(frac);
-        if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
-        x[k] = g.L[k] * (frac - ncr);
+        x[k] = x[k] + v * dt;
     }
+    double ncr[3];
+    wrap_point<DIM, TRI>(g, x, ncr);
+#pragma unroll
+    for (int k = 0; k < DIM; k++)
+        if (ncr[k] != 0.0) s.img[k * s.cap + i] += (int32_t)ncr[k];
     st_pos(&pos_next[i], make_double4(x[0], x[1], x[2], pi.w));
     ke2 += v2;
     vmax2 = fmax(vmax2, w2);
@@ -642,10 +763,12 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
                 int code = (int)(ent >> 27);
                 int kx = code % 3 - 1, ky = (code / 3) % 3 - 1, kz = code / 9 - 1;
                 double4 pj = ldg_pos(nbr_ptr(g, pos, (uint32_t)j));
-                double dx = (pi.x - pj.x) - kx * g.L[0], dy = (pi.y - pj.y) - ky * g.L[1];
+                double sx, sy, sz;
+                image_shift<DIM>(g, kx, ky, kz, sx, sy, sz);
+                double dx = (pi.x - pj.x) - sx, dy = (pi.y - pj.y) - sy;
                 double d2 = fma(dy, dy, dx * dx), dz = 0.0;
                 if (DIM == 3) {
-                    dz = (pi.z - pj.z) - kz * g.L[2];
+                    dz = (pi.z - pj.z) - sz;
                     d2 = fma(dz, dz, d2);
                 }
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
@@ -653,9 +776,8 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
         };
         if (active) {
             pi = pos[i];
-            int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
-            int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
-            int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
+            int cx, cy, cz;
+            cell_of_point<DIM>(g, pi, cx, cy, cz);
             traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, cutoff2,
                                 [&](int j, double dx, double dy, double dz, double d2, double sj, int code) {
                                     if (pot.may_interact(pp, d2, pi.w, sj)) {
@@ -684,7 +806,7 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
 // nl is column-major: nl[k * stride + i], coalesced across the warp.  Particles with more than kmax neighbours are
 // appended to the overflow list and handled exactly by k_force_overflow.
 // ------------------------------------------------------------------------------------------------
-template <int DIM>
+template <int DIM, bool TRI = false>
 __global__ void __launch_bounds__(kForceBlock)
 k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
              uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, uint32_t *__restrict__ ovf, DevCtl *ctl,
@@ -700,12 +822,11 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
         if (xref) {  // unwrapped position at build time: reference for the exact displacement test of Brownian runs
             const double pk[3] = {pi.x, pi.y, pi.z};
 #pragma unroll
-            for (int k = 0; k < DIM; k++) xref[k * st.cap + i] = pk[k] + g.L[k] * (double)st.img[k * st.cap + i];
+            for (int k = 0; k < DIM; k++) xref[k * st.cap + i] = pk[k] + g.L[k] * (double)st.img[k * st.cap + i];  // (diagonal cells only)
         }
-        int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
-        int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
-        int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
-        traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, rlist2,
+        int cx, cy, cz;
+        cell_of_point<DIM, TRI ? 1 : 0>(g, pi, cx, cy, cz);
+        traverse_cells<DIM, TRI ? 1 : 0>(g, start, pos, i, pi, cx, cy, cz, rlist2,
                             [&](int j, double, double, double, double, double, int) {
                                 if (cnt < kmax) nl[(int64_t)cnt * stride + i] = (uint32_t)j;
                                 cnt++;
@@ -726,9 +847,19 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
 
 // minimum image of a listed pair: positions are re-wrapped every step, so the image is decided per evaluation,
 // dx = (xi - xj) - k*L with k = +-1 when |xi - xj| > L/2 (the oracle's nearbyint gives the same k for listed pairs)
-template <int DIM>
+template <int DIM, int TRI = -1>
 __device__ __forceinline__ double separation_wrap(const Grid &g, const double4 &pi, const double4 &pj, double &dx, double &dy, double &dz)
 {
+    const bool tri = (TRI < 0) ? (g.tri != 0) : (TRI != 0);
+    if (tri) {  // general cell: nearest image through the fractional coordinates
+        dx = pi.x - pj.x;
+        dy = pi.y - pj.y;
+        dz = (DIM == 3) ? pi.z - pj.z : 0.0;
+        min_image<DIM, 1>(g, dx, dy, dz);
+        double q2 = fma(dy, dy, dx * dx);
+        if (DIM == 3) q2 = fma(dz, dz, q2);
+        return q2;
+    }
     dx = pi.x - pj.x;
     if (dx > g.hL[0]) dx -= g.L[0];
     else if (dx < -g.hL[0]) dx += g.L[0];
@@ -793,7 +924,7 @@ struct ListView {
 
 // SLAB: neighbour indices >= g.g0 address the ghost buffer of an x-slab (single domain: no such indices, no select)
 // KICK2: 0 forces only, 1 + second half kick, 2 + second half kick and the next step's kick-drift-wrap (leap_epilogue)
-template <int DIM, class Pot, int KICK2, bool SLAB>
+template <int DIM, class Pot, int KICK2, bool SLAB, bool TRI = false>
 __global__ void __launch_bounds__(kForceBlock, MDB_FORCE_MIN_CTAS)
 k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt,
              ForceOut out, int guard)
@@ -877,13 +1008,14 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
         bool wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
         if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
+        if (TRI) wrap = true;  // general cells: every listed pair goes through the fractional nearest image
         const bool wrap_any = __any_sync(0xffffffffu, wrap);  // warp-uniform: the wrapped separation is exact for every pair
         auto drain_one = [&]() {
             if (nq > 0) {
                 int j = (int)queue[--nq][threadIdx.x];
                 double4 pj = ldg_pos(SLAB ? nbr_ptr(g, pos, (uint32_t)j) : pos + j);
                 double dx, dy, dz, d2;
-                if (wrap_any) d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
+                if (wrap_any) d2 = separation_wrap<DIM, TRI ? 1 : 0>(g, pi, pj, dx, dy, dz);
                 else d2 = separation_plain<DIM>(pi, pj, dx, dy, dz);
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
@@ -908,7 +1040,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
                 double dx, dy, dz;
-                double d2 = wrap ? separation_wrap<DIM>(g, pi, pj[u], dx, dy, dz) : separation_plain<DIM>(pi, pj[u], dx, dy, dz);
+                double d2 = wrap ? separation_wrap<DIM, TRI ? 1 : 0>(g, pi, pj[u], dx, dy, dz) : separation_plain<DIM>(pi, pj[u], dx, dy, dz);
                 const bool valid = k0 + u < cnt;
                 if (write_inner && valid && d2 <= lv.rin2) {
                     if (nin < lv.kmax_in) lv.nl_in[(int64_t)nin * stride + i] = jc[u];
@@ -944,7 +1076,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 }
                 acc.v2 += v2;
             }
-            if (KICK2 == 2) leap_epilogue<DIM>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
+            if (KICK2 == 2) leap_epilogue<DIM, TRI ? 1 : 0>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
         }
     }
     if (KICK2 == 2) leap_report<kForceBlock>(vmax2, dt, ctl);
@@ -1026,16 +1158,15 @@ k_force_brute(int n, const DevCtl *__restrict__ ctl, Grid g, double cutoff2, Pot
             for (int j = 0; j < n; j++) {
                 if (j == i) continue;
                 double4 pj = ldg_pos(&s.pos[j]);
-                double dx = pi.x - pj.x;
-                dx = dx - nearbyint(dx * inv[0]) * g.L[0];
-                double dy = pi.y - pj.y;
-                dy = dy - nearbyint(dy * inv[1]) * g.L[1];
-                double d2 = fma(dy, dy, dx * dx), dz = 0.0;
-                if (DIM == 3) {
-                    dz = pi.z - pj.z;
-                    dz = dz - nearbyint(dz * inv[2]) * g.L[2];
-                    d2 = fma(dz, dz, d2);
-                }
+                double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = (DIM == 3) ? pi.z - pj.z : 0.0;
+                if (!g.tri) {
+                    dx = dx - nearbyint(dx * inv[0]) * g.L[0];
+                    dy = dy - nearbyint(dy * inv[1]) * g.L[1];
+                    if (DIM == 3) dz = dz - nearbyint(dz * inv[2]) * g.L[2];
+                } else
+                    min_image<DIM>(g, dx, dy, dz);
+                double d2 = fma(dy, dy, dx * dx);
+                if (DIM == 3) d2 = fma(dz, dz, d2);
                 if (d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj.w))
                     pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
@@ -1060,9 +1191,8 @@ k_count_pairs(int n, const DevCtl *__restrict__ ctl, Grid g,
     if (i < n) {
         double4 pi = pos[i];
         if (use_cells) {
-            int cx = cell_coord(pi.x, g.cinv[0], g.nc[0]);
-            int cy = cell_coord(pi.y, g.cinv[1], g.nc[1]);
-            int cz = (DIM == 3) ? cell_coord(pi.z, g.cinv[2], g.nc[2]) : 0;
+            int cx, cy, cz;
+            cell_of_point<DIM>(g, pi, cx, cy, cz);
             traverse_cells<DIM>(g, start, pos, i, pi, cx, cy, cz, cutoff2,
                                 [&](int, double, double, double, double, double, int) { cnt++; });
         } else {
@@ -1070,16 +1200,15 @@ k_count_pairs(int n, const DevCtl *__restrict__ ctl, Grid g,
             for (int j = 0; j < n; j++) {
                 if (j == i) continue;
                 double4 pj = ldg_pos(&pos[j]);
-                double dx = pi.x - pj.x;
-                dx = dx - nearbyint(dx * inv[0]) * g.L[0];
-                double dy = pi.y - pj.y;
-                dy = dy - nearbyint(dy * inv[1]) * g.L[1];
+                double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = (DIM == 3) ? pi.z - pj.z : 0.0;
+                if (!g.tri) {
+                    dx = dx - nearbyint(dx * inv[0]) * g.L[0];
+                    dy = dy - nearbyint(dy * inv[1]) * g.L[1];
+                    if (DIM == 3) dz = dz - nearbyint(dz * inv[2]) * g.L[2];
+                } else
+                    min_image<DIM>(g, dx, dy, dz);
                 double d2 = fma(dy, dy, dx * dx);
-                if (DIM == 3) {
-                    double dz = pi.z - pj.z;
-                    dz = dz - nearbyint(dz * inv[2]) * g.L[2];
-                    d2 = fma(dz, dz, d2);
-                }
+                if (DIM == 3) d2 = fma(dz, dz, d2);
                 if (d2 <= cutoff2) cnt++;
             }
         }
@@ -1118,12 +1247,13 @@ k_kick_drift(int n, Grid g, double dt, DevCtl *__restrict__ ctl)
             v += (f * dt) * 0.5;  // == f*dt/2.0 bit-for-bit
             s.vel[k * s.cap + i] = v;
             v2 = (k == 0) ? v * v : v2 + v * v;
-            double xv = x[k] + v * dt;
-            double frac = g.invL[k] * xv;
-            double ncr = floor(frac);
-            if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
-            x[k] = g.L[k] * (frac - ncr);
+            x[k] = x[k] + v * dt;
         }
+        double ncr[3];
+        wrap_point<DIM>(g, x, ncr);
+#pragma unroll
+        for (int k = 0; k < DIM; k++)
+            if (ncr[k] != 0.0) s.img[k * s.cap + i] += (int32_t)ncr[k];
         st_pos(&s.pos[i], make_double4(x[0], x[1], x[2], p.w));
         vmax2 = fmax(vmax2, v2);
     }
@@ -1176,16 +1306,20 @@ k_brownian(int n, Grid g, double dt, double ktemp, double sigma, uint64_t seed, 
         double4 p = ld_pos(&s.pos[i]);
         double x[3] = {p.x, p.y, p.z};
         double d2 = 0.0, r2 = 0.0;
+        double ncrv[3];
 #pragma unroll
         for (int k = 0; k < DIM; k++) {
             double f = s.frc[k * s.cap + i];
             double xv = x[k] + (f * dt / ktemp) + (noise[k] * sigma);
             double del = xv - x[k];
             d2 = (k == 0) ? del * del : d2 + del * del;
-            double frac = g.invL[k] * xv;
-            double ncr = floor(frac);
-            x[k] = g.L[k] * (frac - ncr);
-            if (xref) {
+            x[k] = xv;
+        }
+        wrap_point<DIM>(g, x, ncrv);
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            const double ncr = ncrv[k];
+            if (xref) {  // (diagonal cells only: the engine passes no xref for a general cell)
                 // a random walk moves far less than the sum of its per-step maxima: measure the true displacement from
                 // the positions the Verlet list was built for (unwrapped through the image counters)
                 int32_t im = s.img[k * s.cap + i];
@@ -1418,12 +1552,13 @@ k_fire_move(int n, Grid g, DevCtl *__restrict__ ctl)
             s.vel[k * s.cap + i] = v;
             double step = dt * v;
             d2 = (k == 0) ? step * step : d2 + step * step;
-            double xv = x[k] + step;
-            double frac = g.invL[k] * xv;
-            double ncr = floor(frac);
-            if (ncr != 0.0) s.img[k * s.cap + i] += (int32_t)ncr;
-            x[k] = g.L[k] * (frac - ncr);
+            x[k] = x[k] + step;
         }
+        double ncr[3];
+        wrap_point<DIM>(g, x, ncr);
+#pragma unroll
+        for (int k = 0; k < DIM; k++)
+            if (ncr[k] != 0.0) s.img[k * s.cap + i] += (int32_t)ncr[k];
         st_pos(&s.pos[i], make_double4(x[0], x[1], x[2], p.w));
         dmax2 = fmax(dmax2, d2);
     }

@@ -12,7 +12,7 @@ namespace mdb {
 constexpr uint32_t kTagVel = 0x1E10Cu;  // velocity-initialisation stream (spec: oracle/md_oracle.c "Counter-based RNG")
 
 // frame record of particle `id` (original order): {radius, x[DIM], xu[DIM]}; radius = diameter / 2 as written at
-// src/io.jl:141,153; xu = x + L*img for the diagonal cells this engine supports.
+// src/io.jl:141,153; xu = x + U*img.
 template <int DIM>
 __global__ void __launch_bounds__(kStreamBlock)
 k_pack_frame(int64_t n, const DevCtl *__restrict__ ctl, Grid g, double *__restrict__ frame)
@@ -24,10 +24,15 @@ k_pack_frame(int64_t n, const DevCtl *__restrict__ ctl, Grid g, double *__restri
         const double x[3] = {p.x, p.y, p.z};
         double *out = frame + (int64_t)s.id[i] * W;
         out[0] = p.w / 2.0;
+        int32_t im[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < DIM; k++) im[k] = s.img[k * s.cap + i];
+        double xu[3];
+        unwrap_point<DIM>(g, x, im, xu);
 #pragma unroll
         for (int k = 0; k < DIM; k++) {
             out[1 + k] = x[k];
-            out[1 + DIM + k] = x[k] + g.L[k] * (double)s.img[k * s.cap + i];
+            out[1 + DIM + k] = xu[k];
         }
     }
 }
@@ -157,16 +162,25 @@ k_random_positions(int64_t n, Grid g, uint64_t seed, uint64_t stream, DevCtl *__
     for (int64_t i = blockIdx.x * (int64_t)kStreamBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStreamBlock) {
         const uint32_t id = (uint32_t)s.id[i];
         Philox4 o = philox4x32_10(id, (uint32_t)stream, (uint32_t)(stream >> 32), (kTagPos << 8) | 0u, k0, k1);
-        double x[3] = {g.L[0] * u53(o.w[0], o.w[1]), g.L[1] * u53(o.w[2], o.w[3]), 0.0};
+        double u[3] = {u53(o.w[0], o.w[1]), u53(o.w[2], o.w[3]), 0.0};
         if (DIM == 3) {
             Philox4 q = philox4x32_10(id, (uint32_t)stream, (uint32_t)(stream >> 32), (kTagPos << 8) | 1u, k0, k1);
-            x[2] = g.L[2] * u53(q.w[0], q.w[1]);
+            u[2] = u53(q.w[0], q.w[1]);
+        }
+        double x[3] = {0.0, 0.0, 0.0};
+        if (!g.tri) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                x[k] = g.L[k] * u[k];
+                if (!(x[k] < g.L[k])) x[k] = 0.0;
+            }
+        } else {  // uniform in the cell: uniform fractional coordinates (wrapped like any other position)
+            double ncr[3];
+            mat3_mul(g.U, u, x);
+            wrap_point<DIM>(g, x, ncr);
         }
 #pragma unroll
-        for (int k = 0; k < DIM; k++) {
-            if (!(x[k] < g.L[k])) x[k] = 0.0;
-            s.img[k * s.cap + i] = 0;
-        }
+        for (int k = 0; k < DIM; k++) s.img[k * s.cap + i] = 0;
         const double w = s.pos[i].w;
         s.pos[i] = make_double4(x[0], x[1], x[2], w);
     }

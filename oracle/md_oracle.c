@@ -668,6 +668,123 @@ ORC_API int orc_run(int ensemble, int dim, int64_t n, double *x, double *v, doub
 }
 
 /* ------------------------------------------------------------------------------------------
+ * General (triclinic) unit cells.  The cell is a dim x dim matrix with the lattice vectors in its columns, x = U*frac
+ * (to_unitcell, src/initialization.jl:7-18; wrap_to_box, src/boundary.jl:7-17; CellListMap accepts the same matrix,
+ * src/initialization.jl:100-107).  U is passed row-major embedded in 3x3 (U[3*r+c]; a 2-D cell has U[8] = 1).
+ * Matrix-vector products sum each row left to right.  Pairs: every unordered pair whose nearest periodic image,
+ * d - U*nearbyint(U^-1 d), lies within the cutoff (valid for cutoff < half the smallest perpendicular width).
+ * ---------------------------------------------------------------------------------------- */
+ORC_API double orc_cell_inverse(const double *U, double *Ui)
+{
+    const double a = U[0], b = U[1], c = U[2], d = U[3], e = U[4], f = U[5], g = U[6], h = U[7], i = U[8];
+    const double A = e * i - f * h, B = f * g - d * i, C = d * h - e * g;
+    const double det = a * A + b * B + c * C;
+    Ui[0] = A / det;             Ui[1] = (c * h - b * i) / det; Ui[2] = (b * f - c * e) / det;
+    Ui[3] = B / det;             Ui[4] = (a * i - c * g) / det; Ui[5] = (c * d - a * f) / det;
+    Ui[6] = C / det;             Ui[7] = (b * g - a * h) / det; Ui[8] = (a * e - b * d) / det;
+    return det;
+}
+
+static inline void mat3_mul(const double *M, const double *v, double *o)
+{
+    for (int r = 0; r < 3; r++) o[r] = M[3 * r] * v[0] + M[3 * r + 1] * v[1] + M[3 * r + 2] * v[2];
+}
+
+/* src/boundary.jl:7-17 with a full matrix */
+ORC_API void orc_wrap_tri(int dim, double *x, int32_t *img, const double *U, const double *Ui)
+{
+    double v[3] = {x[0], x[1], dim == 3 ? x[2] : 0.0}, fr[3], o[3];
+    mat3_mul(Ui, v, fr);
+    for (int k = 0; k < 3; k++) {
+        double nc = k < dim ? floor(fr[k]) : 0.0;
+        fr[k] = k < dim ? fr[k] - nc : 0.0;
+        if (k < dim) img[k] += (int32_t)nc;
+    }
+    mat3_mul(U, fr, o);
+    for (int k = 0; k < dim; k++) x[k] = o[k];
+}
+
+ORC_API int orc_forces_tri(int dim, int64_t n, const double *x, const double *diam, const double *U, double cutoff, int tag,
+                           const double *p, double *Fout, double *E, double *W, int64_t *n_cut, int64_t *n_int)
+{
+    double Ui[9];
+    orc_cell_inverse(U, Ui);
+    double *xs = malloc(sizeof(double) * n * dim);
+    long double *F = calloc(n * dim, sizeof(long double));
+    if (!xs || !F) { free(xs); free(F); return -1; }
+    for (int64_t i = 0; i < n; i++) {
+        int32_t scratch[3] = {0, 0, 0};
+        for (int k = 0; k < dim; k++) xs[i * dim + k] = x[i * dim + k];
+        orc_wrap_tri(dim, xs + i * dim, scratch, U, Ui);
+    }
+    pair_acc acc = {0, 0, 0, 0};
+    double cutoff2 = cutoff * cutoff;
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t j = i + 1; j < n; j++) {
+            double d[3] = {0, 0, 0}, fr[3], kk[3], sh[3];
+            for (int k = 0; k < dim; k++) d[k] = xs[i * dim + k] - xs[j * dim + k];
+            mat3_mul(Ui, d, fr);
+            for (int k = 0; k < 3; k++) kk[k] = k < dim ? nearbyint(fr[k]) : 0.0;
+            mat3_mul(U, kk, sh);
+            double d2 = 0.0;
+            for (int k = 0; k < dim; k++) {
+                d[k] = d[k] - sh[k];
+                d2 = (k == 0) ? d[k] * d[k] : fma(d[k], d[k], d2);
+            }
+            if (d2 <= cutoff2) pair_update(dim, d, d2, i, j, diam, tag, p, F, &acc, NULL);
+        }
+    finish(dim, n, F, &acc, Fout, E, W, n_cut, n_int);
+    free(xs); free(F);
+    return 0;
+}
+
+/* the loops of orc_run with the general cell (all-pairs enumeration: small systems) */
+ORC_API int orc_run_tri(int ensemble, int dim, int64_t n, double *x, double *v, double *f, int32_t *img, const double *diam,
+                        const double *U, double cutoff, int tag, const double *p, double dt, int64_t nsteps,
+                        const double *ktemp_per_step, double tau, double nf, uint64_t seed, uint64_t rng_step0, double *thermo)
+{
+    double Ui[9];
+    orc_cell_inverse(U, Ui);
+    for (int64_t s = 0; s < nsteps; s++) {
+        double E, W, ke = 0.0;
+        int64_t n_cut, n_int;
+        if (ensemble == 2) {
+            if (orc_forces_tri(dim, n, x, diam, U, cutoff, tag, p, f, &E, &W, &n_cut, &n_int)) return -1;
+            double sigma = sqrt(2.0 * dt);
+            for (int64_t i = 0; i < n; i++) {
+                double noise[3];
+                orc_brownian_noise(seed, rng_step0 + s, (uint32_t)i, dim, noise);
+                for (int k = 0; k < dim; k++)
+                    x[i * dim + k] = x[i * dim + k] + (f[i * dim + k] * dt / ktemp_per_step[0]) + (noise[k] * sigma);
+                orc_wrap_tri(dim, x + i * dim, img + i * dim, U, Ui);
+            }
+        } else {
+            for (int64_t i = 0; i < n; i++) {
+                for (int k = 0; k < dim; k++) {
+                    v[i * dim + k] += f[i * dim + k] * dt / 2.0;
+                    x[i * dim + k] += v[i * dim + k] * dt;
+                }
+                orc_wrap_tri(dim, x + i * dim, img + i * dim, U, Ui);
+            }
+            if (orc_forces_tri(dim, n, x, diam, U, cutoff, tag, p, f, &E, &W, &n_cut, &n_int)) return -1;
+            orc_integrate_second_half(dim, n, v, f, dt);
+            if (ensemble == 1) {
+                double r1, r2;
+                double k0 = orc_kinetic(dim, n, v);
+                orc_bussi_noises(seed, rng_step0 + s, nf, &r1, &r2);
+                double scale = orc_bussi_scale(k0, ktemp_per_step[s], nf, dt, tau, r1, r2);
+                for (int64_t q = 0; q < n * dim; q++) v[q] = v[q] * scale;
+            }
+            ke = orc_kinetic(dim, n, v);
+        }
+        if (thermo) {
+            thermo[4 * s + 0] = E; thermo[4 * s + 1] = W; thermo[4 * s + 2] = ke; thermo[4 * s + 3] = (double)n_int;
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Timing variant: "reference-equivalent CPU path" (BASELINE.md section 3).  Same algorithmic shape as
  * the Julia package: cell list rebuilt EVERY step with cell = cutoff (src/simulation.jl:100-104),
  * one visit per unordered pair with Newton's third law (src/pairwise.jl:35-36), per-thread

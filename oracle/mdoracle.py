@@ -65,6 +65,14 @@ def lib():
             [C.c_int, _dp, C.POINTER(C.c_int), _dp]
         _lib.orc_init_velocities.argtypes = [C.c_int, C.c_int64, C.c_double, C.c_uint64, C.c_uint64, _dp]
         _lib.orc_random_positions.argtypes = [C.c_int, C.c_int64, _dp, C.c_uint64, C.c_uint64, _dp]
+        _lib.orc_cell_inverse.restype = C.c_double
+        _lib.orc_cell_inverse.argtypes = [_dp, _dp]
+        _lib.orc_wrap_tri.argtypes = [C.c_int, _dp, _ip, _dp, _dp]
+        _lib.orc_forces_tri.restype = C.c_int
+        _lib.orc_forces_tri.argtypes = [C.c_int, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _lp, _lp]
+        _lib.orc_run_tri.restype = C.c_int
+        _lib.orc_run_tri.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, C.c_double, C.c_int, _dp,
+                                     C.c_double, C.c_int64, _dp, C.c_double, C.c_double, C.c_uint64, C.c_uint64, _dp]
         _lib.orc_threads.restype = C.c_int
         _lib.orc_run_timing.restype = C.c_int
         _lib.orc_run_timing.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, C.c_double, C.c_int,
@@ -161,6 +169,69 @@ def brownian_noise(seed, step, pid, dim):
     out = np.zeros(3)
     lib().orc_brownian_noise(seed, step, pid, dim, _d(out))
     return out[:dim]
+
+
+def cell3(cell, dim):
+    """dim x dim cell matrix (lattice vectors in the columns) embedded row-major in 3x3"""
+    U = np.eye(3)
+    U[:dim, :dim] = np.asarray(cell, dtype=np.float64)[:dim, :dim]
+    return np.ascontiguousarray(U.ravel())
+
+
+def cell_inverse(cell, dim):
+    U = cell3(cell, dim)
+    Ui = np.zeros(9)
+    det = lib().orc_cell_inverse(_d(U), _d(Ui))
+    return Ui.reshape(3, 3), det
+
+
+def wrap_tri(x, img, cell):
+    """wrap_to_box with a full matrix (src/boundary.jl:7-17), row by row"""
+    x = np.array(x, dtype=np.float64)
+    img = np.array(img, dtype=np.int32)
+    n, dim = x.shape
+    U = cell3(cell, dim)
+    Ui = np.ascontiguousarray(cell_inverse(cell, dim)[0].ravel())
+    for i in range(n):
+        xi, ii = np.ascontiguousarray(x[i]), np.ascontiguousarray(img[i])
+        lib().orc_wrap_tri(dim, _d(xi), _i(ii), _d(U), _d(Ui))
+        x[i], img[i] = xi, ii
+    return x, img
+
+
+def forces_tri(x, diam, cell, cutoff, tag, params=()):
+    """all-pairs enumeration under a general unit cell -> dict(F, E, W, n_cut, n_int)"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n, dim = x.shape
+    diam = np.ascontiguousarray(diam, dtype=np.float64)
+    U, q = cell3(cell, dim), _params(params)
+    F = np.zeros_like(x)
+    E, W = C.c_double(), C.c_double()
+    ncut, nint = C.c_int64(), C.c_int64()
+    rc = lib().orc_forces_tri(dim, n, _d(x), _d(diam), _d(U), float(cutoff), tag, _d(q), _d(F), C.byref(E), C.byref(W),
+                              C.byref(ncut), C.byref(nint))
+    if rc != 0:
+        raise RuntimeError("oracle forces_tri failed rc=%d" % rc)
+    return dict(F=F, E=E.value, W=W.value, n_cut=ncut.value, n_int=nint.value)
+
+
+def run_tri(ensemble, x, v, f, img, diam, cell, cutoff, tag, params, dt, nsteps, ktemp=None, tau=1.0, nf=None, seed=0,
+            rng_step0=0):
+    """orc_run with a general unit cell; returns (x, v, f, img, thermo)"""
+    x, v, f = (np.array(a, dtype=np.float64) for a in (x, v, f))
+    img = np.array(img, dtype=np.int32)
+    n, dim = x.shape
+    diam = np.ascontiguousarray(diam, dtype=np.float64)
+    U, q = cell3(cell, dim), _params(params)
+    if nf is None:
+        nf = dim * (n - 1.0)
+    kt = np.ascontiguousarray(np.broadcast_to(np.asarray(1.0 if ktemp is None else ktemp, dtype=np.float64), (max(nsteps, 1),)))
+    thermo = np.zeros((nsteps, 4))
+    rc = lib().orc_run_tri(ensemble, dim, n, _d(x), _d(v), _d(f), _i(img), _d(diam), _d(U), float(cutoff), tag, _d(q), dt, nsteps,
+                           _d(kt), tau, nf, seed, rng_step0, _d(thermo))
+    if rc != 0:
+        raise RuntimeError("oracle run_tri failed rc=%d" % rc)
+    return x, v, f, img, thermo
 
 
 def random_positions(dim, n, box, seed, stream=0):

@@ -162,9 +162,9 @@ def test_bitwise_reproducible(md, orc):
 
 def test_error_paths(md):
     from mdjl_b200 import _capi
-    with pytest.raises(md.MdbError) as ei:
-        md.Engine(3, 100, np.array([[5, 1, 0], [0, 5, 0], [0, 0, 5.0]]), 1.5, 0)
-    assert ei.value.code == _capi.ERR_UNSUPPORTED_CELL
+    with pytest.raises(md.MdbError) as ei:   # singular cell matrix (tilted cells themselves are supported: test_gpu_triclinic.py)
+        md.Engine(3, 100, np.array([[5, 5, 0], [5, 5, 0], [0, 0, 5.0]]), 1.5, 0)
+    assert ei.value.code == _capi.ERR_INVALID_ARG
     with pytest.raises(md.MdbError) as ei:
         md.Engine(3, 100, 5.0, 1.5, 42)
     assert ei.value.code == _capi.ERR_UNSUPPORTED_POTENTIAL
