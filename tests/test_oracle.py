@@ -251,3 +251,35 @@ def test_init_velocities_restatement(orc):
     pair = orc.init_velocities(2, 2, 1.0, 99, 5)
     d_raw, d_out = box_muller(0) - box_muller(1), pair[0] - pair[1]
     assert np.allclose(d_out / np.linalg.norm(d_out), d_raw / np.linalg.norm(d_raw), rtol=0, atol=1e-14)
+
+
+def test_general_cell_restatement(orc):
+    """wrap_to_box with a full matrix (src/boundary.jl:7-17) and the nearest-image pair enumeration: x + U*img preserved,
+    fractional coordinates in [0, 1), a diagonal matrix reproduces the per-axis oracle, forces are invariant under
+    shifting any particle by a lattice vector, and sum to zero"""
+    rng = np.random.default_rng(11)
+    cell = np.array([[11.0, 2.5, -1.5], [0.7, 10.0, 2.0], [-0.4, 0.9, 12.0]])
+    Ui, det = orc.cell_inverse(cell, 3)
+    assert np.allclose(Ui @ cell, np.eye(3), atol=1e-15) and abs(det - np.linalg.det(cell)) < 1e-9
+    x = rng.uniform(-50, 70, (400, 3))
+    xw, img = orc.wrap_tri(x, np.zeros((400, 3), np.int32), cell)
+    fr = np.linalg.solve(cell, xw.T).T
+    assert fr.min() > -1e-13 and fr.max() < 1 + 1e-13
+    assert np.max(np.abs(xw + img @ cell.T - x)) < 1e-12
+    xw2, img2 = orc.wrap_tri(xw, img, cell)                         # idempotent up to rounding of the round trip
+    assert np.max(np.abs(xw2 - xw)) < 1e-12 and np.array_equal(img2, img)
+    # diagonal matrix == per-axis brute force
+    L = np.array([9.0, 10.0, 11.0])
+    xo = rng.uniform(0, 1, (300, 3)) * L
+    a = orc.forces_tri(xo, np.ones(300), np.diag(L), 1.5, orc.POT_SOFT, (1.0, 1.5))
+    b = orc.forces(xo, np.ones(300), L, 1.5, orc.POT_SOFT, (1.0, 1.5), brute=True)
+    assert a["n_cut"] == b["n_cut"] and a["n_int"] == b["n_int"]
+    assert np.allclose(a["F"], b["F"], rtol=1e-13, atol=1e-15) and abs(a["E"] - b["E"]) <= 1e-13 * abs(b["E"])
+    # lattice-vector shifts change nothing; Newton's third law
+    xs = xw[:300].copy()
+    ref = orc.forces_tri(xs, np.ones(300), cell, 1.4, orc.POT_SOFT, (1.0, 1.4))
+    shift = rng.integers(-2, 3, (300, 3)) @ cell.T
+    moved = orc.forces_tri(xs + shift, np.ones(300), cell, 1.4, orc.POT_SOFT, (1.0, 1.4))
+    assert ref["n_cut"] == moved["n_cut"] > 100
+    assert np.allclose(ref["F"], moved["F"], rtol=0, atol=1e-11) and abs(ref["E"] - moved["E"]) < 1e-11
+    assert np.max(np.abs(ref["F"].sum(axis=0))) < 1e-12
