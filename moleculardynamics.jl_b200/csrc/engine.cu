@@ -1745,11 +1745,41 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     CU(cudaSetDevice(e->cfg.device));
     const int64_t n = e->N;
     const size_t d = (size_t)e->dim;
+    // single domain with the staging buffers already in place (every upload after the first): the host-to-device copies
+    // start now and overlap the host-side scan of the diameters and the planning below
+    bool staged = false;
+    if (!e->slab && e->stage_n >= n && e->sx && n > 0) {
+        cudaStream_t s0 = e->stream;
+        CU(cudaMemcpyAsync(e->sx, positions, sizeof(double) * n * d, cudaMemcpyHostToDevice, s0));
+        CU(cudaMemcpyAsync(e->sd, diameters, sizeof(double) * n, cudaMemcpyHostToDevice, s0));
+        if (velocities) CU(cudaMemcpyAsync(e->sv, velocities, sizeof(double) * n * d, cudaMemcpyHostToDevice, s0));
+        if (forces) CU(cudaMemcpyAsync(e->sf, forces, sizeof(double) * n * d, cudaMemcpyHostToDevice, s0));
+        if (images) CU(cudaMemcpyAsync(e->si, images, sizeof(int32_t) * n * d, cudaMemcpyHostToDevice, s0));
+        staged = true;
+    }
     // diameter extrema decide the potential's range (non-additive mixtures)
     double smin = diameters[0], smax = diameters[0];
-    for (int64_t i = 1; i < n; i++) {
-        smin = std::min(smin, diameters[i]);
-        smax = std::max(smax, diameters[i]);
+    {
+        const int nthr = (n >= (1 << 20)) ? (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1;
+        std::vector<double> lo(nthr, diameters[0]), hi(nthr, diameters[0]);
+        auto scan = [&](int t) {
+            const int64_t b = n * t / nthr, en = n * (t + 1) / nthr;
+            double a = diameters[b], c = diameters[b];
+            for (int64_t i = b + 1; i < en; i++) {
+                a = std::min(a, diameters[i]);
+                c = std::max(c, diameters[i]);
+            }
+            lo[t] = a;
+            hi[t] = c;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; t++) th.emplace_back(scan, t);
+        scan(0);
+        for (auto &t : th) t.join();
+        for (int t = 0; t < nthr; t++) {
+            smin = std::min(smin, lo[t]);
+            smax = std::max(smax, hi[t]);
+        }
     }
     if (!(smin > 0) || !std::isfinite(smax)) return fail(e, MDB_ERR_INVALID_ARG, "diameters must be positive and finite");
     e->smin = smin; e->smax = smax;
@@ -1809,7 +1839,7 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     if (e->dim == 3) query_occupancy<3>(e);
     else query_occupancy<2>(e);
     cudaStream_t s = e->stream;
-    if (n_res > 0) {
+    if (n_res > 0 && !staged) {
         CU(cudaMemcpyAsync(e->sx, hx, sizeof(double) * n_res * d, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(e->sd, hd, sizeof(double) * n_res, cudaMemcpyHostToDevice, s));
         if (hv) CU(cudaMemcpyAsync(e->sv, hv, sizeof(double) * n_res * d, cudaMemcpyHostToDevice, s));
