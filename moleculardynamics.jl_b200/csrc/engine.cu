@@ -605,7 +605,13 @@ static void query_occupancy(Engine *e)
                 if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, true>, kForceBlock, 0);
                 else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, false>, kForceBlock, 0);
                 a = std::min(a, c2);
+                if (!e->slab) {
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 3, false, false>, kForceBlock, 0);
+                    b = std::min(b, c2);
+                }
                 if (e->tri) {
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 3, false, true>, kForceBlock, 0);
+                    b = std::min(b, c2);
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 2, false, true>, kForceBlock, 0);
                     a = std::min(a, c2);
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, k_force_list<DIM, Pot, 1, false, true>, kForceBlock, 0);
@@ -650,11 +656,15 @@ static void enqueue_finalize(Engine *e, int ensemble, double dt, double tau, int
 // kick, thermo.  NVE runs in list mode rotate it: one kick-drift in front of the run, then kStepFused steps whose force
 // kernel also performs the NEXT step's kick-drift (KICK2 = 2, no K5 sweep at all), and a kStepLast that ends the run
 // with the plain second kick -- the state after n steps is bit-identical to n kStepFull steps.
-enum StepKind { kStepFull = 0, kStepFused = 1, kStepLast = 2 };
+// Brownian runs in list mode (single domain) fuse the move into the force kernel too (KICK2 = 3, kStepBrownFused): a
+// Brownian step IS forces-then-move (src/simulation.jl:231-250), so every step is fused and nothing special happens at
+// the ends of a run.
+enum StepKind { kStepFull = 0, kStepFused = 1, kStepLast = 2, kStepBrownFused = 3 };
 static bool fused_step(const Engine *e, int ensemble)
 {
     static const bool off = getenv("MDB200_NO_FUSE") != nullptr;
-    return ensemble == MDB_NVE && e->mode == MDB_MODE_LIST && !e->brute && e->cfg.potential != MDB_POT_USER && !e->cfg.no_fuse && !off;
+    if (e->mode != MDB_MODE_LIST || e->brute || e->cfg.potential == MDB_POT_USER || e->cfg.no_fuse || off) return false;
+    return ensemble == MDB_NVE || (ensemble == MDB_BROWNIAN && !e->slab);
 }
 
 // the part of one step before the (conditional) rebuild
@@ -683,6 +693,13 @@ static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, do
         else enqueue_force<DIM, 1>(e, dt);
         if (prof) cudaEventRecord(e->evp[3], e->stream);
         enqueue_finalize(e, ensemble, dt, tau, thermo, 1, 0, 0, kind == kStepFused ? 1 : 0);
+    } else if (kind == kStepBrownFused) {
+        if (prof) cudaEventRecord(e->evp[2], e->stream);
+        if (prof) cudaEventRecord(e->evp[0], e->stream);
+        if (prof) cudaEventRecord(e->evp[1], e->stream);
+        enqueue_force<DIM, 3>(e, dt);  // forces + move; parameters were put into DevCtl by k_set_brownian
+        if (prof) cudaEventRecord(e->evp[3], e->stream);
+        enqueue_finalize(e, ensemble, dt, tau, thermo, 1, 0, 0, 1);
     } else {
         if (prof) cudaEventRecord(e->evp[2], e->stream);
         enqueue_force<DIM, 0>(e, dt);
@@ -703,7 +720,9 @@ static int build_graph(Engine *e, const GraphKey &key)
 {
     drop_graph(e);
     int rc;
-    if (key.fused) {
+    if (key.fused && key.ensemble == MDB_BROWNIAN) {
+        if ((rc = build_one_graph<DIM>(e, key, kStepBrownFused, &e->graph, &e->gexec))) return rc;
+    } else if (key.fused) {
         if ((rc = build_one_graph<DIM>(e, key, kStepFused, &e->graph, &e->gexec))) return rc;
         if ((rc = build_one_graph<DIM>(e, key, kStepLast, &e->graph_last, &e->gexec_last))) return rc;
     } else if ((rc = build_one_graph<DIM>(e, key, kStepFull, &e->graph, &e->gexec)))
@@ -1495,6 +1514,10 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
         if (rc) return rc;
     }
     CU(cudaEventRecord(e->ev0, s));
+    if (ensemble == MDB_BROWNIAN && fused) {
+        k_set_brownian<<<1, 1, 0, s>>>(e->ctl, ktemp, std::sqrt(2.0 * dt), (unsigned long long)e->cfg.seed, e->tri ? nullptr : e->xref);
+        e->stats.kernel_launches += 1;
+    }
     e->stats.prof_kick_ms = e->stats.prof_force_ms = e->stats.prof_rebuild_ms = 0.0;
     e->stats.prof_steps = 0;
     int64_t done = 0;
@@ -1512,7 +1535,8 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
         for (int64_t q = 0; q < m; q++) {
             // fused NVE schedule: the run's only stand-alone kick-drift, then fused steps, then a plain last step
             int kind = kStepFull;
-            if (fused) {
+            if (fused && ensemble == MDB_BROWNIAN) kind = kStepBrownFused;
+            else if (fused) {
                 kind = (done + q == nsteps - 1) ? kStepLast : kStepFused;
                 if (done + q == 0) {
                     k_kick_drift<DIM><<<kick_grid(e), kStreamBlock, 0, s>>>(e->n, e->grid, dt, e->ctl);

@@ -165,6 +165,10 @@ struct DevCtl {
     StatePtrs st[2];
     double fire[8];               // FIRE scalars: dt, alpha, steps_since_neg, converged, P, vnorm2, fnorm2, energy
     double scratch[4];            // initialize_velocities: mean per component, scale factor (setup_io.cuh)
+    // Brownian parameters of the run in progress, read by the fused force + move kernel (KICK2 == 3)
+    double bd_ktemp, bd_sigma;
+    unsigned long long bd_seed;
+    const double *bd_xref;        // unwrapped build-time positions for the exact displacement test, or null
 };
 
 
@@ -719,6 +723,59 @@ __device__ __forceinline__ void leap_report(double vmax2, double dt, DevCtl *ctl
     if (threadIdx.x == 0) atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
 }
 
+// Fused Brownian step (KICK2 == 3): the move x += f*dt/kT + noise*sigma, wrap (k_brownian's arithmetic, operation for
+// operation: src/integrate.jl:66-82) while F and x are in registers; the moved position goes to the other position
+// buffer like in the fused NVE step.
+template <int DIM, int TRI = -1>
+__device__ __forceinline__ void brown_epilogue(int i, const double (&F)[3], const double4 &pi, const StatePtrs &s,
+                                               double4 *__restrict__ pos_next, const Grid &g, double dt, const DevCtl *__restrict__ ctl,
+                                               unsigned long long rng_step, double &dmax2, double &dref2)
+{
+    const double ktemp = ctl->bd_ktemp, sigma = ctl->bd_sigma;
+    const double *__restrict__ xref = ctl->bd_xref;
+    double noise[3];
+    brownian_noise<DIM>(ctl->bd_seed, rng_step, (uint32_t)s.id[i], noise);
+    double x[3] = {pi.x, pi.y, pi.z};
+    double d2 = 0.0, r2 = 0.0;
+    double ncrv[3];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        double xv = x[k] + (F[k] * dt / ktemp) + (noise[k] * sigma);
+        double del = xv - x[k];
+        d2 = (k == 0) ? del * del : d2 + del * del;
+        x[k] = xv;
+    }
+    wrap_point<DIM, TRI>(g, x, ncrv);
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+        const double ncr = ncrv[k];
+        if (xref) {
+            int32_t im = s.img[k * s.cap + i];
+            if (ncr != 0.0) {
+                im += (int32_t)ncr;
+                s.img[k * s.cap + i] = im;
+            }
+            double dr = (x[k] + g.L[k] * (double)im) - xref[k * s.cap + i];
+            r2 = (k == 0) ? dr * dr : r2 + dr * dr;
+        } else if (ncr != 0.0) {
+            s.img[k * s.cap + i] += (int32_t)ncr;
+        }
+    }
+    st_pos(&pos_next[i], make_double4(x[0], x[1], x[2], pi.w));
+    dmax2 = fmax(dmax2, d2);
+    dref2 = fmax(dref2, r2);
+}
+template <int BLOCK>
+__device__ __forceinline__ void brown_report(double dmax2, double dref2, DevCtl *ctl)
+{
+    double r[2] = {dmax2, dref2};
+    block_reduce<2, BLOCK, true>(r);
+    if (threadIdx.x == 0) {
+        atomicMax(&ctl->dmax2_bits, (unsigned long long)__double_as_longlong(r[0]));
+        if (ctl->bd_xref) atomicMax(&ctl->dref2_bits, (unsigned long long)__double_as_longlong(r[1]));
+    }
+}
+
 // one deterministic CTA reduction at the end of the persistent loop
 __device__ __forceinline__ void cta_epilogue(const ThreadSums &acc, ForceOut out, int slot)
 {
@@ -936,7 +993,8 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 == 2 only
-    double vmax2 = 0.0;
+    double vmax2 = 0.0, dref2 = 0.0;
+    const unsigned long long rng_step = ctl->rng_step;  // KICK2 == 3 only
     const bool refresh = ctl->inner_refresh != 0;  // uniform over the grid
     const uint32_t *__restrict__ nl = refresh ? lv.nl : lv.nl_in;
     const int32_t *__restrict__ nnbr = refresh ? lv.nnbr : lv.nnbr_in;
@@ -974,7 +1032,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         for (int u = 0; u < kUnroll; u++) jj[u] = jn[u];
         // this tile's velocities (needed only by the epilogue) and the next tile's operands: in flight during the gathers
         double vel[3] = {0.0, 0.0, 0.0};
-        if (KICK2 && active) {
+        if ((KICK2 == 1 || KICK2 == 2) && active) {
 #pragma unroll
             for (int k = 0; k < DIM; k++) vel[k] = s.vel[k * s.cap + i];
         }
@@ -1077,9 +1135,11 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 acc.v2 += v2;
             }
             if (KICK2 == 2) leap_epilogue<DIM, TRI ? 1 : 0>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
+            if (KICK2 == 3) brown_epilogue<DIM, TRI ? 1 : 0>(i, F, pi, s, pos_next, g, dt, ctl, rng_step, vmax2, dref2);
         }
     }
     if (KICK2 == 2) leap_report<kForceBlock>(vmax2, dt, ctl);
+    if (KICK2 == 3) brown_report<kForceBlock>(vmax2, dref2, ctl);
     if (refresh) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) max_in = max(max_in, __shfl_xor_sync(0xffffffffu, max_in, o));
@@ -1100,8 +1160,9 @@ k_force_overflow(DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ 
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     const int novf = ctl->n_overflow;
-    double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 == 2 only
-    double vmax2 = 0.0;
+    double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 >= 2 only
+    double vmax2 = 0.0, dref2 = 0.0;
+    const unsigned long long rng_step = ctl->rng_step;
     ThreadSums acc;
     for (int q = blockIdx.x * kForceBlock + threadIdx.x; q < novf; q += gridDim.x * kForceBlock) {
         const int i = (int)ovf[q];
@@ -1130,10 +1191,15 @@ k_force_overflow(DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ 
                 vel[k] = s.vel[k * s.cap + i];
             }
             leap_epilogue<DIM>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
+        } else if (KICK2 == 3) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
+            brown_epilogue<DIM>(i, F, pi, s, pos_next, g, dt, ctl, rng_step, vmax2, dref2);
         } else
             particle_epilogue<DIM, KICK2 != 0>(i, F, s, dt, acc);
     }
     if (KICK2 == 2 && novf > 0) leap_report<kForceBlock>(vmax2, dt, ctl);  // novf is grid-uniform
+    if (KICK2 == 3 && novf > 0) brown_report<kForceBlock>(vmax2, dref2, ctl);
     cta_epilogue(acc, out, slot0 + blockIdx.x);
 }
 
@@ -1276,6 +1342,13 @@ __global__ void k_scale(int n, DevCtl *ctl)
     }
 }
 __global__ void k_reset_alpha(DevCtl *ctl) { ctl->alpha = 1.0; }
+__global__ void k_set_brownian(DevCtl *ctl, double ktemp, double sigma, unsigned long long seed, const double *xref)
+{
+    ctl->bd_ktemp = ktemp;
+    ctl->bd_sigma = sigma;
+    ctl->bd_seed = seed;
+    ctl->bd_xref = xref;
+}
 // after the gather-reorder: the other state buffer becomes live
 __global__ void k_flip(DevCtl *ctl, const uint32_t *__restrict__ n_new)
 {

@@ -77,6 +77,27 @@ def test_fused_nve_step_is_bit_identical_to_reference_order(md, orc, use_graph):
     assert out[1][2]["kernel_launches"] < out[0][2]["kernel_launches"]
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_brownian_step_is_bit_identical_to_reference_order(md, orc, use_graph):
+    """Brownian list-mode runs do the move inside the force kernel (no separate K8 sweep): same bits as forces-then-move
+    in two kernels, across list rebuilds (exact displacement test included) and several run calls"""
+    from mdjl_b200 import workloads
+    n = 4096
+    cfg = workloads.phs_fluid(n)
+    out = []
+    for no_fuse in (True, False):
+        e = md.Engine(3, n, cfg["box"], 1.5, md._capi.POT_PSEUDOHS, seed=31, mode=md._capi.MODE_LIST, use_graph=use_graph, no_fuse=no_fuse)
+        e.upload(cfg["x"], cfg["diam"])
+        rows = [e.run_brownian(k, 2e-5, 1.4737) for k in (1, 2, 400, 37)]
+        out.append((np.concatenate(rows), e.download(), e.stats(), e.rng_step))
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    assert out[0][2]["rebuilds"] == out[1][2]["rebuilds"] > 1 and out[0][3] == out[1][3]
+    assert out[1][2]["kernel_launches"] < out[0][2]["kernel_launches"]
+
+
 def test_list_mode_equals_cell_mode(md, orc):
     """same pair set every step: pair counts identical, energies to rounding, over several list rebuilds"""
     res = {}
