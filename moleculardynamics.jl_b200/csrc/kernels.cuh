@@ -525,7 +525,9 @@ __global__ void k_gather(int64_t n, const uint32_t *__restrict__ order, const De
 // (same value as the oracle's k = nearbyint(dx/L) for every pair within the search radius).
 // visit(j, dx, dy, dz, d2, sigma_j, code) is called for every candidate j != i with d2 <= r2.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int TRI = -1, class Visit>
+// ALWAYS: visit is called for EVERY candidate, with d2 = -1 for the ones that fail the test, so that a visitor can stay
+// branch-free (the list build: a divergent accept path was half of its instructions at 5 of 32 lanes)
+template <int DIM, int TRI = -1, bool ALWAYS = false, class Visit>
 __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__restrict__ start,
                                                const double4 *__restrict__ pos, int i, const double4 &pi, int cx, int cy,
                                                int cz, double r2, Visit &&visit)
@@ -588,7 +590,8 @@ __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__
                             dz_ = pi.z - pj.z;
                             d2 = fma(dz_, dz_, d2);
                         }
-                        if (d2 <= r2 && (int)j != i) visit((int)j, dx, dy_, dz_, d2, pj.w, code);
+                        if (ALWAYS) visit((int)j, dx, dy_, dz_, (d2 <= r2 && (int)j != i) ? d2 : -1.0, pj.w, code);
+                        else if (d2 <= r2 && (int)j != i) visit((int)j, dx, dy_, dz_, d2, pj.w, code);
                     }
                 } else {
                     double sx, sy, sz;
@@ -602,7 +605,8 @@ __device__ __forceinline__ void traverse_cells(const Grid &g, const uint32_t *__
                             dz_ = (pi.z - pj.z) - sz;
                             d2 = fma(dz_, dz_, d2);
                         }
-                        if (d2 <= r2 && (int)j != i) visit((int)j, dx, dy_, dz_, d2, pj.w, code);
+                        if (ALWAYS) visit((int)j, dx, dy_, dz_, (d2 <= r2 && (int)j != i) ? d2 : -1.0, pj.w, code);
+                        else if (d2 <= r2 && (int)j != i) visit((int)j, dx, dy_, dz_, d2, pj.w, code);
                     }
                 }
             }
@@ -883,11 +887,14 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
         }
         int cx, cy, cz;
         cell_of_point<DIM, TRI ? 1 : 0>(g, pi, cx, cy, cz);
-        traverse_cells<DIM, TRI ? 1 : 0>(g, start, pos, i, pi, cx, cy, cz, rlist2,
-                            [&](int j, double, double, double, double, double, int) {
-                                if (cnt < kmax) nl[(int64_t)cnt * stride + i] = (uint32_t)j;
-                                cnt++;
-                            });
+        uint32_t *slot = nl + i;  // next free row of this particle's column
+        traverse_cells<DIM, TRI ? 1 : 0, true>(g, start, pos, i, pi, cx, cy, cz, rlist2,
+                                               [&](int j, double, double, double, double d2, double, int) {
+                                                   const bool hit = d2 >= 0.0;
+                                                   if (hit && cnt < kmax) *slot = (uint32_t)j;
+                                                   slot += hit ? stride : 0;
+                                                   cnt += hit ? 1 : 0;
+                                               });
         nnbr[i] = cnt;
         if (cnt > kmax) ovf[atomicAdd(&ctl->n_overflow, 1)] = (uint32_t)i;
     }
