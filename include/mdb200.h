@@ -127,6 +127,11 @@ int mdb_destroy(mdb_handle h);
  * keeps the particles of its slab. */
 int mdb_upload(mdb_handle h, const double *positions, const double *velocities, const double *forces,
                const double *diameters, const int32_t *images);
+/* nranks > 1, after one mdb_upload has planned the slab: hand back the rows of the particles this rank owns (what
+ * mdb_download_owned returned: original indices + rows), without touching the global arrays.  The next force evaluation
+ * rebuilds the neighbour structures and migrates whatever the host moved across a slab face. */
+int mdb_upload_owned(mdb_handle h, int64_t count, const int32_t *ids, const double *positions, const double *velocities,
+                     const double *forces, const double *diameters, const int32_t *images);
 /* state.velocities = initialize_velocities(...) assignment (README.md:38-41) */
 int mdb_set_velocities(mdb_handle h, const double *velocities);
 /* any pointer may be NULL.  nranks == 1: arrays are [n_particles][dim] in original order.

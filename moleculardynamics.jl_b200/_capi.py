@@ -22,7 +22,7 @@ MODE_AUTO, MODE_CELLS, MODE_LIST, MODE_SMALL = 0, 1, 2, 3
 # every symbol include/mdb200.h declares (tests/test_capi_symbols.py checks the header against this list and the .so)
 SYMBOLS = [
     "mdb_version", "mdb_last_error", "mdb_create", "mdb_destroy", "mdb_upload", "mdb_set_velocities", "mdb_download",
-    "mdb_download_owned", "mdb_compute_forces", "mdb_count_pairs", "mdb_run_nve", "mdb_run_nvt", "mdb_run_brownian",
+    "mdb_download_owned", "mdb_upload_owned", "mdb_compute_forces", "mdb_count_pairs", "mdb_run_nve", "mdb_run_nvt", "mdb_run_brownian",
     "mdb_thermo", "mdb_fire_minimize", "mdb_bussi_scale_from", "mdb_bussi_noises", "mdb_get_rng_step",
     "mdb_set_rng_step", "mdb_set_user_potential", "mdb_comm_unique_id", "mdb_comm_init", "mdb_comm_init_local",
     "mdb_get_stats", "mdb_device_ptr", "mdb_stream", "mdb_synchronize",
@@ -89,6 +89,7 @@ def load():
     L.mdb_set_velocities.argtypes = [_H, _dp]
     L.mdb_download.argtypes = [_H, _dp, _dp, _dp, _ip]
     L.mdb_download_owned.argtypes = [_H, C.c_int64, _ip, _dp, _dp, _dp, _ip, C.POINTER(C.c_int64)]
+    L.mdb_upload_owned.argtypes = [_H, C.c_int64, _ip, _dp, _dp, _dp, _dp, _ip]
     L.mdb_compute_forces.argtypes = [_H, _dp, _dp, C.POINTER(C.c_int64)]
     L.mdb_count_pairs.argtypes = [_H, C.c_double, C.POINTER(C.c_int64), _ip]
     L.mdb_run_nve.argtypes = [_H, C.c_int64, C.c_double, _dp]
@@ -217,6 +218,17 @@ class Engine:
         im = None if images is None else np.ascontiguousarray(images, dtype=np.int32)
         self._check(self._lib.mdb_upload(self._h, _d(x), _d(v), _d(f), _d(d), _i(im)))
 
+    def upload_owned(self, ids, positions, diameters, velocities=None, forces=None, images=None):
+        """slab handle: re-upload the rows this rank owns (as returned by download_owned; `diameters` per row)"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        m = ids.size
+        x = _f64(positions, (m, self.dim))
+        v = _f64(velocities, (m, self.dim))
+        f = _f64(forces, (m, self.dim))
+        dm = _f64(diameters, (m,))
+        im = None if images is None else np.ascontiguousarray(images, dtype=np.int32)
+        self._check(self._lib.mdb_upload_owned(self._h, m, _i(ids), _d(x), _d(v), _d(f), _d(dm), _i(im)))
+
     def set_velocities(self, velocities):
         v = _f64(velocities, (self.n, self.dim))
         self._check(self._lib.mdb_set_velocities(self._h, _d(v)))
@@ -340,9 +352,8 @@ class Engine:
 
     def download_owned(self):
         """-> (ids, x, v, f, img) of the particles this slab currently owns (device slot order)"""
-        cap = int(self.stats()["n_owned"]) + 0
-        # the owned count can change at rebuilds; ask for a safe upper bound
-        cap = max(cap * 2 + 1024, 1024)
+        # the owned count can change at rebuilds (migration moves a thin layer per rebuild): room for 25 % more
+        cap = max(int(int(self.stats()["n_owned"]) * 1.25) + 4096, 4096)
         ids = np.empty(cap, dtype=np.int32)
         x = np.empty((cap, self.dim))
         v = np.empty((cap, self.dim))
@@ -351,7 +362,7 @@ class Engine:
         cnt = C.c_int64()
         self._check(self._lib.mdb_download_owned(self._h, cap, _i(ids), _d(x), _d(v), _d(f), _i(im), C.byref(cnt)))
         k = cnt.value
-        return ids[:k].copy(), x[:k].copy(), v[:k].copy(), f[:k].copy(), im[:k].copy()
+        return ids[:k], x[:k], v[:k], f[:k], im[:k]
 
     def comm_init(self, unique_id):
         """join the NCCL slab ring (one process per GPU); unique_id = bytes from unique_id() on rank 0"""
@@ -425,9 +436,19 @@ class SlabRing:
     def run_brownian(self, nsteps, dt, ktemp, thermo=True):
         return self.lead.run_brownian(nsteps, dt, ktemp, thermo)
 
+    def upload_owned(self, parts):
+        """re-upload owned rows without the global arrays: `parts` = one (ids, x, diameters, v, f, img) tuple per slab this
+        process holds (a single tuple is accepted for the one-slab-per-process NCCL case)"""
+        if isinstance(parts, tuple):
+            parts = [parts]
+        for e, (ids, x, diam, v, f, im) in zip(self.engines, parts):
+            e.upload_owned(ids, x, diam, velocities=v, forces=f, images=im)
+
     def download_local(self):
         """owned particles of the slabs this process holds, concatenated: (ids, x, v, f, img)"""
         parts = [e.download_owned() for e in self.engines]
+        if len(parts) == 1:
+            return parts[0]
         return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
 
     def download(self):

@@ -1818,30 +1818,58 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     int64_t n_res = n;
     if (e->slab) {
         const Grid &g = e->grid;
-        for (int64_t i = 0; i < n; i++) {
-            double xv = positions[i * d];
-            if (xv < 0.0 || xv >= g.L[0]) {
-                double frac = g.invL[0] * xv;
-                xv = g.L[0] * (frac - std::floor(frac));
+        // every rank scans the global arrays for the particles of its cell columns: threaded, chunk results joined in index
+        // order (the kept set and its order do not depend on the thread count)
+        const int nthr = (n >= (1 << 18)) ? (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1;
+        std::vector<std::vector<int32_t>> part(nthr);
+        auto scan = [&](int t) {
+            std::vector<int32_t> &out = part[t];
+            const int64_t b = n * t / nthr, en = n * (t + 1) / nthr;
+            out.reserve((size_t)((en - b) / std::max(1, e->nranks) * 5 / 4 + 16));
+            for (int64_t i = b; i < en; i++) {
+                double xv = positions[i * d];
+                if (xv < 0.0 || xv >= g.L[0]) {
+                    double frac = g.invL[0] * xv;
+                    xv = g.L[0] * (frac - std::floor(frac));
+                }
+                int cx = (int)(xv * g.cinv[0]);
+                cx = cx < g.nc[0] - 1 ? (cx < 0 ? 0 : cx) : g.nc[0] - 1;
+                if (cx >= e->c0 && cx < e->c0 + e->nxo) out.push_back((int32_t)i);
             }
-            int cx = (int)(xv * g.cinv[0]);
-            cx = cx < g.nc[0] - 1 ? (cx < 0 ? 0 : cx) : g.nc[0] - 1;
-            if (cx >= e->c0 && cx < e->c0 + e->nxo) keep.push_back((int32_t)i);
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nthr; t++) th.emplace_back(scan, t);
+            scan(0);
+            for (auto &t : th) t.join();
         }
+        size_t total = 0;
+        for (auto &v : part) total += v.size();
+        keep.reserve(total);
+        for (auto &v : part) keep.insert(keep.end(), v.begin(), v.end());
         n_res = (int64_t)keep.size();
         bx.resize(n_res * d); bd.resize(n_res);
         if (velocities) bv.resize(n_res * d);
         if (forces) bf.resize(n_res * d);
         if (images) bi.resize(n_res * d);
-        for (int64_t q = 0; q < n_res; q++) {
-            int64_t i = keep[q];
-            bd[q] = diameters[i];
-            for (size_t k = 0; k < d; k++) {
-                bx[q * d + k] = positions[i * d + k];
-                if (velocities) bv[q * d + k] = velocities[i * d + k];
-                if (forces) bf[q * d + k] = forces[i * d + k];
-                if (images) bi[q * d + k] = images[i * d + k];
+        auto pack = [&](int t) {
+            const int64_t b = n_res * t / nthr, en = n_res * (t + 1) / nthr;
+            for (int64_t q = b; q < en; q++) {
+                int64_t i = keep[q];
+                bd[q] = diameters[i];
+                for (size_t k = 0; k < d; k++) {
+                    bx[q * d + k] = positions[i * d + k];
+                    if (velocities) bv[q * d + k] = velocities[i * d + k];
+                    if (forces) bf[q * d + k] = forces[i * d + k];
+                    if (images) bi[q * d + k] = images[i * d + k];
+                }
             }
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nthr; t++) th.emplace_back(pack, t);
+            pack(0);
+            for (auto &t : th) t.join();
         }
         hx = bx.data(); hd = bd.data();
         hv = velocities ? bv.data() : nullptr;
@@ -1893,6 +1921,63 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     CU(cudaStreamSynchronize(s));
     CU(cudaGetLastError());
     e->uploaded = true;
+    e->have_vel = velocities != nullptr;
+    e->stats.n_owned = e->n;
+    return MDB_OK;
+}
+
+// Slab re-upload without the global arrays: the caller hands back what mdb_download_owned gave it (ids + rows of the
+// particles this rank owns).  The plan of the last mdb_upload (grid, capacities, exchange buffers) is kept; the
+// neighbour structures are invalidated, so the next force evaluation starts with a rebuild (which also migrates any
+// particle the host moved into a neighbouring slab).
+MDB_EXPORT int mdb_upload_owned(mdb_handle e, int64_t count, const int32_t *ids, const double *positions, const double *velocities,
+                                const double *forces, const double *diameters, const int32_t *images)
+{
+    if (!e) return MDB_ERR_INVALID_ARG;
+    if (!e->slab) return fail(e, MDB_ERR_STATE, "mdb_upload_owned is for slab handles (nranks > 1); use mdb_upload");
+    if (!e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload (global arrays) must plan the slab once before mdb_upload_owned");
+    if (count < 0 || !ids || !positions || !diameters) return fail(e, MDB_ERR_INVALID_ARG, "ids, positions and diameters are required");
+    if (count > e->cap_own) return fail(e, MDB_ERR_INVALID_ARG, "more particles than the slab capacity planned by mdb_upload");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc;
+    if ((rc = ensure_stage(e, std::max<int64_t>(count, 1)))) return rc;
+    cudaStream_t s = e->stream;
+    const size_t d = (size_t)e->dim;
+    if (count > 0) {
+        CU(cudaMemcpyAsync(e->sx, positions, sizeof(double) * count * d, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(e->sd, diameters, sizeof(double) * count, cudaMemcpyHostToDevice, s));
+        if (velocities) CU(cudaMemcpyAsync(e->sv, velocities, sizeof(double) * count * d, cudaMemcpyHostToDevice, s));
+        if (forces) CU(cudaMemcpyAsync(e->sf, forces, sizeof(double) * count * d, cudaMemcpyHostToDevice, s));
+        if (images) CU(cudaMemcpyAsync(e->si, images, sizeof(int32_t) * count * d, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(e->sid, ids, sizeof(int32_t) * count, cudaMemcpyHostToDevice, s));
+    }
+    // cell ranges and boundary-row offsets describe the previous particle set: empty until the rebuild refills them
+    CU(cudaMemsetAsync(e->start, 0, sizeof(uint32_t) * (e->ncell + 1), s));
+    for (int q = 0; q < 2; q++) {
+        CU(cudaMemsetAsync(e->rowoff[q], 0, sizeof(uint32_t) * ((size_t)e->nrows + 1), s));
+        CU(cudaMemsetAsync(e->gstart[q], 0, sizeof(uint32_t) * ((size_t)e->nrows + 1), s));
+    }
+    e->n = (int)count;
+    DevCtl c;
+    memset(&c, 0, sizeof(c));
+    c.alpha = 1.0;
+    c.rng_step = e->rng_step;
+    c.n_own = (int)count;
+    c.n_tmp = (int)count;
+    c.st[0] = e->st[0];
+    c.st[1] = e->st[1];
+    *e->h_ctl = c;
+    CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
+    const int blocks = std::max(1, nblk(count, kStreamBlock));
+    if (e->dim == 3)
+        k_import<3><<<blocks, kStreamBlock, 0, s>>>(count, e->sx, velocities ? e->sv : nullptr, forces ? e->sf : nullptr, e->sd,
+                                                   images ? e->si : nullptr, e->sid, e->st[0], e->grid);
+    else
+        k_import<2><<<blocks, kStreamBlock, 0, s>>>(count, e->sx, velocities ? e->sv : nullptr, forces ? e->sf : nullptr, e->sd,
+                                                   images ? e->si : nullptr, e->sid, e->st[0], e->grid);
+    e->stats.kernel_launches += 1;
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
     e->have_vel = velocities != nullptr;
     e->stats.n_owned = e->n;
     return MDB_OK;

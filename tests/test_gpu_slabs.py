@@ -82,6 +82,39 @@ def test_fused_slab_step_is_bit_identical(md, orc):
     assert all(s["rebuilds"] >= 2 for s in out[1][2])
 
 
+def test_upload_owned_round_trip(md, orc):
+    """a rank can hand back the rows it owns (download_owned -> upload_owned) instead of the global arrays: the run
+    continues exactly like after a global re-upload of the same state (slab sorts are canonical in particle id)"""
+    cfg, x, v, f, img = _cfg(md)
+    n = x.shape[0]
+    out = []
+    for owned in (False, True):
+        ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=21)
+        ring.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
+        ring.run_nve(80, 1e-3)
+        if owned:
+            parts = []
+            for e in ring.engines:
+                ids, xo, vo, fo, io = e.download_owned()
+                parts.append((ids, xo, cfg["diam"][ids], vo, fo, io))
+            ring.upload_owned(parts)
+        else:
+            X, V, F, I = ring.download()
+            ring.upload(X, cfg["diam"], velocities=V, forces=F, images=I)
+        t = ring.run_nve(120, 1e-3)
+        out.append((t, ring.download()))
+        assert sum(s["n_owned"] for s in ring.stats()) == n
+        ring.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    e = md.Engine(3, n, cfg["box"], 1.5, 0)
+    e.upload(x, cfg["diam"])
+    with pytest.raises(md.MdbError):          # single-domain handles use mdb_upload
+        e.upload_owned(np.arange(4, dtype=np.int32), x[:4], cfg["diam"][:4])
+    e.close()
+
+
 def test_migration_over_long_run(md, orc):
     """particles cross slab boundaries (and the periodic box face) during a longer run; ownership stays a partition,
     the pair count still matches an independent recount by the oracle at the end"""
