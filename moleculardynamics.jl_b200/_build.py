@@ -8,7 +8,8 @@ CSRC = os.path.join(HERE, "csrc")
 # MDB200_LIB / MDB200_NVCC_EXTRA: build and load tuning variants side by side (tools/tune_force.py)
 LIB = os.environ.get("MDB200_LIB") or os.path.join(CSRC, "libmdb200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["kernels.cuh", "potentials.cuh", "rng.cuh", os.path.join("..", "..", "include", "mdb200.h")]
+HEADERS = ["kernels.cuh", "potentials.cuh", "rng.cuh", "slab.cuh", "small.cuh", "setup_io.cuh", "engine_setup_io.inl",
+           os.path.join("..", "..", "include", "mdb200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
