@@ -34,11 +34,32 @@ def test_struct_layouts_match_header(md):
     assert C.sizeof(md._capi.FireParams) == 8 + 6 * 8 + 8
 
 
+def test_struct_offsets_match_a_c_compiler(md, tmp_path):
+    """the ctypes mirrors of mdb_config / mdb_stats / mdb_fire_params have the size and field offsets gcc gives the header"""
+    import ctypes as C
+    structs = {"mdb_config": md._capi.Config, "mdb_stats": md._capi.Stats, "mdb_fire_params": md._capi.FireParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mdb200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_product_path_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "moleculardynamics.jl_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inl")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "mdoracle" not in txt and "libmdoracle" not in txt and "oracle/" not in txt.replace("oracle/md_oracle.c", ""), f
 
