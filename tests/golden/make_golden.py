@@ -74,8 +74,29 @@ def main():
                               orc.philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0))], dtype=np.uint64),
              bussi=np.array([orc.bussi_noises(1234, s, nf) for s in (0, 1, 99) for nf in (3069.0, 3068.0)]),
              brownian=np.array([orc.brownian_noise(1234, s, i, 3) for s in (0, 7) for i in (0, 1, 1023)]))
+    setup_fixtures()
     print("golden fixtures written to", HERE)
 
 
+CELL = np.array([[11.0, 2.5, -1.5], [0.7, 10.0, 2.0], [-0.4, 0.9, 12.0]])
+
+
+def setup_fixtures():
+    """set-up streams and the general-cell path: velocity normals, uniform positions, wrap_to_box with a
+    full matrix and nearest-image forces for a small fixed configuration"""
+    x = orc.random_positions(3, 200, (1.0, 1.0, 1.0), 7, 3) @ CELL.T          # uniform fractional coordinates -> cell
+    x[::7] += CELL[:, 0] * 3 - CELL[:, 2]                                       # some points outside the cell
+    xw, img = orc.wrap_tri(x, np.zeros((200, 3), np.int32), CELL)
+    ref = orc.forces_tri(x, np.ones(200), CELL, 1.6, orc.POT_SOFT, (1.0, 1.6))
+    np.savez(os.path.join(HERE, "setup_streams.npz"), cell=CELL, x=x, xw=xw, img=img, F=ref["F"], E=ref["E"], W=ref["W"],
+             n_cut=ref["n_cut"], n_int=ref["n_int"],
+             velocities3=orc.init_velocities(3, 64, 1.4737, 1234, 5), velocities2=orc.init_velocities(2, 64, 0.11, 1234, 5),
+             positions3=orc.random_positions(3, 64, (9.0, 11.0, 13.0), 1234, 5),
+             positions2=orc.random_positions(2, 64, (9.0, 11.0, 1.0), 1234, 5))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "setup":
+        setup_fixtures()
+    else:
+        main()

@@ -142,3 +142,28 @@ def test_errors(md):
         e.upload(np.zeros((100, 3)), np.ones(100))
     assert ei.value.code == md._capi.ERR_BOX_TOO_SMALL
     e.close()
+
+
+def test_against_committed_golden_vectors(md):
+    """tests/golden/setup_streams.npz (oracle-generated, committed): general-cell wrap bit-exact, nearest-image forces and
+    pair counts, device velocity / position streams"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "setup_streams.npz"))
+    cell, x = g["cell"], g["x"]
+    e = md.Engine(3, 200, cell, 1.6, md._capi.POT_SOFT, (1.0, 1.6), seed=1234)
+    e.upload(x, np.ones(200))
+    xw, _, _, img = e.download()
+    assert np.array_equal(xw, g["xw"]) and np.array_equal(img, g["img"])
+    E, W, npairs = e.compute_forces()
+    F = e.download()[2]
+    assert npairs == int(g["n_int"]) and e.count_pairs(1.6) == int(g["n_cut"])
+    assert relerr(E, float(g["E"])) <= 1e-12 and relerr(W, float(g["W"])) <= 1e-12 and force_error(F, g["F"]) <= 1e-12
+    e.close()
+    for dim, box, kt, vkey, pkey in ((3, (9.0, 11.0, 13.0), 1.4737, "velocities3", "positions3"), (2, (9.0, 11.0), 0.11, "velocities2", "positions2")):
+        e = md.Engine(dim, 64, np.array(box), 1.0, md._capi.POT_SOFT, (1.0, 1.0), seed=1234)
+        e.upload(np.zeros((64, dim)), np.ones(64))
+        e.random_positions(stream=5)
+        assert np.array_equal(e.download()[0], g[pkey])
+        e.init_velocities(kt, stream=5)
+        assert np.max(np.abs(e.download()[1] - g[vkey])) <= 1e-12 * np.max(np.abs(g[vkey]))
+        e.close()

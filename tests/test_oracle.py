@@ -283,3 +283,19 @@ def test_general_cell_restatement(orc):
     assert ref["n_cut"] == moved["n_cut"] > 100
     assert np.allclose(ref["F"], moved["F"], rtol=0, atol=1e-11) and abs(ref["E"] - moved["E"]) < 1e-11
     assert np.max(np.abs(ref["F"].sum(axis=0))) < 1e-12
+
+
+def test_setup_and_general_cell_golden(orc):
+    """committed fixture tests/golden/setup_streams.npz (tests/golden/make_golden.py setup): the velocity / position
+    streams are integer-exact functions of (seed, id, stream) up to libm's log/cos/sin, the general-cell wrap and forces
+    are plain arithmetic -- a rebuilt oracle must reproduce them"""
+    g = np.load(os.path.join(GOLD, "setup_streams.npz"))
+    assert np.array_equal(orc.random_positions(3, 64, (9.0, 11.0, 13.0), 1234, 5), g["positions3"])
+    assert np.array_equal(orc.random_positions(2, 64, (9.0, 11.0, 1.0), 1234, 5), g["positions2"])
+    assert np.allclose(orc.init_velocities(3, 64, 1.4737, 1234, 5), g["velocities3"], rtol=1e-13, atol=1e-15)
+    assert np.allclose(orc.init_velocities(2, 64, 0.11, 1234, 5), g["velocities2"], rtol=1e-13, atol=1e-15)
+    xw, img = orc.wrap_tri(g["x"], np.zeros((200, 3), np.int32), g["cell"])
+    assert np.array_equal(xw, g["xw"]) and np.array_equal(img, g["img"]) and np.any(img != 0)
+    ref = orc.forces_tri(g["x"], np.ones(200), g["cell"], 1.6, orc.POT_SOFT, (1.0, 1.6))
+    assert ref["n_cut"] == int(g["n_cut"]) > 50 and ref["n_int"] == int(g["n_int"])
+    assert np.allclose(ref["F"], g["F"], rtol=1e-13, atol=1e-15) and abs(ref["E"] - float(g["E"])) <= 1e-13 * abs(float(g["E"]))
