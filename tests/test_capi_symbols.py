@@ -78,3 +78,36 @@ def test_fails_loudly_without_gpu(md):
     p = md.Parameters(0.5, 16, 1e-3, md.PseudoHS())
     with pytest.raises(md.MdbError):
         md.initialize_state(p, None, random_init=True, write_init=False)
+
+
+def test_hot_kernels_keep_their_register_budget(md):
+    """compile-time guard (no GPU needed): the dominant kernel was tuned to 72 registers / 7 CTAs per SM with a small
+    stack frame -- register spills to local memory cost it 10 % when they crept in (profiles/r01_session2.md)"""
+    import shutil
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.check_output([tool, "--dump-resource-usage", md._capi.lib_path()]).decode()
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+            name = None
+    def find(*parts):
+        hits = [v for k, v in usage.items() if all(p in k for p in parts)]
+        assert hits, parts
+        return hits
+    # k_force_list<3, PotPHS, KICK2, SLAB=0, TRI=0>: fused NVE (2), plain second kick (1), forces only (0), fused Brownian (3)
+    for kick, max_stack in ((2, 64), (1, 32), (0, 16), (3, 32)):
+        for reg, stack in find("k_force_listILi3ENS_6PotPHSELi%dELb0ELb0" % kick):
+            assert reg <= 72 and stack <= max_stack, (kick, reg, stack)
+    for reg, stack in find("k_kick_driftILi3"):
+        assert reg <= 64 and stack == 0
+    for reg, stack in find("k_build_listILi3ELb0"):
+        assert reg <= 64 and stack == 0
