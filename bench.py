@@ -172,6 +172,12 @@ def cpu_port_rate(n_sample, steps, warmup, x=None, v=None, box=None):
     """reference-shaped OpenMP port (oracle/md_oracle.c orc_run_timing) on the host cores: particle-steps/s"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mdoracle as orc
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers; in the reference arm the
+    # other ranks exit at once, so rank 0 has the box to itself)
+    try:
+        orc.set_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        orc.set_threads(os.cpu_count() or 1)
     if x is None:
         cfg, v = make_workload(n_sample)
         x, box = cfg["x"], cfg["box"]

@@ -801,6 +801,16 @@ ORC_API int orc_threads(void)
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timing baseline asks for the host's cores explicitly */
+ORC_API void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_run_timing(int ensemble, int dim, int64_t n, double *x, double *v, double *f, int32_t *img,
                            const double *diam, const double *box, double cutoff, int tag, const double *p, double dt,
                            int64_t nsteps, double ktemp, double tau, double nf, uint64_t seed, double *out)

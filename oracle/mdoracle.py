@@ -278,6 +278,11 @@ def threads():
     return lib().orc_threads()
 
 
+def set_threads(n):
+    """OpenMP team size of the timing baseline (launchers like torchrun export OMP_NUM_THREADS=1)"""
+    lib().orc_set_threads(int(n))
+
+
 def run_timing(ensemble, x, v, f, img, diam, box, cutoff, tag, params, dt, nsteps, ktemp=1.0, tau=1.0, seed=0):
     """Reference-shaped OpenMP loop, in place on the given arrays; returns (E, W, KE) of the last step."""
     n, dim = x.shape
