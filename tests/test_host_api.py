@@ -85,3 +85,25 @@ def test_workloads_are_overlap_free(md, orc):
         assert r["E"] < 50.0 * n and np.all(np.isfinite(r["F"]))
     p = workloads.poly2d()
     assert p["diam"].min() >= 0.73 and p["diam"].max() <= 1.62 and abs(p["box"][0] - math.sqrt(1200.0)) < 1e-12
+
+
+def test_reference_arm_under_torchrun_prints_one_line_and_uses_the_host_cores():
+    """bench.py --impl reference launched like the driver does for N > 1: rank 0 alone prints ONE JSON line, the other rank
+    exits 0 without work, and the OpenMP team is not pinned to the single thread torchrun exports to its workers"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+           "--warmup", "1", "--particles", "32768"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    lines = [l for l in p.stdout.decode().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    assert d["cpu_baseline"]["cores"] == ncpu
