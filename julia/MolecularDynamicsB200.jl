@@ -107,6 +107,30 @@ function download(sys::GPUSystem{D}; positions=true, velocities=true, forces=tru
     return u(x), u(v), u(f), u(im)
 end
 
+# Slab handles (cfg.nranks > 1, one Julia process per GPU): only the rows a rank owns travel between host and device once
+# mdb_upload has planned the slabs.  `ids` are the original (0-based) particle indices of the rows.
+function download_owned(sys::GPUSystem{D}; capacity::Int=sys.n) where {D}
+    ids = Vector{Int32}(undef, capacity)
+    x, v, f = (Vector{Float64}(undef, D * capacity) for _ in 1:3)
+    im = Vector{Int32}(undef, D * capacity)
+    cnt = Ref{Int64}(0)
+    GC.@preserve ids x v f im check(sys.handle, ccall((:mdb_download_owned, libmdb), Cint,
+        (Handle, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int64}),
+        sys.handle, capacity, ids, x, v, f, im, cnt))
+    k = Int(cnt[])
+    return ids[1:k], unflat(Val(D), x[1:D*k]), unflat(Val(D), v[1:D*k]), unflat(Val(D), f[1:D*k]), unflat(Val(D), im[1:D*k])
+end
+function upload_owned!(sys::GPUSystem{D}, ids::Vector{Int32}, positions, diameters; velocities=nothing, forces=nothing, images=nothing) where {D}
+    p(a) = a === nothing ? C_NULL : pointer(a)
+    x, d = flat(positions), Vector{Float64}(diameters)
+    v = velocities === nothing ? nothing : flat(velocities)
+    f = forces === nothing ? nothing : flat(forces)
+    im = images === nothing ? nothing : flat(images)
+    GC.@preserve ids x d v f im check(sys.handle, ccall((:mdb_upload_owned, libmdb), Cint,
+        (Handle, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        sys.handle, length(ids), ids, p(x), p(v), p(f), p(d), p(im)))
+end
+
 struct EnergyAndForcesView{D}
     sys::GPUSystem{D}
 end
