@@ -66,51 +66,72 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region.  NVML is polled from a thread every 2 ms (timed regions of
-    the multi-GPU runs last tens of milliseconds, shorter than one `nvidia-smi -lms` period); nvidia-smi is the fallback."""
+    """SM clock and throttle reasons DURING the timed region.
+
+    NVML is opened ONCE, at program start (`open()`: nvmlInit and the device handles cost tens of milliseconds and take
+    driver-wide locks, so they must never fall inside or next to a timed region), and polled from a thread while the
+    timed region runs: first sample 0.5 ms after `start()`, then every `period` seconds.  Multi-GPU runs poll from rank 0
+    only, for every GPU of the job (one process talking to NVML instead of N: round 1's 8-GPU line lost 36 ms to eight
+    processes polling every 2 ms).  nvidia-smi is the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device = device
+    def __init__(self, devices, period=0.005, enabled=True):
+        self.devices = list(devices)
+        self.period = period
+        self.enabled = enabled
+        self.nv = None
+        self.handles = []
         self.proc = None
         self.path = None
         self.thread = None
         self.samples = []   # (sm_mhz, reason bitmask)
         self.sm_max = None
 
-    def _poll(self, nv, handle):
-        import threading
-        self._stop = threading.Event()
-
-        def loop():
-            while True:
-                try:
-                    self.samples.append((float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)),
-                                         int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))))
-                except Exception:
-                    pass
-                if self._stop.wait(0.002):
-                    break
-        self.thread = threading.Thread(target=loop, daemon=True)
-        self.thread.start()
-
-    def start(self):
+    def open(self):
+        if not self.enabled:
+            return self
         try:
             import pynvml as nv
             nv.nvmlInit()
-            handle = nv.nvmlDeviceGetHandleByIndex(self.device)
-            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.handles = [nv.nvmlDeviceGetHandleByIndex(d) for d in self.devices]
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.handles[0], nv.NVML_CLOCK_SM))
+            for h in self.handles:   # first query of a handle is slower than the following ones
+                nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             self.nv = nv
-            self._poll(nv, handle)
-            return
         except Exception:
-            self.thread = None
+            self.nv = None
+        return self
+
+    def start(self):
+        self.samples = []
+        if not self.enabled:
+            return
+        if self.nv is not None:
+            nv, handles = self.nv, self.handles
+            self._stop = threading.Event()
+
+            def loop():
+                if self._stop.wait(0.0005):
+                    return
+                while True:
+                    for h in handles:
+                        try:
+                            self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                                 int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                        except Exception:
+                            pass
+                    if self._stop.wait(self.period):
+                        break
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
         try:
             fd, self.path = tempfile.mkstemp(prefix="mdb_clocks_", suffix=".csv")
             os.close(fd)
             self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(d) for d in self.devices), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
@@ -118,9 +139,13 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.enabled:
+            out["source"] = "sampled on rank 0 for every GPU of the job"
+            return out
         if self.thread is not None:
             self._stop.set()
             self.thread.join(timeout=2)
+            self.thread = None
             nv = self.nv
             bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
@@ -129,7 +154,8 @@ class ClockSampler:
                 for _, m in self.samples:
                     mask |= m
                 out.update(sm_mhz=statistics.median([c for c, _ in self.samples]), sm_max_mhz=self.sm_max,
-                           reasons=sorted(k for k, b in bits.items() if mask & b), samples=len(self.samples), source="nvml")
+                           reasons=sorted(k for k, b in bits.items() if mask & b), samples=len(self.samples), source="nvml",
+                           gpus_sampled=len(self.handles), period_ms=1e3 * self.period)
             return out
         if not self.proc:
             return out
@@ -159,6 +185,18 @@ class ClockSampler:
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
+
+
+def nvml_indices(cuda_ordinals):
+    """NVML index of each CUDA ordinal (CUDA_VISIBLE_DEVICES remaps the latter)"""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            table = [int(t) for t in vis.split(",") if t.strip() != ""]
+            return [table[d] for d in cuda_ordinals]
+        except (ValueError, IndexError):
+            pass
+    return list(cuda_ordinals)
 
 
 def make_workload(n, seed_shift=0):
@@ -203,14 +241,17 @@ def run_reference(args, rank, world):
     network), so the reference arm is the reference-shaped OpenMP port in oracle/ on all host threads."""
     if rank != 0:
         return
-    n_sample = min(args.n, 1 << 20)
+    # the same configuration as our arm (N = args.n, default 2^24): one step of the port takes ~0.8 s on 16 threads, so the
+    # driver's --steps 20 --warmup 5 run ends within a minute; --ref-sample bounds it for very long step counts
+    n_sample = min(args.n, args.ref_sample) if args.ref_sample > 0 else args.n
     rate, t, threads = cpu_port_rate(n_sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "particle-steps/s", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C5 3-D pseudo-hard-sphere NVE phi=0.47 dt=1e-3 (bounded sample N=%d of the N=%d workload)" % (n_sample, args.n),
-                   "cutoff": CUTOFF},
+        "config": {"workload": "C5 3-D pseudo-hard-sphere NVE N=%d phi=%.2f dt=%g cutoff=%g" % (n_sample, PHI, DT, CUTOFF) +
+                               ("" if n_sample == args.n else " (bounded sample of the N=%d workload)" % args.n),
+                   "n_particles": n_sample, "cutoff": CUTOFF},
         "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
                          "sample": "N=%d particles x %d steps, cell list rebuilt every step at cell=cutoff=1.5, OpenMP" % (n_sample, args.steps)},
         "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -230,6 +271,8 @@ def main_slabs(args, rank, world, local_rank):
     import mdjl_b200 as md
     from mdjl_b200 import slabs
     dev = torch.device("cuda", local_rank)
+    # clocks: NVML opened now, far from any timed region; rank 0 samples every GPU of the job
+    sampler = ClockSampler(nvml_indices(range(world)), enabled=(rank == 0)).open()
     # NCCL prints its version banner on stdout when NCCL_DEBUG asks for it; stdout carries exactly one JSON line
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -265,7 +308,6 @@ def main_slabs(args, rank, world, local_rank):
     run(args.warmup)
     sync()
     st0 = ring.lead.stats()
-    sampler = ClockSampler(local_rank)
     sampler.start()
     t_thermo = run(args.steps, thermo=True)
     sync()
@@ -281,41 +323,59 @@ def main_slabs(args, rank, world, local_rank):
 
     e2e = None
     if not args.no_e2e:
-        ids, x_now, v_now, f_now, img_now = ring.download_local()
         # steady-state round trip of a rank: hand back the rows it owns (mdb_upload_owned), step, read them again
-        # (mdb_download_owned); the global arrays were only needed once, to plan the slabs
+        # (mdb_download_owned); the global arrays were only needed once, to plan the slabs.  Both directions move through
+        # pinned host buffers that are allocated once and reused (capacity 1.25 x the owned count: migration changes it
+        # by a thin layer per rebuild).
+        cap = int(st1["n_owned"] * 1.25) + 4096
         keep = []
 
-        def pinned(a):
-            t = torch.empty(a.shape, dtype={np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32}[a.dtype], pin_memory=True)
+        def pinned(shape, dtype):
+            t = torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[dtype], pin_memory=True)
             keep.append(t)
-            arr = t.numpy()
-            arr[...] = a
-            return arr
-        ids, x_now, v_now, f_now, img_now = (pinned(np.ascontiguousarray(a)) for a in (ids, x_now, v_now, f_now, img_now))
-        diam_own = pinned(np.ascontiguousarray(cfg["diam"][ids]))
-        sync()
-        ok = 1
-        t0 = time.perf_counter()
-        try:
-            ring.upload_owned((ids, x_now, diam_own, v_now, f_now, img_now))
+            return t.numpy()
+
+        def bufset():
+            return {"ids": pinned((cap,), np.int32), "x": pinned((cap, 3), np.float64), "v": pinned((cap, 3), np.float64),
+                    "f": pinned((cap, 3), np.float64), "img": pinned((cap, 3), np.int32), "diam": pinned((cap,), np.float64)}
+        A, B = bufset(), bufset()
+
+        def down(buf):
+            k = ring.download_local_into(buf["ids"], buf["x"], buf["v"], buf["f"], buf["img"])
+            return k
+
+        def round_trip(src, k_src, dst):
+            ring.upload_owned((src["ids"][:k_src], src["x"][:k_src], src["diam"][:k_src], src["v"][:k_src], src["f"][:k_src],
+                               src["img"][:k_src]))
             th = run(args.steps, thermo=True)
-            out = ring.download_local()
+            return th, down(dst)
+
+        ok, th, k_in, k_out, t_e2e = 1, None, 0, 0, 0.0
+        try:
+            k_in = down(A)
+            A["diam"][:k_in] = cfg["diam"][A["ids"][:k_in]]
+            th, k_mid = round_trip(A, k_in, B)           # untimed warm-up of exactly the timed call (buffers, first touch)
+            B["diam"][:k_mid] = cfg["diam"][B["ids"][:k_mid]]
+            sync()
+            t0 = time.perf_counter()
+            th, k_out = round_trip(B, k_mid, A)
+            torch.cuda.synchronize()
+            t_e2e = time.perf_counter() - t0
+            k_in = k_mid
         except Exception as exc:   # the bench line must still be printed; the end-to-end figure is then absent
             print("slab e2e failed on rank %d: %s" % (rank, exc), file=sys.stderr)
             ok = 0
         sync()
-        t_e2e = time.perf_counter() - t0
         tt = torch.tensor([t_e2e, float(ok)], dtype=torch.float64, device=dev)
         dist.all_reduce(tt[:1], op=dist.ReduceOp.MAX)
         dist.all_reduce(tt[1:], op=dist.ReduceOp.MIN)
         t_e2e = float(tt[0].item())
         if tt[1].item() > 0.5:
-            own = out[0].size
             e2e = {"value": n * args.steps / t_e2e, "unit": "particle-steps/s",
-                   "h2d_bytes_per_step": own * (3 * 24 + 8 + 12 + 4) / args.steps,
-                   "d2h_bytes_per_step": (own * (3 * 24 + 12 + 4) + th.nbytes) / args.steps, "seconds": t_e2e,
-                   "what": "per rank: mdb_upload_owned(own rows, pinned host) + %d steps + mdb_download_owned" % args.steps}
+                   "h2d_bytes_per_step": k_in * (3 * 24 + 8 + 12 + 4) / args.steps,
+                   "d2h_bytes_per_step": (k_out * (3 * 24 + 12 + 4) + th.nbytes) / args.steps, "seconds": t_e2e,
+                   "what": "per rank (max over ranks): mdb_upload_owned(own rows, pinned host) + %d steps + mdb_download_owned "
+                           "into pinned host buffers; one untimed warm-up round trip before" % args.steps}
 
     nf = 3 * (n - 1.0)
     E = t_thermo[:, 0] + t_thermo[:, 2]
@@ -365,6 +425,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1 << 20)
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: cap on the particle count (0 = the full --n workload)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -383,6 +444,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         return main_slabs(args, rank, world, local_rank)
+    sampler = ClockSampler(nvml_indices([local_rank])).open()
 
     n = args.n
     cfg, v0 = make_workload(n)
@@ -406,7 +468,6 @@ def main():
     run(eng, args.warmup)
     torch.cuda.synchronize()
     st0 = eng.stats()
-    sampler = ClockSampler(local_rank)
     sampler.start()
     t_thermo = run(eng, args.steps, thermo=True)
     st1 = eng.stats()

@@ -364,6 +364,14 @@ class Engine:
         k = cnt.value
         return ids[:k], x[:k], v[:k], f[:k], im[:k]
 
+    def download_owned_into(self, ids, x=None, v=None, f=None, im=None):
+        """like download_owned, into caller-owned buffers (e.g. pinned host memory) of at least n_owned rows; returns the
+        number of rows written.  The buffers are reused call after call: nothing is allocated and the copies run at
+        pinned-memory speed."""
+        cnt = C.c_int64()
+        self._check(self._lib.mdb_download_owned(self._h, ids.shape[0], _i(ids), _d(x), _d(v), _d(f), _i(im), C.byref(cnt)))
+        return cnt.value
+
     def comm_init(self, unique_id):
         """join the NCCL slab ring (one process per GPU); unique_id = bytes from unique_id() on rank 0"""
         buf = C.create_string_buffer(bytes(unique_id), 128)
@@ -450,6 +458,12 @@ class SlabRing:
         if len(parts) == 1:
             return parts[0]
         return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+
+    def download_local_into(self, ids, x=None, v=None, f=None, im=None):
+        """one-slab-per-process (NCCL / peer ring) form of download_local into caller-owned (pinned) buffers -> row count"""
+        if len(self.engines) != 1:
+            raise RuntimeError("download_local_into serves one slab per process; use download_local for an in-process ring")
+        return self.engines[0].download_owned_into(ids, x, v, f, im)
 
     def download(self):
         """global arrays in original particle order (in-process ring only; with NCCL gather download_local across ranks)"""

@@ -557,7 +557,9 @@ def run_simulation(state, params, ensemble, total_steps, frequency, pathname, tr
         if step % frequency == 0:
             if is_bd:
                 ener = U / n
-                pressure = virial_acc / (dimension * nprom * volume) + params.rho * ensemble.ktemp
+                # nprom == 0 (no step with step % 10 == 0 in this output interval): the reference evaluates 0.0/0 = NaN,
+                # writes the row and carries on (src/simulation.jl:252-262)
+                pressure = (virial_acc / (dimension * nprom * volume) if nprom else float("nan")) + params.rho * ensemble.ktemp
                 row = (step, ener, ensemble.ktemp, pressure)
                 virial_acc, nprom = 0.0, 0
             else:

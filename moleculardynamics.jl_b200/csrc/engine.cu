@@ -135,6 +135,7 @@ struct mdb_engine_s {
     // ---- K0-small: persistent single-CTA step loop for n <= kSmallMaxN ------------------------------
     bool small = false;
     uint32_t *small_nl = nullptr;
+    size_t small_nl_words = 0;  // allocated size of small_nl (small_kmax * n can grow on a re-upload)
     int32_t *small_nnbr = nullptr;
     double *small_part = nullptr;
     int small_kmax = 0;
@@ -206,6 +207,7 @@ static void free_state(Engine *e)
     e->xref = nullptr;
     e->small_part = nullptr;
     e->ovf = nullptr; e->nl_in = nullptr; e->nnbr_in = nullptr; e->small_nl = nullptr; e->small_nnbr = nullptr;
+    e->small_nl_words = 0;
     e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
     e->nl = nullptr; e->nnbr = nullptr;
     e->alloc_ncell = -1;
@@ -1427,7 +1429,15 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
                      double *thermo)
 {
     cudaStream_t s = e->stream;
-    if (!e->small_nl) CU(cudaMalloc(&e->small_nl, sizeof(uint32_t) * (size_t)e->small_kmax * (size_t)std::max(e->n, 1)));
+    {
+        const size_t need = (size_t)e->small_kmax * (size_t)std::max(e->n, 1);
+        if (!e->small_nl || e->small_nl_words < need) {
+            cudaFree(e->small_nl);
+            e->small_nl = nullptr;
+            CU(cudaMalloc(&e->small_nl, sizeof(uint32_t) * need));
+            e->small_nl_words = need;
+        }
+    }
     CU(cudaEventRecord(e->ev0, s));
     int rc = sync_ctl(e);
     if (rc) return rc;
@@ -1439,7 +1449,7 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
     a.nf = e->dim * ((double)e->N - 1.0);
     a.ktemp_per_step = e->d_ktemp;
     a.nl = e->small_nl; a.kmax = e->small_kmax;
-    if (!e->small_part) CU(cudaMalloc(&e->small_part, sizeof(double) * 2 * kSmallMaxGrid * 5));
+    if (!e->small_part) CU(cudaMalloc(&e->small_part, sizeof(double) * 3 * kSmallMaxGrid * 5));
     a.gpart = e->small_part;
     a.skin = e->small_skin;
     double rl = e->r_search + e->small_skin;
@@ -1886,6 +1896,10 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     if (e->slab) e->cap_own = (int)e->cap;
     if ((rc = ensure_stage(e, std::max<int64_t>(n_res, 1)))) return rc;
     if ((rc = alloc_neighbors(e))) return rc;
+    // the captured step graphs bake in the search radii, skins, cutoff, potential parameters and the grid BY VALUE, and a new
+    // particle set can change them with the buffers unchanged (e.g. a wider diameter range of a Polydisperse system): never
+    // replay a graph across an upload
+    drop_graph(e);
     if (e->slab && (rc = alloc_slab(e))) return rc;
     if (e->group && (*e->group)[0]) drop_graph((*e->group)[0]);  // a captured ring step holds every member's buffers
     if (e->dim == 3) query_occupancy<3>(e);

@@ -80,13 +80,19 @@ static bool write_lammps_frame(const FrameIO *f, const FrameJob &job, std::strin
             th.emplace_back([&, t, lo, hi]() {
                 std::string &out = bufs[t];
                 out.reserve((size_t)(hi - lo) * (16 + 14 * (size_t)W));
-                char line[512];
+                // "%lf" of a finite double prints at most 1 + 309 + 1 + 6 characters (a coordinate near 1e308 after a blow-up
+                // that has not tripped MDB_ERR_NONFINITE yet): every column is formatted on its own and appended, so no
+                // row length can run past the buffer
+                char col[352];
                 for (int64_t i = lo; i < hi; i++) {
                     const double *r = fr + i * W;
-                    int len = snprintf(line, sizeof(line), "%lld %d", (long long)(i + 1), 1);
-                    for (int c = 0; c < W; c++) len += snprintf(line + len, sizeof(line) - len, " %lf", r[c]);
-                    line[len++] = '\n';
-                    out.append(line, (size_t)len);
+                    int len = snprintf(col, sizeof(col), "%lld %d", (long long)(i + 1), 1);
+                    out.append(col, (size_t)std::min<int>(len, (int)sizeof(col) - 1));
+                    for (int c = 0; c < W; c++) {
+                        len = snprintf(col, sizeof(col), " %lf", r[c]);
+                        out.append(col, (size_t)std::min<int>(std::max(len, 0), (int)sizeof(col) - 1));
+                    }
+                    out.push_back('\n');
                 }
             });
         }
@@ -408,6 +414,20 @@ MDB_EXPORT int mdb_checkpoint_load(mdb_handle e, const char *path)
         smax = std::max(smax, hpos[i].w);
     }
     if (!(smin > 0) || !std::isfinite(smax)) return fail(e, MDB_ERR_IO, "checkpoint holds invalid diameters");
+    // the kernels scatter through id[] (export, frames, velocity import): it must be a permutation of 0..n-1, and a state
+    // with non-finite entries is a corrupted file, not something to step
+    {
+        std::vector<uint8_t> seen((size_t)n, 0);
+        for (int64_t i = 0; i < n; i++) {
+            const int32_t q = hid[i];
+            if (q < 0 || q >= n || seen[q]) return fail(e, MDB_ERR_IO, std::string("corrupted checkpoint ") + path + ": particle ids are not a permutation of 0..n-1");
+            seen[q] = 1;
+        }
+        bool finite = true;
+        for (int64_t i = 0; i < n && finite; i++) finite = std::isfinite(hpos[i].x) && std::isfinite(hpos[i].y) && std::isfinite(hpos[i].z);
+        for (size_t i = 0; i < (size_t)n * d && finite; i++) finite = std::isfinite(hvel[i]) && std::isfinite(hfrc[i]);
+        if (!finite) return fail(e, MDB_ERR_IO, std::string("corrupted checkpoint ") + path + ": non-finite positions, velocities or forces");
+    }
     e->smin = smin; e->smax = smax;
     int rc;
     if ((rc = plan_neighbors(e))) return rc;

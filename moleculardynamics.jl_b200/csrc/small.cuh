@@ -34,7 +34,8 @@ struct SmallArgs {
     double skin, cutoff2;
     float rlist2_f;          // (r_list^2 + margin) for the FP32 membership test
     unsigned long long seed;
-    double *gpart;           // [2][kSmallMaxGrid][5] per-CTA partials: phase 0 = {vmax2}, phase 1 = {e, w, np, ke2, dmax2}
+    double *gpart;           // [3][kSmallMaxGrid][5] per-CTA partials: phase 0 = {vmax2}, phase 1 = {e, w, np, ke2, dmax2},
+                             // phase 1 double-buffered by step parity (see the step loop)
 };
 
 template <int DIM, class Pot>
@@ -50,7 +51,10 @@ k_small_run(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParams pp
     const int n = a.n, tid = threadIdx.x, G = gridDim.x;
     const int i = blockIdx.x * kSmallBlock + tid;
     const bool active = i < n;
-    double *part0 = a.gpart, *part1 = a.gpart + kSmallMaxGrid * 5;
+    // Brownian steps have a single grid barrier (B): a CTA that is one step ahead must not overwrite the phase-1 partials a
+    // slower CTA is still folding, so they alternate between two buffers by step parity (two steps ahead is impossible:
+    // barrier B of the step in between needs every CTA)
+    double *part0 = a.gpart, *part1_base = a.gpart + kSmallMaxGrid * 5;
     // Brownian dynamics has a single barrier per step, so the move must not overwrite positions other CTAs may still be
     // staging: it ping-pongs between the two state buffers (velocity Verlet writes before barrier A and needs no such care)
     double4 *pbuf[2] = {s.pos, ctl->st[ctl->cur ^ 1].pos};
@@ -97,6 +101,7 @@ k_small_run(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParams pp
     };
 
     for (long long step = 0; step < a.nsteps; step++) {
+        double *part1 = part1_base + (step & 1) * (kSmallMaxGrid * 5);
         double dmax2;
         if (a.ensemble != 2) {
             // ---- first half kick + drift + wrap (src/integrate.jl:8-21, src/boundary.jl:7-17); Bussi scale of the previous step
