@@ -261,6 +261,50 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def slab_parity(md, dist, torch, rank, world, local_rank, uid, tr, n=65536, steps=(150, 150)):
+    """The multi-process slab path against the single-domain engine on the same input, BEFORE anything is timed: per-step
+    interacting-pair counts exact, thermo rows and final positions to rounding (what tests/mp_slab_worker.py asserts; the
+    driver's 1-GPU test box cannot run that test, so the record travels on the bench line).  NVT then NVE, across list
+    rebuilds and migrations; the ring uses its own communicator id derived from the main one."""
+    from mdjl_b200 import slabs, workloads
+    uid2 = slabs.broadcast_unique_id(dist, rank, md.unique_id, device=torch.device("cuda", local_rank))
+    cfg = workloads.phs_fluid(n)
+    v0 = workloads.velocities(n, 3, KT)
+    ring = md.SlabRing.nccl(rank, world, uid2, 3, n, cfg["box"], CUTOFF, md._capi.POT_PSEUDOHS, seed=77, device=local_rank,
+                            slab_transport=tr)
+    ring.upload(cfg["x"], cfg["diam"], velocities=v0)
+    t1 = ring.run_nvt(steps[0], DT, KT, 100 * DT)
+    t2 = ring.run_nve(steps[1], DT)
+    st = ring.lead.stats()
+    ids, x, v, f, img = ring.download_local()
+    parts = [None] * world
+    dist.all_gather_object(parts, (ids, x, v))
+    ring.close()
+    rec = None
+    if rank == 0:
+        X, V = np.empty((n, 3)), np.empty((n, 3))
+        seen = np.zeros(n, dtype=np.int64)
+        for (i_, x_, v_) in parts:
+            X[i_], V[i_] = x_, v_
+            seen[i_] += 1
+        single = md.Engine(3, n, cfg["box"], CUTOFF, md._capi.POT_PSEUDOHS, seed=77, device=local_rank, mode=md._capi.MODE_LIST)
+        single.upload(cfg["x"], cfg["diam"], velocities=v0)
+        s1 = single.run_nvt(steps[0], DT, KT, 100 * DT)
+        s2 = single.run_nve(steps[1], DT)
+        xs, vs, _, _ = single.download()
+        single.close()
+        rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+        rec = {"n_particles": n, "steps_nvt": steps[0], "steps_nve": steps[1], "ownership_is_partition": bool(np.all(seen == 1)),
+               "pair_counts_equal_every_step": bool(np.array_equal(t1[:, 3], s1[:, 3]) and np.array_equal(t2[:, 3], s2[:, 3])),
+               "thermo_max_rel_diff": max(rel(t1[:, :3], s1[:, :3]), rel(t2[:, :3], s2[:, :3])),
+               "positions_max_abs_diff": float(np.max(np.abs(X - xs))), "velocities_max_abs_diff": float(np.max(np.abs(V - vs))),
+               "rebuilds": int(st["rebuilds"]), "slab_transport": int(st["slab_transport"]), "slab_graph": int(st["slab_graph"]),
+               "against": "single-domain engine (list mode) on rank 0, same input and RNG stream"}
+        rec["ok"] = bool(rec["ownership_is_partition"] and rec["pair_counts_equal_every_step"] and rec["thermo_max_rel_diff"] < 1e-8 and
+                         rec["positions_max_abs_diff"] < 1e-7)
+    return rec
+
+
 def main_slabs(args, rank, world, local_rank):
     """N > 1: the same N-particle workload cut into x-slabs, one process per GPU (strong scaling).  Ghost columns
     travel with ncclSend/ncclRecv every step, migration at neighbour rebuilds, ncclAllReduce for the rebuild consensus
@@ -282,8 +326,10 @@ def main_slabs(args, rank, world, local_rank):
     n = args.n
     cfg, v0 = make_workload(n)
     box = cfg["box"]
+    tr = {"auto": 0, "nccl": 1, "peer": 2}[args.transport]
+    parity = None if args.no_parity else slab_parity(md, dist, torch, rank, world, local_rank, uid, tr)
     ring = md.SlabRing.nccl(rank, world, uid, 3, n, box, CUTOFF, md._capi.POT_PSEUDOHS, seed=20261018, device=local_rank,
-                            skin=args.skin)
+                            skin=args.skin, slab_transport=tr)
     ring.upload(cfg["x"], cfg["diam"], velocities=v0)
     ring.compute_forces()   # first collective: communicator warm-up (and its banner) happen here
     torch.cuda.synchronize()
@@ -344,11 +390,18 @@ def main_slabs(args, rank, world, local_rank):
             k = ring.download_local_into(buf["ids"], buf["x"], buf["v"], buf["f"], buf["img"])
             return k
 
+        parts = {}
+
         def round_trip(src, k_src, dst):
+            ta = time.perf_counter()
             ring.upload_owned((src["ids"][:k_src], src["x"][:k_src], src["diam"][:k_src], src["v"][:k_src], src["f"][:k_src],
                                src["img"][:k_src]))
+            tb = time.perf_counter()
             th = run(args.steps, thermo=True)
-            return th, down(dst)
+            tc = time.perf_counter()
+            k = down(dst)
+            parts.update(upload_s=tb - ta, run_s=tc - tb, download_s=time.perf_counter() - tc)
+            return th, k
 
         ok, th, k_in, k_out, t_e2e = 1, None, 0, 0, 0.0
         try:
@@ -374,6 +427,7 @@ def main_slabs(args, rank, world, local_rank):
             e2e = {"value": n * args.steps / t_e2e, "unit": "particle-steps/s",
                    "h2d_bytes_per_step": k_in * (3 * 24 + 8 + 12 + 4) / args.steps,
                    "d2h_bytes_per_step": (k_out * (3 * 24 + 12 + 4) + th.nbytes) / args.steps, "seconds": t_e2e,
+                   "breakdown_s_rank0": parts,
                    "what": "per rank (max over ranks): mdb_upload_owned(own rows, pinned host) + %d steps + mdb_download_owned "
                            "into pinned host buffers; one untimed warm-up round trip before" % args.steps}
 
@@ -387,7 +441,13 @@ def main_slabs(args, rank, world, local_rank):
         "config": {"workload": "C5 3-D pseudo-hard-sphere %s N=%d phi=%.2f dt=%g cutoff=%g" % (args.ensemble.upper(), n, PHI, DT, CUTOFF),
                    "n_particles": n, "mode": "list", "skin": args.skin or "default",
                    "l2": "per-rank state (%.2f GiB) exceeds L2" % (n * 96 / 2 ** 30 / world),
-                   "melt_steps": args.melt, "parallelism": "x-slabs x%d, NCCL send/recv ghosts + allreduce, eager launches" % world},
+                   "melt_steps": args.melt,
+                   "parallelism": "x-slabs x%d, %s" % (world, {3: "peer-memory mailboxes over NVLink (own kernels write ghosts/migrants/"
+                                                                   "reductions into cudaIpc-mapped peer memory), step replayed as one CUDA graph"
+                                                                   if st1["slab_graph"] == 1 else "peer-memory mailboxes over NVLink, eager launches",
+                                                               2: "NCCL send/recv ghosts + allreduce, eager launches"}.get(st1["slab_transport"], "?"))},
+        "slab_transport": {3: "peer", 2: "nccl"}.get(st1["slab_transport"]), "slab_graph": bool(st1["slab_graph"] == 1),
+        "slab_parity": parity,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
         "roofline": None,
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm * world, "unit": "GB/s", "frac": step_gbs / (hbm * world),
@@ -425,6 +485,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1 << 20)
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "peer"],
+                    help="multi-GPU: auto = peer-memory mailboxes over NVLink (NCCL send/recv if cudaIpc is unavailable)")
+    ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the slab-vs-single-domain parity record")
     ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: cap on the particle count (0 = the full --n workload)")
     args = ap.parse_args()
 

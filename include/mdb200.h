@@ -88,7 +88,11 @@ typedef struct mdb_config {
     int32_t no_fuse;        /* 0 (default): NVE runs in list mode fuse the next step's kick-drift into the force kernel
                                (bit-identical results, one sweep less per step); 1: keep the reference's kernel order */
     double skin_inner;      /* skin of the inner (tight) list derived from the Verlet list; <= 0 picks a default */
-    int32_t reserved[2];
+    int32_t slab_transport; /* nranks > 1: how ghost columns / migrants / reductions travel.  0 default (mdb_comm_init: peer memory
+                               over NVLink with cudaIpc-mapped mailboxes, NCCL send/recv if they cannot be mapped;
+                               mdb_comm_init_local: device copies), 1 classic (NCCL send/recv + all-reduce, or device copies),
+                               2 peer memory (in the in-process ring too: the same kernels, on one device) */
+    int32_t reserved;
 } mdb_config;
 
 typedef struct mdb_stats {
@@ -110,6 +114,8 @@ typedef struct mdb_stats {
     double prof_force_ms;     /* K4 pair-force kernel (with the fused second kick) */
     double prof_rebuild_ms;   /* K1-K3 (+ list build) when they ran */
     int64_t prof_steps;
+    int64_t slab_transport;   /* last run: 0 single domain, 1 in-process ring (device copies), 2 NCCL send/recv, 3 peer memory */
+    int64_t slab_graph;       /* last run: 1 = the slab step replayed as one CUDA graph (peer memory), 2 = NCCL graph experiment */
 } mdb_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

@@ -33,7 +33,8 @@ struct MdbConfig
     nranks::Int32
     no_fuse::Int32
     skin_inner::Float64
-    reserved::NTuple{2,Int32}
+    slab_transport::Int32      # nranks > 1: 0 default (peer memory, else NCCL), 1 classic NCCL send/recv, 2 peer memory
+    reserved::Int32
 end
 
 const MDB_OK = Cint(0)
@@ -169,7 +170,7 @@ function to_gpu(state::SimulationState, params::Parameters; cutoff=1.5, seed=ran
     tag, pp = potential_tag(params.potential)
     cell = ntuple(q -> (r = (q - 1) ÷ 3 + 1; c = (q - 1) % 3 + 1; (r <= D && c <= D) ? Float64(U[r, c]) : 0.0), 9)
     cfg = MdbConfig(D, tag, length(state.system.xpositions), cell, cutoff, pad8(pp), seed, device, mode, skin, 1, 0, 1,
-                    Int32(0), 0.0, ntuple(_ -> Int32(0), 2))
+                    Int32(0), 0.0, Int32(0), Int32(0))
     sys = GPUSystem{D}(cfg)
     upload!(sys, state.system.xpositions, state.diameters;
             velocities=isempty(state.velocities) ? nothing : state.velocities,
@@ -229,7 +230,7 @@ function initialize_random_gpu(unitcell, npart::Int, dimension::Int; tol::Float6
     cell = ntuple(q -> (r = (q - 1) ÷ 3 + 1; c = (q - 1) % 3 + 1; (r <= dimension && c <= dimension) ? Float64(unitcell[r, c]) : 0.0), 9)
     tp = 1.001 * tol
     cfg = MdbConfig(dimension, Int32(4), npart, cell, tp, pad8((1.0, tp)), seed, device, 0, 0.0, 1, 0, 1, Int32(0), 0.0,
-                    ntuple(_ -> Int32(0), 2))
+                    Int32(0), Int32(0))
     sys = dimension == 3 ? GPUSystem{3}(cfg) : GPUSystem{2}(cfg)
     upload!(sys, [zeros(dimension) for _ in 1:npart], ones(npart); velocities=[zeros(dimension) for _ in 1:npart])
     check(sys.handle, ccall((:mdb_random_positions, libmdb), Cint, (Handle, UInt64), sys.handle, UInt64(0)))

@@ -42,7 +42,8 @@ class Config(C.Structure):
     _fields_ = [("dim", C.c_int32), ("potential", C.c_int32), ("n_particles", C.c_int64), ("unitcell", C.c_double * 9),
                 ("cutoff", C.c_double), ("pot_params", C.c_double * 8), ("seed", C.c_uint64), ("device", C.c_int32),
                 ("mode", C.c_int32), ("skin", C.c_double), ("use_graph", C.c_int32), ("rank", C.c_int32),
-                ("nranks", C.c_int32), ("no_fuse", C.c_int32), ("skin_inner", C.c_double), ("reserved", C.c_int32 * 2)]
+                ("nranks", C.c_int32), ("no_fuse", C.c_int32), ("skin_inner", C.c_double), ("slab_transport", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -51,7 +52,7 @@ class Stats(C.Structure):
                 ("r_search", C.c_double), ("cell_len", C.c_double * 3), ("ncell", C.c_int32 * 3), ("mode", C.c_int32),
                 ("last_run_ms", C.c_double), ("last_force_ms", C.c_double),
                 ("prof_kick_ms", C.c_double), ("prof_force_ms", C.c_double), ("prof_rebuild_ms", C.c_double),
-                ("prof_steps", C.c_int64)]
+                ("prof_steps", C.c_int64), ("slab_transport", C.c_int64), ("slab_graph", C.c_int64)]
 
 
 class FireParams(C.Structure):
@@ -155,7 +156,7 @@ class Engine:
     """Thin object wrapper over one mdb_handle (one GPU, one host thread)."""
 
     def __init__(self, dim, n_particles, box, cutoff, potential, pot_params=(), seed=0, device=0, mode=MODE_AUTO,
-                 skin=0.0, use_graph=True, rank=0, nranks=1, skin_inner=0.0, no_fuse=False):
+                 skin=0.0, use_graph=True, rank=0, nranks=1, skin_inner=0.0, no_fuse=False, slab_transport=0):
         L = load()
         cfg = Config()
         cfg.dim = dim
@@ -184,6 +185,7 @@ class Engine:
         cfg.no_fuse = 1 if no_fuse else 0
         cfg.rank = rank
         cfg.nranks = nranks
+        cfg.slab_transport = slab_transport
         self._lib = L
         self.dim = dim
         self.n = n_particles
@@ -410,7 +412,8 @@ class SlabRing:
 
     @classmethod
     def local(cls, nranks, dim, n_particles, box, cutoff, potential, pot_params=(), **kw):
-        engines = [Engine(dim, n_particles, box, cutoff, potential, pot_params, rank=r, nranks=nranks, use_graph=False, **kw)
+        kw.setdefault("use_graph", True)   # only the peer-memory transport (slab_transport=2) replays its step as a graph
+        engines = [Engine(dim, n_particles, box, cutoff, potential, pot_params, rank=r, nranks=nranks, **kw)
                    for r in range(nranks)]
         arr = (_H * nranks)(*[e._h for e in engines])
         rc = load().mdb_comm_init_local(arr, nranks)
@@ -420,7 +423,8 @@ class SlabRing:
 
     @classmethod
     def nccl(cls, rank, nranks, uid, dim, n_particles, box, cutoff, potential, pot_params=(), **kw):
-        e = Engine(dim, n_particles, box, cutoff, potential, pot_params, rank=rank, nranks=nranks, use_graph=False, **kw)
+        kw.setdefault("use_graph", True)
+        e = Engine(dim, n_particles, box, cutoff, potential, pot_params, rank=rank, nranks=nranks, **kw)
         e.comm_init(uid)
         return cls([e], e)
 

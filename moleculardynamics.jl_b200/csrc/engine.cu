@@ -118,6 +118,15 @@ struct mdb_engine_s {
     bool slab_graph_failed = false;
     bool prof_step_open = false;
     ncclComm_t comm = nullptr;
+    // peer-memory transport (slab.cuh): this rank's mailbox, the mapped mailboxes of the other ranks, how kernels address them
+    bool peer = false;            // the step's exchanges go through peer memory (decided when the communicator is set up)
+    bool peer_connected = false;  // links are valid for the current mailboxes (re-established lazily after every mdb_upload)
+    char *box = nullptr;
+    size_t box_bytes = 0, box_hdr_bytes = 0, box_ghost_bytes = 0;
+    void *box_mapped[kMaxRanks] = {};
+    PeerLinks links;
+    unsigned int *peer_done = nullptr;
+    int graph_launches_fixed = 0, graph_launches_rebuild = 0;  // kernels per replay of the captured slab step / of its rebuild body
     // graph replay: NCCL keeps per-communicator capture state, and a graph captured in several segments (one per
     // conditional node) needs a different communicator in every segment that communicates
     ncclComm_t comm_seg[3] = {nullptr, nullptr, nullptr};
@@ -404,16 +413,38 @@ static int alloc_neighbors(Engine *e)
     return MDB_OK;
 }
 
+static PeerView box_view(const Engine *e, char *base)
+{
+    PeerView v;
+    v.hdr = (PeerHdr *)base;
+    v.ghost = (double4 *)(base + e->box_hdr_bytes);
+    v.mig = (MigRec *)(base + e->box_hdr_bytes + e->box_ghost_bytes);
+    return v;
+}
+
+static void peer_disconnect(Engine *e)
+{
+    for (int r = 0; r < kMaxRanks; r++) {
+        if (e->box_mapped[r]) cudaIpcCloseMemHandle(e->box_mapped[r]);
+        e->box_mapped[r] = nullptr;
+    }
+    e->peer_connected = false;
+}
+
 static void free_slab(Engine *e)
 {
+    peer_disconnect(e);
     for (int d = 0; d < 2; d++) {
-        cudaFree(e->mig_send[d]); cudaFree(e->mig_recv[d]); cudaFree(e->gh_send[d]);
+        cudaFree(e->mig_send[d]); cudaFree(e->gh_send[d]);
         cudaFree(e->row_cnt[d]); cudaFree(e->rowoff[d]); cudaFree(e->gcnt[d]); cudaFree(e->gstart[d]);
-        e->mig_send[d] = e->mig_recv[d] = nullptr;
+        e->mig_send[d] = e->mig_recv[d] = nullptr;  // mig_recv and gpos_raw live inside the mailbox
         e->gh_send[d] = nullptr;
         e->row_cnt[d] = e->rowoff[d] = e->gcnt[d] = e->gstart[d] = nullptr;
     }
-    cudaFree(e->gpos_raw);
+    cudaFree(e->box);
+    cudaFree(e->peer_done);
+    e->box = nullptr;
+    e->peer_done = nullptr;
     e->gpos_raw = nullptr;
 }
 
@@ -428,11 +459,22 @@ static int alloc_slab(Engine *e)
     e->mig_cap = (int)std::max(2048.0, 0.3 * per_col + 1024.0);
     e->ghost_cap = (int)std::max(2048.0, 1.3 * per_col + 1024.0);
     size_t nr = (size_t)e->nrows + 1;
+    // the mailbox (slab.cuh): header with the flags and reduction slots, ghost columns [2 parity][2 side], migration
+    // records [2 side].  Every transport receives into it (the classic ones use parity 0 only); its layout depends on
+    // global quantities only, so every rank can address every other rank's mailbox.
+    e->box_hdr_bytes = (sizeof(PeerHdr) + 255) & ~(size_t)255;
+    e->box_ghost_bytes = sizeof(double4) * 4 * (1 + (size_t)e->ghost_cap);
+    e->box_bytes = e->box_hdr_bytes + e->box_ghost_bytes + sizeof(MigRec) * 2 * (1 + (size_t)e->mig_cap);
+    CU(cudaMalloc(&e->box, e->box_bytes));
+    CU(cudaMemset(e->box, 0, e->box_bytes));
+    CU(cudaMalloc(&e->peer_done, sizeof(unsigned int)));
+    CU(cudaMemset(e->peer_done, 0, sizeof(unsigned int)));
+    const PeerView self = box_view(e, e->box);
+    e->gpos_raw = self.ghost;
     for (int d = 0; d < 2; d++) {
         CU(cudaMalloc(&e->mig_send[d], sizeof(MigRec) * (1 + (size_t)e->mig_cap)));
-        CU(cudaMalloc(&e->mig_recv[d], sizeof(MigRec) * (1 + (size_t)e->mig_cap)));
+        e->mig_recv[d] = self.mig + (size_t)d * (1 + (size_t)e->mig_cap);
         CU(cudaMemset(e->mig_send[d], 0, sizeof(MigRec)));
-        CU(cudaMemset(e->mig_recv[d], 0, sizeof(MigRec)));
         CU(cudaMalloc(&e->gh_send[d], sizeof(double4) * (1 + (size_t)e->ghost_cap)));
         CU(cudaMemset(e->gh_send[d], 0, sizeof(double4)));
         CU(cudaMalloc(&e->row_cnt[d], sizeof(uint32_t) * nr));
@@ -442,13 +484,22 @@ static int alloc_slab(Engine *e)
         CU(cudaMemset(e->rowoff[d], 0, sizeof(uint32_t) * nr));
         CU(cudaMemset(e->gstart[d], 0, sizeof(uint32_t) * nr));
     }
-    CU(cudaMalloc(&e->gpos_raw, sizeof(double4) * 2 * (1 + (size_t)e->ghost_cap)));
-    CU(cudaMemset(e->gpos_raw, 0, sizeof(double4) * 2 * (1 + (size_t)e->ghost_cap)));
     Grid &g = e->grid;
     g.g0 = (uint32_t)e->cap_own;
     g.gstart_l = e->gstart[0];
     g.gstart_r = e->gstart[1];
     g.gpos_m = e->gpos_raw - (ptrdiff_t)g.g0;
+    memset(&e->links, 0, sizeof(e->links));
+    e->links.self = self;
+    e->links.me = e->rank;
+    e->links.nranks = e->nranks;
+    e->links.ghost_cap = e->ghost_cap;
+    e->links.mig_cap = e->mig_cap;
+    {
+        const char *t = getenv("MDB200_PEER_TIMEOUT_S");
+        double sec = t ? atof(t) : 20.0;
+        e->links.timeout_ns = (long long)(std::max(0.001, sec) * 1e9);
+    }
     return MDB_OK;
 }
 
@@ -818,6 +869,7 @@ struct NcclApi {
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -849,6 +901,7 @@ static bool load_nccl(std::string &why)
     LOADSYM(Recv, "ncclRecv")
     LOADSYM(AllReduce, "ncclAllReduce")
     LOADSYM(Broadcast, "ncclBroadcast")
+    LOADSYM(AllGather, "ncclAllGather")
     LOADSYM(GroupStart, "ncclGroupStart")
     LOADSYM(GroupEnd, "ncclGroupEnd")
     LOADSYM(GetErrorString, "ncclGetErrorString")
@@ -942,6 +995,78 @@ static int group_allreduce(Group &G, int count, bool is_max, GetPtr ptr)
     return MDB_OK;
 }
 
+// Peer-memory links of a ring (slab.cuh).  In-process ring: the other engines' mailboxes are ordinary device pointers.
+// One process per GPU: every rank exports its mailbox with cudaIpcGetMemHandle, the 64-byte handles travel with one
+// ncclAllGather, every rank maps all the others (cudaIpcMemLazyEnablePeerAccess turns on NVLink peer access), and an
+// all-reduce(min) makes the outcome unanimous: if any rank could not map a mailbox, all ranks stay on the NCCL transport.
+// Collective; called at the top of every group entry point, does nothing once connected.
+static int ensure_peer(Group &G)
+{
+    Engine *e = G[0];
+    if (!e->peer) return MDB_OK;
+    bool all = true;
+    for (Engine *m : G) all = all && m->peer_connected;
+    if (all) return MDB_OK;
+    if (e->transport == 1) {
+        const int P = (int)G.size();
+        for (int r = 0; r < P; r++) {
+            Engine *m = G[r];
+            if (!m->box) return fail(e, MDB_ERR_STATE, "mdb_upload has not been called on every slab");
+            m->links.self = box_view(m, m->box);
+            m->links.left = box_view(m, G[(r + P - 1) % P]->box);
+            m->links.right = box_view(m, G[(r + 1) % P]->box);
+            for (int q = 0; q < P; q++) m->links.all[q] = (PeerHdr *)G[q]->box;
+            m->peer_connected = true;
+        }
+        return MDB_OK;
+    }
+    const int P = e->nranks, me = e->rank;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t handles[kMaxRanks];
+    memset(handles, 0, sizeof(handles));
+    double ok_flag = 1.0;
+    if (cudaIpcGetMemHandle(&handles[me], e->box) != cudaSuccess) {
+        ok_flag = 0.0;
+        cudaGetLastError();
+    }
+    char *d = (char *)e->d_thermo;  // scratch: P * 64 bytes + one double
+    CU(cudaMemcpyAsync(d + 64 * (size_t)me, &handles[me], 64, cudaMemcpyHostToDevice, e->stream));
+    NC(g_nccl.AllGather(d + 64 * (size_t)me, d, 64, ncclInt8, e->comm, e->stream));
+    CU(cudaMemcpyAsync(handles, d, 64 * (size_t)P, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (ok_flag > 0) {
+        for (int r = 0; r < P && ok_flag > 0; r++) {
+            if (r == me) continue;
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok_flag = 0.0;
+                cudaGetLastError();
+                break;
+            }
+            e->box_mapped[r] = ptr;
+        }
+    }
+    double *dflag = (double *)(d + 64 * (size_t)kMaxRanks);
+    CU(cudaMemcpyAsync(dflag, &ok_flag, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    NC(g_nccl.AllReduce(dflag, dflag, 1, ncclDouble, ncclMin, e->comm, e->stream));
+    CU(cudaMemcpyAsync(&ok_flag, dflag, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (!(ok_flag > 0)) {
+        peer_disconnect(e);
+        e->peer = false;  // unanimous: the classic NCCL transport serves this ring
+        if (getenv("MDB200_VERBOSE")) fprintf(stderr, "[mdb200] rank %d: peer mailboxes could not be mapped; NCCL send/recv transport\n", me);
+        return MDB_OK;
+    }
+    auto base = [&](int r) { return r == me ? e->box : (char *)e->box_mapped[r]; };
+    e->links.self = box_view(e, e->box);
+    e->links.left = box_view(e, base((me + P - 1) % P));
+    e->links.right = box_view(e, base((me + 1) % P));
+    for (int q = 0; q < P; q++) e->links.all[q] = (PeerHdr *)base(q);
+    e->peer_connected = true;
+    if (getenv("MDB200_VERBOSE")) fprintf(stderr, "[mdb200] rank %d: peer-memory transport connected (%d mailboxes of %zu bytes)\n", me, P, e->box_bytes);
+    return MDB_OK;
+}
+
 static inline void *mig_buf(Engine *e, int which) { return which < 2 ? (void *)e->mig_send[which] : (void *)e->mig_recv[which - 2]; }
 static inline void *ghost_buf(Engine *e, int which)
 {
@@ -973,6 +1098,27 @@ static int group_exchange_ghosts(Group &G)
     return group_exchange(G, sizeof(double4) * (1 + (size_t)G[0]->ghost_cap), ghost_buf);
 }
 
+// the two exchanges of a rebuild.  Peer memory: the data was written into the neighbours' mailboxes by the packing kernels
+// (rebuild_part1 / rebuild_part2), what remains is to wait for the neighbours' flags.
+static int group_exchange_migrants(Group &G)
+{
+    if (!G[0]->peer) return group_exchange(G, sizeof(MigRec) * (1 + (size_t)G[0]->mig_cap), mig_buf);
+    for (Engine *e : G) {
+        k_peer_wait<<<1, 32, 0, e->stream>>>(e->links, 0, e->ctl);
+        e->stats.kernel_launches += 1;
+    }
+    return MDB_OK;
+}
+static int group_exchange_rebuilt_ghosts(Group &G)
+{
+    if (!G[0]->peer) return group_send_ghosts(G);
+    for (Engine *e : G) {
+        k_peer_wait<<<1, 32, 0, e->stream>>>(e->links, 1, e->ctl);
+        e->stats.kernel_launches += 1;
+    }
+    return MDB_OK;
+}
+
 // the neighbour rebuild of a slab ring: migration, counting sort of the owned set, ghost columns, Verlet list
 template <int DIM>
 static int rebuild_part1(Group &G);
@@ -986,9 +1132,9 @@ static int group_rebuild(Group &G)
 {
     int rc;
     if ((rc = rebuild_part1<DIM>(G))) return rc;
-    if ((rc = group_exchange(G, sizeof(MigRec) * (1 + (size_t)G[0]->mig_cap), mig_buf))) return rc;
+    if ((rc = group_exchange_migrants(G))) return rc;
     if ((rc = rebuild_part2<DIM>(G))) return rc;
-    if ((rc = group_send_ghosts(G))) return rc;
+    if ((rc = group_exchange_rebuilt_ghosts(G))) return rc;
     return rebuild_part3<DIM>(G);
 }
 
@@ -999,9 +1145,17 @@ static int rebuild_part1(Group &G)
     for (Engine *e : G) {
         cudaStream_t s = e->stream;
         CU(cudaMemsetAsync(e->counts, 0, sizeof(uint32_t) * (e->ncell + 1), s));
-        k_slab_classify<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(e->ctl, e->grid, e->cell_of, e->slot_of, e->counts,
-                                                                                   e->mig_send[0], e->mig_send[1], e->mig_cap);
-        k_slab_mig_headers<<<1, 1, 0, s>>>(e->ctl, e->mig_send[0], e->mig_send[1], e->mig_cap);
+        if (e->peer) {
+            // leavers go straight into the neighbours' mailboxes (my left-goers arrive "from the right" over there)
+            k_slab_classify<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(e->ctl, e->grid, e->cell_of, e->slot_of, e->counts,
+                                                                                       e->links.left.mig + (1 + (size_t)e->mig_cap),
+                                                                                       e->links.right.mig, e->mig_cap);
+            k_peer_mig_publish<<<1, 1, 0, s>>>(e->ctl, e->links);
+        } else {
+            k_slab_classify<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(e->ctl, e->grid, e->cell_of, e->slot_of, e->counts,
+                                                                                       e->mig_send[0], e->mig_send[1], e->mig_cap);
+            k_slab_mig_headers<<<1, 1, 0, s>>>(e->ctl, e->mig_send[0], e->mig_send[1], e->mig_cap);
+        }
         e->stats.kernel_launches += 2;
         PHASE(e, "classify");
     }
@@ -1035,7 +1189,14 @@ static int rebuild_part2(Group &G)
         e->stats.kernel_launches += 10;
         PHASE(e, "rowscan");
     }
-    group_pack_ghosts(G);
+    if (G[0]->peer) {
+        for (Engine *e : G) {
+            k_peer_pack_ghost<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->nxo, e->start, e->rowoff[0],
+                                                                                          e->rowoff[1], e->links, 1, e->peer_done);
+            e->stats.kernel_launches += 1;
+        }
+    } else
+        group_pack_ghosts(G);
     return MDB_OK;
 }
 
@@ -1049,7 +1210,10 @@ static int rebuild_part3(Group &G)
         CU(cudaMemsetAsync(e->gcnt[0], 0, sizeof(uint32_t) * nr, s));
         CU(cudaMemsetAsync(e->gcnt[1], 0, sizeof(uint32_t) * nr, s));
         const double4 *gl = e->gpos_raw, *gr = e->gpos_raw + 1 + (size_t)e->ghost_cap;
-        k_slab_ghost_count<DIM><<<nblk(2 * e->ghost_cap, kStreamBlock), kStreamBlock, 0, s>>>(e->grid, gl, gr, e->gcnt[0], e->gcnt[1]);
+        if (e->peer)  // the live parity of the mailbox
+            k_peer_ghost_count<DIM><<<nblk(2 * e->ghost_cap, kStreamBlock), kStreamBlock, 0, s>>>(e->grid, e->ctl, e->links, e->gcnt[0], e->gcnt[1]);
+        else
+            k_slab_ghost_count<DIM><<<nblk(2 * e->ghost_cap, kStreamBlock), kStreamBlock, 0, s>>>(e->grid, gl, gr, e->gcnt[0], e->gcnt[1]);
         uint32_t base_l = e->grid.g0 + 1u, base_r = e->grid.g0 + 1u + (uint32_t)e->ghost_cap + 1u;
         PHASE(e, "ghost exchange");
         k_slab_rowscan<<<1, 1024, 0, s>>>(e->nrows, e->gcnt[0], e->gstart[0], base_l, e->gcnt[1], e->gstart[1], base_r);
@@ -1096,6 +1260,24 @@ template <int DIM>
 static int slab_head(Group &G, CondHandles hs)
 {
     int rc;
+    if (G[0]->peer) {
+        // peer memory: every rank writes its boundary columns and its displacement bound straight into the mailboxes of
+        // its neighbours / of all ranks, then waits for theirs and takes the (identical) decision -- two kernels, no NCCL
+        const char *mute = getenv("MDB200_PEER_TEST_MUTE_RANK");  // fault injection for the time-out test: this rank stays silent
+        for (Engine *e : G) {
+            if (mute && atoi(mute) == e->rank) continue;
+            k_peer_pack_ghost<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->nxo, e->start, e->rowoff[0],
+                                                                                          e->rowoff[1], e->links, 0, e->peer_done);
+            e->stats.kernel_launches += 1;
+        }
+        for (Engine *e : G) {
+            int always = (e->mode != MDB_MODE_LIST) ? 1 : 0;
+            k_peer_wait_head<<<1, 32, 0, e->stream>>>(e->links, e->skin, e->skin_in, always, e->ctl, e->grid.gpos_m,
+                                                     e == G[0] ? hs : CondHandles{{0, 0, 0}, 0});
+            e->stats.kernel_launches += 1;
+        }
+        return MDB_OK;
+    }
     // the ghost exchange and the all-reduce of the displacement bound are independent: under NCCL they go out as ONE
     // group (one launch, one rendezvous of the ranks instead of two)
     static const bool merged = getenv("MDB200_NO_MERGED_HEAD") == nullptr;
@@ -1131,6 +1313,15 @@ static int slab_tail(Group &G, int ensemble, double dt, double tau, double ktemp
         e->stats.kernel_launches += 1;
     }
     if (!reduce_now) return MDB_OK;
+    if (G[0]->peer) {
+        // sums to every rank's mailbox, then added in rank order: the same bits everywhere (guarded like the kernels around
+        // them: a speculative tail behind a pending rebuild must not publish anything)
+        for (Engine *e : G) k_peer_sum_publish<<<1, 1, 0, e->stream>>>(e->ctl, e->links, guard);
+        for (Engine *e : G) {
+            k_peer_sum_wait<<<1, 32, 0, e->stream>>>(e->ctl, e->links, guard);
+            e->stats.kernel_launches += 2;
+        }
+    } else
     // the collective itself always runs (every rank enqueues it); under a pending rebuild it moves stale numbers nobody reads
     if ((rc = group_allreduce(G, 4, false, [](Engine *e) { return e->ctl->red; }))) return rc;
     for (Engine *e : G) {
@@ -1275,6 +1466,110 @@ static int build_graph_slab(Group &G, const GraphKey &key, bool per_step_reduce)
     return MDB_OK;
 }
 
+// Peer-memory transport: the slab step holds no NCCL call, so it is captured like the single-domain step -- head,
+// ONE conditional node with the whole rebuild (both exchanges inside), tail -- and replays without any host round trip.
+// kind: kStepFull (kick-drift + forces + second kick; NVT, Brownian, unfused NVE), kStepFused / kStepLast (NVE, see StepKind).
+template <int DIM>
+static int build_one_graph_peer(Group &G, const GraphKey &key, int kind, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out)
+{
+    Engine *e = G[0];
+    cudaStream_t s = e->stream;
+    cudaGraph_t &graph = *graph_out;
+    CU(cudaGraphCreate(&graph, 0));
+    const bool conditional = (e->mode == MDB_MODE_LIST);
+    CondHandles hs{{0, 0, 0}, 0};
+    if (conditional) {
+        CU(cudaGraphConditionalHandleCreate(&hs.h[0], graph, 0, cudaGraphCondAssignDefault));
+        hs.n = 1;
+    }
+    cudaGraph_t g2 = nullptr;
+    auto abort_capture = [&](int code, const char *what = nullptr) {
+        cudaError_t last = cudaGetLastError();
+        if (what) e->err = std::string(what) + ": " + cudaGetErrorString(last);
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &st);
+        if (st != cudaStreamCaptureStatusNone) cudaStreamEndCapture(s, &g2);
+        cudaGetLastError();
+        return code;
+    };
+    // kernels enqueued during capture are counted per replay, not now
+    std::vector<int64_t> saved;
+    for (Engine *g : G) saved.push_back(g->stats.kernel_launches);
+    auto launched = [&]() {
+        int64_t t = 0;
+        for (size_t q = 0; q < G.size(); q++) t += G[q]->stats.kernel_launches - saved[q];
+        return t;
+    };
+    int rc = MDB_OK;
+    if (cudaStreamBeginCaptureToGraph(s, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph");
+    if (key.ensemble != MDB_BROWNIAN && kind == kStepFull)
+        for (Engine *g : G) {
+            k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, key.dt, g->ctl);
+            g->stats.kernel_launches += 1;
+        }
+    if ((rc = slab_head<DIM>(G, hs))) return abort_capture(rc);
+    int64_t n_rebuild = 0;
+    if (conditional) {
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t *d = nullptr;
+        size_t nd = 0;
+        if (cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &d, &nd) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamGetCaptureInfo");
+        std::vector<cudaGraphNode_t> deps(d, d + nd);
+        if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture");
+        cudaGraphNodeParams cp = {};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = hs.h[0];
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        cudaGraphNode_t cnode;
+        if (cudaGraphAddNode(&cnode, graph, deps.data(), deps.size(), &cp) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaGraphAddNode");
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        if (cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+            return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph(body)");
+        const int64_t before = launched();
+        if ((rc = group_rebuild<DIM>(G))) return abort_capture(rc);
+        n_rebuild = launched() - before;
+        if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture(body)");
+        if (cudaStreamBeginCaptureToGraph(s, graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+            return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph(tail)");
+    } else {
+        const int64_t before = launched();
+        if ((rc = group_rebuild<DIM>(G))) return abort_capture(rc);
+        n_rebuild = launched() - before;
+    }
+    const bool reduce_now = key.ensemble == MDB_NVT;
+    if (key.ensemble == MDB_BROWNIAN) rc = slab_tail<DIM, 0>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
+    else if (kind == kStepFused) rc = slab_tail<DIM, 2>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
+    else rc = slab_tail<DIM, 1>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
+    if (rc) return abort_capture(rc);
+    if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture");
+    if (cudaGraphInstantiate(exec_out, graph, 0) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaGraphInstantiate");
+    e->graph_launches_rebuild = (int)n_rebuild;
+    e->graph_launches_fixed = (int)(launched() - n_rebuild) - (conditional ? 0 : 0);
+    if (!conditional) {  // cell mode: the rebuild is part of every step
+        e->graph_launches_fixed += (int)n_rebuild;
+        e->graph_launches_rebuild = 0;
+    }
+    for (size_t q = 0; q < G.size(); q++) G[q]->stats.kernel_launches = saved[q];
+    return MDB_OK;
+}
+
+template <int DIM>
+static int build_graph_peer(Group &G, const GraphKey &key)
+{
+    Engine *e = G[0];
+    drop_graph(e);
+    int rc;
+    if (key.fused) {
+        if ((rc = build_one_graph_peer<DIM>(G, key, kStepLast, &e->graph_last, &e->gexec_last))) return rc;
+        if ((rc = build_one_graph_peer<DIM>(G, key, kStepFused, &e->graph, &e->gexec))) return rc;
+    } else if ((rc = build_one_graph_peer<DIM>(G, key, kStepFull, &e->graph, &e->gexec)))
+        return rc;
+    e->gkey = key;
+    return MDB_OK;
+}
+
 // NVE / Brownian: the thermo rows of a chunk were written rank-locally (halved pair sums, local KE); one all-reduce
 // over the whole chunk makes them global.  Row `m-1` also refreshes ctl->last.
 __global__ void k_last_from_row(const double *__restrict__ thermo, long long row, DevCtl *ctl)
@@ -1300,6 +1595,7 @@ static int group_check_errors(Group &G)
             if (bits & kErrGhostOverflow) m += " ghost buffer overflow;";
             if (bits & kErrOwnedOverflow) m += " slab capacity exceeded;";
             if (bits & kErrLongJump) m += " a particle crossed more than one cell column between rebuilds;";
+            if (bits & kErrPeerTimeout) m += " a ring neighbour's message did not arrive within MDB200_PEER_TIMEOUT_S (peer-memory transport);";
             return fail(G[0], MDB_ERR_STATE, m);
         }
     }
@@ -1323,9 +1619,33 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
     int rc;
     lead->stats.prof_kick_ms = lead->stats.prof_force_ms = lead->stats.prof_rebuild_ms = 0.0;
     lead->stats.prof_steps = 0;
-    // graph replay of the slab step (conditional rebuild with the NCCL exchanges captured inside): opt-in until validated
-    // on more systems; any failure to capture falls back to eager launches
-    bool use_graph = !lead->slab_graph_failed && getenv("MDB200_SLAB_GRAPH") != nullptr && !debug_sync();
+    if ((rc = ensure_peer(G))) return rc;
+    static const bool slab_prof_run = getenv("MDB200_SLAB_PROF") != nullptr;
+    // Peer-memory transport: the step is all kernels and replays as a CUDA graph (fused NVE schedule included): no host
+    // round trip inside the run.  cfg.use_graph = 0, MDB200_DEBUG_SYNC and MDB200_SLAB_PROF keep the eager, host-driven
+    // loop (same kernels; the rebuild decision is read back every step).
+    const bool fused_ok = fused_step(lead, ensemble);
+    bool peer_graph = lead->peer && lead->cfg.use_graph && !lead->slab_graph_failed && !debug_sync() && !slab_prof_run;
+    if (peer_graph) {
+        GraphKey key;
+        key.ensemble = ensemble; key.dt = dt; key.tau = tau; key.ktemp = ktemp; key.thermo = 1;
+        key.fused = fused_ok ? 1 : 0;
+        if (!(lead->gexec && lead->gkey == key)) {
+            int grc = build_graph_peer<DIM>(G, key);
+            if (grc != MDB_OK) {
+                lead->slab_graph_failed = true;
+                peer_graph = false;
+                drop_graph(lead);
+                for (int q = 0; q < 4; q++) cudaGetLastError();  // a failed capture must not poison the eager path
+            }
+            if (getenv("MDB200_VERBOSE"))
+                fprintf(stderr, "[mdb200] rank %d: peer slab step graph %s%s\n", lead->rank, grc == MDB_OK ? "captured" : "NOT captured, eager launches: ",
+                        grc == MDB_OK ? "" : lead->err.c_str());
+        }
+    }
+    // graph replay of the NCCL slab step (conditional rebuild cut into three bodies around the captured exchanges): opt-in
+    // experiment, slower than eager launches
+    bool use_graph = !peer_graph && !lead->peer && !lead->slab_graph_failed && getenv("MDB200_SLAB_GRAPH") != nullptr && !debug_sync();
     if (use_graph) {
         GraphKey key;
         key.ensemble = ensemble; key.dt = dt; key.tau = tau; key.ktemp = ktemp; key.thermo = 1;
@@ -1341,9 +1661,14 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
                         grc == MDB_OK ? "" : lead->err.c_str());
         }
     }
+    unsigned long long rebuilds0 = 0;
+    if (peer_graph) {
+        if ((rc = sync_ctl(lead))) return rc;
+        rebuilds0 = lead->h_ctl->rebuilds;
+    }
     CU(cudaEventRecord(lead->ev0, s));
     int64_t done = 0;
-    const bool fused = !use_graph && fused_step(lead, ensemble);
+    const bool fused = !use_graph && fused_ok;
     while (done < nsteps) {
         int64_t m = std::min(lead->chunk, nsteps - done);
         for (Engine *g : G) {
@@ -1353,7 +1678,18 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
         }
         // only the thermostat needs the global kinetic energy inside the step
         const bool per_step_reduce = (ensemble == MDB_NVT);
-        if (use_graph) {
+        if (peer_graph) {
+            for (int64_t q = 0; q < m; q++) {
+                const bool first = done + q == 0, last = done + q == nsteps - 1;
+                if (fused && first) {
+                    for (Engine *g : G) {
+                        k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
+                        g->stats.kernel_launches += 1;
+                    }
+                }
+                CU(cudaGraphLaunch((fused && last) ? lead->gexec_last : lead->gexec, s));
+            }
+        } else if (use_graph) {
             for (int64_t q = 0; q < m; q++) CU(cudaGraphLaunch(lead->gexec, s));
         } else
         for (int64_t q = 0; q < m; q++) {
@@ -1397,11 +1733,16 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
     CU(cudaEventRecord(lead->ev1, s));
     if ((rc = group_check_errors(G))) return rc;
     CU(cudaGetLastError());
+    if (peer_graph)  // kernel nodes replayed: the fixed part every step, the conditional body once per rebuild
+        lead->stats.kernel_launches += nsteps * lead->graph_launches_fixed +
+                                       (int64_t)(lead->h_ctl->rebuilds - rebuilds0) * lead->graph_launches_rebuild;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, lead->ev0, lead->ev1));
     for (Engine *g : G) {
         g->stats.last_run_ms = ms;
         g->stats.steps += nsteps;
+        g->stats.slab_transport = g->peer ? 3 : g->transport;
+        g->stats.slab_graph = peer_graph ? 1 : (use_graph ? 2 : 0);
     }
     if (lead->h_ctl->nonfinite) {
         for (Engine *g : G) CU(cudaMemsetAsync(&g->ctl->nonfinite, 0, sizeof(int), g->stream));
@@ -1922,6 +2263,8 @@ MDB_EXPORT int mdb_upload(mdb_handle e, const double *positions, const double *v
     c.n_tmp = (int)n_res;
     c.st[0] = e->st[0];
     c.st[1] = e->st[1];
+    c.epoch = 0;                 // fresh mailboxes (alloc_slab), fresh epoch
+    c.gpos_m = e->grid.gpos_m;   // slabs: parity 0 of the mailbox; null otherwise
     *e->h_ctl = c;
     CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
     int blocks = std::max(1, nblk(n_res, kStreamBlock));
@@ -1972,6 +2315,9 @@ MDB_EXPORT int mdb_upload_owned(mdb_handle e, int64_t count, const int32_t *ids,
         CU(cudaMemsetAsync(e->gstart[q], 0, sizeof(uint32_t) * ((size_t)e->nrows + 1), s));
     }
     e->n = (int)count;
+    // the mailboxes and their flags outlive this call (the plan is kept): the epoch counter must go on from where it is
+    if ((rc = sync_ctl(e))) return rc;
+    const unsigned long long epoch = e->h_ctl->epoch;
     DevCtl c;
     memset(&c, 0, sizeof(c));
     c.alpha = 1.0;
@@ -1980,6 +2326,8 @@ MDB_EXPORT int mdb_upload_owned(mdb_handle e, int64_t count, const int32_t *ids,
     c.n_tmp = (int)count;
     c.st[0] = e->st[0];
     c.st[1] = e->st[1];
+    c.epoch = epoch;
+    c.gpos_m = e->grid.gpos_m + (size_t)(epoch & 1ull) * 2 * (size_t)(1 + e->ghost_cap);
     *e->h_ctl = c;
     CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
     const int blocks = std::max(1, nblk(count, kStreamBlock));
@@ -2100,6 +2448,7 @@ MDB_EXPORT int mdb_compute_forces(mdb_handle e, double *energy, double *virial, 
         if ((rc = slab_group(e, storage, &G))) return rc;
         for (Engine *m : *G)
             if (!m->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload has not been called on every slab");
+        if ((rc = ensure_peer(*G))) return rc;
         rc = e->dim == 3 ? group_force_phase<3, false>(*G, MDB_BROWNIAN, 0.0, 1.0, 1.0, 1.0, 0, 0)
                          : group_force_phase<2, false>(*G, MDB_BROWNIAN, 0.0, 1.0, 1.0, 1.0, 0, 0);
         if (rc) return rc;
@@ -2534,6 +2883,9 @@ MDB_EXPORT int mdb_comm_init(mdb_handle e, const char *id)
     memcpy(&uid, id, sizeof(uid));
     NC(g_nccl.CommInitRank(&e->comm, e->nranks, uid, e->rank));
     e->transport = 2;
+    // step exchanges through peer memory (slab.cuh) unless the classic NCCL send/recv transport is asked for; the mailboxes
+    // are mapped at the first run after every mdb_upload (ensure_peer), falling back to NCCL if cudaIpc is unavailable
+    e->peer = e->cfg.slab_transport != 1 && getenv("MDB200_NO_PEER") == nullptr;
     if (getenv("MDB200_SLAB_GRAPH")) {
         // three more communicators for the later capture segments of the step graph; their ids travel over the first one
         ncclUniqueId ids[3];
@@ -2562,6 +2914,7 @@ MDB_EXPORT int mdb_comm_init_local(mdb_handle *handles, int32_t count)
         Engine *m = handles[r];
         m->group = G;
         m->transport = 1;
+        m->peer = handles[0]->cfg.slab_transport == 2;  // in-process ring: device copies by default, peer-memory kernels on request
         if (r > 0) {  // one stream orders the whole ring
             cudaStreamSynchronize(m->stream);
             cudaStreamDestroy(m->stream);

@@ -169,6 +169,11 @@ struct DevCtl {
     double bd_ktemp, bd_sigma;
     unsigned long long bd_seed;
     const double *bd_xref;        // unwrapped build-time positions for the exact displacement test, or null
+    // x-slabs: force-evaluation heads executed so far (the epoch of the peer-memory transport, slab.cuh) and the live ghost
+    // buffer, biased like Grid::gpos_m (the peer transport double-buffers the ghosts by epoch parity, so captured kernels
+    // read the pointer here instead of from their by-value Grid)
+    unsigned long long epoch;
+    const double4 *gpos_m;
 };
 
 
@@ -805,6 +810,7 @@ k_force_cells(int n, const DevCtl *__restrict__ ctl, Grid g, const uint32_t *__r
 {
     // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
     if (guard && ctl->need_rebuild) return;
+    if (g.slab) g.gpos_m = ctl->gpos_m;
     __shared__ uint32_t queue[kQueue][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
@@ -875,6 +881,7 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
 {
     const StatePtrs st = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = st.pos;
+    if (g.slab) g.gpos_m = ctl->gpos_m;
     if (n < 0) n = ctl->n_own;
     int i = blockIdx.x * kForceBlock + threadIdx.x;
     int cnt = 0;
@@ -995,6 +1002,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
 {
     // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
     if (guard && ctl->need_rebuild) return;
+    if (SLAB) g.gpos_m = ctl->gpos_m;
     constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0);  // park hits in a queue, or evaluate them where they are found
     __shared__ uint32_t queue[kPark ? kQueue : 1][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
@@ -1164,6 +1172,7 @@ k_force_overflow(DevCtl *__restrict__ ctl, Grid g, const uint32_t *__restrict__ 
                  double cutoff2, Pot pot, PotParams pp, double dt, ForceOut out, int slot0, int guard)
 {
     if (guard && ctl->need_rebuild) return;
+    if (g.slab) g.gpos_m = ctl->gpos_m;
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
     const int novf = ctl->n_overflow;

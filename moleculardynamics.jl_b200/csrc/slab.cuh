@@ -13,6 +13,7 @@ constexpr int kErrMigrationOverflow = 1;   // more leavers than the migration bu
 constexpr int kErrGhostOverflow = 2;       // boundary column larger than the ghost buffer
 constexpr int kErrOwnedOverflow = 4;       // owned + arrivals exceed the slab capacity
 constexpr int kErrLongJump = 8;            // a particle moved more than one cell column between rebuilds
+constexpr int kErrPeerTimeout = 16;        // a ring neighbour's message did not arrive in time (peer-memory transport)
 
 struct MigRec {  // 96 bytes; record 0 of every buffer is a header with p.x = record count
     double4 p;
@@ -68,6 +69,7 @@ __global__ void k_slab_classify(DevCtl *ctl, Grid g, uint32_t *__restrict__ cell
     }
     r.id = s.id[i];
     (dir == 0 ? out_l : out_r)[1 + k] = r;
+    __threadfence_system();  // the record may live in a neighbour's mailbox (peer-memory transport)
 }
 
 // graph replay exchanges the migration buffers every step: without a rebuild they must say "nobody leaves"
@@ -197,6 +199,254 @@ template <int DIM>
 __global__ void k_slab_ghost_count(Grid g, const double4 *__restrict__ gl, const double4 *__restrict__ gr,
                                    uint32_t *__restrict__ cnt_l, uint32_t *__restrict__ cnt_r)
 {
+    const int nl = (int)gl[0].x, nr = (int)gr[0].x;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nl + nr) return;
+    const double4 p = t < nl ? gl[1 + t] : gr[1 + (t - nl)];
+    int cy = cell_coord(p.y, g.cinv[1], g.nc[1]);
+    int cz = (DIM == 3) ? cell_coord(p.z, g.cinv[2], g.nc[2]) : 0;
+    atomicAdd(&(t < nl ? cnt_l : cnt_r)[cz * g.nc[1] + cy], 1u);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory transport (one process per GPU, NVLink/NVSwitch): every rank owns one MAILBOX in its own HBM, mapped into
+// its ring neighbours (and, for the tiny reduction slots, into every rank) with cudaIpc*.  Messages are written by the
+// SENDER's kernels straight into the receiver's mailbox (st.global on the mapped address), followed by a system-scope
+// fence and a 64-bit epoch flag; the receiver's stream waits in a one-warp kernel with a bounded spin.  No NCCL call, no
+// host round trip and no copy engine in the step: the whole slab step (head, conditional rebuild with its two
+// exchanges, forces, thermo) is plain kernels and replays as ONE CUDA graph.
+//   * epoch E = number of force-evaluation heads executed so far (ctl->epoch, identical on every rank);
+//   * per-step ghost data and the reduction slots are double-buffered by the parity of E: a sender can only be one
+//     head ahead of a receiver (head E+1 waits for the neighbour's head-E+1 message, which the neighbour sends after its
+//     forces of head E), so parity E is never overwritten while a rank still reads it;
+//   * flags only grow (wait for >= E).
+// The in-process ring of the single-GPU tests runs the same kernels with the other engines' mailboxes as "peers"; the
+// kernels of all ranks are then launched phase by phase on one stream, so every wait finds its flag already set.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+
+struct PeerHdr {
+    unsigned long long ghost_flag[2];   // [side] epoch of the last per-step ghost message from the left (0) / right (1) neighbour
+    unsigned long long rghost_flag[2];  // same, rebuild-time ghost message (new ghost set)
+    unsigned long long mig_flag[2];     // same, migration message
+    unsigned long long pad[2];
+    unsigned long long red_tag[2][kMaxRanks];   // [parity][source rank] epoch of red_val
+    unsigned long long red_val[2][kMaxRanks];   // bit pattern of the rank's largest squared displacement
+    unsigned long long sum_tag[2][kMaxRanks];   // thermostat sums (NVT: global kinetic energy inside the step)
+    double sum_val[2][kMaxRanks][4];
+};
+struct PeerView {
+    PeerHdr *hdr;
+    double4 *ghost;  // [2 parity][2 side][1 + ghost_cap]; side 0 = column received from the left neighbour, 1 = from the right
+    MigRec *mig;     // [2 side][1 + mig_cap]
+};
+struct PeerLinks {
+    PeerView self, left, right;
+    PeerHdr *all[kMaxRanks];  // every rank's header; all[me] == self.hdr
+    int me, nranks, ghost_cap, mig_cap;
+    long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded spin until *flag >= want; false on timeout.  A timeout is sticky (ctl->error): later waits return at once, so a
+// dead neighbour costs one timeout, not one per step, and the run ends with MDB_ERR_STATE instead of hanging the GPU.
+__device__ __forceinline__ bool peer_wait_flag(const unsigned long long *flag, unsigned long long want, long long timeout_ns, DevCtl *ctl)
+{
+    if (ld_acquire_sys_u64(flag) >= want) return true;
+    if (*(volatile int *)&ctl->error & kErrPeerTimeout) return false;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        if (ld_acquire_sys_u64(flag) >= want) return true;
+        if ((long long)(global_timer_ns() - t0) > timeout_ns) {
+            atomicOr(&ctl->error, kErrPeerTimeout);
+            return false;
+        }
+        __nanosleep(64);
+    }
+}
+
+__device__ __forceinline__ double4 *peer_ghost(const PeerView &v, int parity, int side, int ghost_cap)
+{
+    return v.ghost + (size_t)(parity * 2 + side) * (size_t)(1 + ghost_cap);
+}
+
+// Boundary columns -> the NEIGHBOURS' ghost buffers (same row-by-row order as k_slab_pack_ghost), then the flags.
+// kind 0: head of a force evaluation (epoch E = ctl->epoch + 1): per-step ghost flag + this rank's displacement bound
+//         into every rank's reduction slot;  kind 1: rebuild (E = ctl->epoch, already advanced): rebuild ghost flag.
+// `done` is a zeroed counter used to find the last CTA (it re-zeroes it).
+__global__ void __launch_bounds__(kStreamBlock)
+k_peer_pack_ghost(DevCtl *ctl, int nrows, int nxo, const uint32_t *__restrict__ start, const uint32_t *__restrict__ rowoff_l,
+                  const uint32_t *__restrict__ rowoff_r, PeerLinks lk, int kind, unsigned int *done)
+{
+    const double4 *__restrict__ pos = ctl->st[ctl->cur].pos;
+    const unsigned long long E = ctl->epoch + (kind == 0 ? 1ull : 0ull);
+    const int par = (int)(E & 1ull);
+    double4 *out_l = peer_ghost(lk.left, par, 1, lk.ghost_cap);   // my first column is the left neighbour's RIGHT ghost column
+    double4 *out_r = peer_ghost(lk.right, par, 0, lk.ghost_cap);
+    const uint32_t cap = (uint32_t)lk.ghost_cap;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row == 0) {
+        uint32_t tl = rowoff_l[nrows], tr = rowoff_r[nrows];
+        if (tl > cap || tr > cap) atomicOr(&ctl->error, kErrGhostOverflow);
+        out_l[0] = make_double4((double)min(tl, cap), 0, 0, 0);
+        out_r[0] = make_double4((double)min(tr, cap), 0, 0, 0);
+    }
+    if (row < nrows) {
+        uint32_t b = (uint32_t)row * nxo;
+        uint32_t o = rowoff_l[row];
+        for (uint32_t j = start[b]; j < start[b + 1]; j++, o++)
+            if (o < cap) out_l[1 + o] = pos[j];
+        o = rowoff_r[row];
+        for (uint32_t j = start[b + nxo - 1]; j < start[b + nxo]; j++, o++)
+            if (o < cap) out_r[1 + o] = pos[j];
+    }
+    __threadfence_system();  // this thread's remote stores are visible system-wide before the CTA reports
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int k = atomicAdd(done, 1u);
+        if (k == gridDim.x - 1) {  // last CTA: everybody's stores are out
+            *done = 0u;
+            __threadfence_system();
+            if (kind == 0) {
+                const unsigned long long bits = ctl->dmax2_bits;
+                for (int r = 0; r < lk.nranks; r++) lk.all[r]->red_val[par][lk.me] = bits;
+                __threadfence_system();
+                for (int r = 0; r < lk.nranks; r++) st_release_sys_u64(&lk.all[r]->red_tag[par][lk.me], E);
+                st_release_sys_u64(&lk.left.hdr->ghost_flag[1], E);
+                st_release_sys_u64(&lk.right.hdr->ghost_flag[0], E);
+            } else {
+                st_release_sys_u64(&lk.left.hdr->rghost_flag[1], E);
+                st_release_sys_u64(&lk.right.hdr->rghost_flag[0], E);
+            }
+        }
+    }
+}
+
+// the skin test of k_skin_check (kernels.cuh) as a function: the peer head runs it behind its own reduction
+__device__ __forceinline__ int skin_decide(double m, double scale, double skin, double skin_in, int always, int exact, DevCtl *ctl)
+{
+    double step = sqrt(m) * scale;
+    const unsigned long long dref = ctl->dref2_bits;
+    double disp = (exact && dref != 0ull) ? sqrt(__longlong_as_double((long long)dref)) : ctl->disp + step;
+    if (!exact) ctl->dref2_bits = 0ull;
+    int need = always || !ctl->list_valid || !(2.0 * disp <= skin);
+    ctl->disp = need ? 0.0 : disp;
+    ctl->need_rebuild = need;
+    double disp_in = ctl->disp_in + step;
+    int need_in = need || !(2.0 * disp_in <= skin_in);
+    ctl->disp_in = need_in ? 0.0 : disp_in;
+    ctl->inner_refresh = need_in;
+    return need;
+}
+
+#ifndef __CUDACC_RTC__
+// Head of a force evaluation on the receiving side: wait for both neighbours' ghost columns and every rank's
+// displacement bound of epoch E, take the global maximum (bit patterns of non-negative doubles order like the values;
+// NaN sorts above everything and forces a rebuild, as in the single-domain path), decide the rebuild -- every rank
+// reaches the same decision from the same P numbers -- and make parity E the live ghost buffer.
+__global__ void k_peer_wait_head(PeerLinks lk, double skin, double skin_in, int always, DevCtl *ctl, const double4 *ghost_base_biased,
+                                 CondHandles hs)
+{
+    const unsigned long long E = ctl->epoch + 1ull;
+    const int par = (int)(E & 1ull);
+    const int lane = threadIdx.x;
+    unsigned long long v = 0ull;
+    bool ok = true;
+    if (lane < lk.nranks) {
+        ok = peer_wait_flag(&lk.self.hdr->red_tag[par][lane], E, lk.timeout_ns, ctl);
+        v = ok ? *(volatile unsigned long long *)&lk.self.hdr->red_val[par][lane] : 0x7ff8000000000000ull;
+    }
+    if (lane < 2) ok = peer_wait_flag(&lk.self.hdr->ghost_flag[lane], E, lk.timeout_ns, ctl) && ok;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    if (lane == 0) {
+        ctl->dmax2_bits = 0ull;  // consumed
+        const int need = skin_decide(__longlong_as_double((long long)v), 1.0, skin, skin_in, always, 0, ctl);
+        ctl->epoch = E;
+        ctl->gpos_m = ghost_base_biased + (size_t)par * 2 * (size_t)(1 + lk.ghost_cap);
+        for (int q = 0; q < hs.n; q++) cudaGraphSetConditional(hs.h[q], need ? 1u : 0u);
+    }
+}
+#endif
+
+// rebuild, after k_slab_classify wrote the leavers into the neighbours' migration buffers: counts, fence, flags
+__global__ void k_peer_mig_publish(DevCtl *ctl, PeerLinks lk)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long E = ctl->epoch;
+    MigRec *out_l = lk.left.mig + (size_t)(1 + lk.mig_cap);  // arrives "from the right" at the left neighbour
+    MigRec *out_r = lk.right.mig;
+    out_l[0].p.x = (double)min(ctl->mig_count[0], lk.mig_cap);
+    out_r[0].p.x = (double)min(ctl->mig_count[1], lk.mig_cap);
+    __threadfence_system();
+    st_release_sys_u64(&lk.left.hdr->mig_flag[1], E);
+    st_release_sys_u64(&lk.right.hdr->mig_flag[0], E);
+}
+// which: 0 migration flags, 1 rebuild-ghost flags (both sides), epoch = ctl->epoch
+__global__ void k_peer_wait(PeerLinks lk, int which, DevCtl *ctl)
+{
+    const unsigned long long E = ctl->epoch;
+    if (threadIdx.x < 2) {
+        const unsigned long long *f = which == 0 ? &lk.self.hdr->mig_flag[threadIdx.x] : &lk.self.hdr->rghost_flag[threadIdx.x];
+        peer_wait_flag(f, E, lk.timeout_ns, ctl);
+    }
+}
+
+// thermostat steps: this rank's {U, W, n_pairs, |v|^2} sums (ctl->red, left by k_finalize stage 1) to every rank ...
+__global__ void k_peer_sum_publish(DevCtl *ctl, PeerLinks lk, int guard)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (guard && ctl->need_rebuild) return;
+    const unsigned long long E = ctl->epoch;
+    const int par = (int)(E & 1ull);
+    for (int r = 0; r < lk.nranks; r++)
+        for (int c = 0; c < 4; c++) lk.all[r]->sum_val[par][lk.me][c] = ctl->red[c];
+    __threadfence_system();
+    for (int r = 0; r < lk.nranks; r++) st_release_sys_u64(&lk.all[r]->sum_tag[par][lk.me], E);
+}
+// ... and the global sums, added in rank order (the same bits on every rank), back into ctl->red for k_finalize stage 2
+__global__ void k_peer_sum_wait(DevCtl *ctl, PeerLinks lk, int guard)
+{
+    if (guard && ctl->need_rebuild) return;
+    const unsigned long long E = ctl->epoch;
+    const int par = (int)(E & 1ull);
+    const int lane = threadIdx.x;
+    bool ok = true;
+    if (lane < lk.nranks) ok = peer_wait_flag(&lk.self.hdr->sum_tag[par][lane], E, lk.timeout_ns, ctl);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r < lk.nranks; r++)
+            for (int c = 0; c < 4; c++) acc[c] += *(volatile double *)&lk.self.hdr->sum_val[par][r][c];
+        for (int c = 0; c < 4; c++) ctl->red[c] = ok ? acc[c] : __longlong_as_double(0x7ff8000000000000ll);
+    }
+}
+
+// ghost cell populations from the live parity of this rank's own mailbox
+template <int DIM>
+__global__ void k_peer_ghost_count(Grid g, const DevCtl *__restrict__ ctl, PeerLinks lk, uint32_t *__restrict__ cnt_l, uint32_t *__restrict__ cnt_r)
+{
+    const int par = (int)(ctl->epoch & 1ull);
+    const double4 *gl = peer_ghost(lk.self, par, 0, lk.ghost_cap), *gr = peer_ghost(lk.self, par, 1, lk.ghost_cap);
     const int nl = (int)gl[0].x, nr = (int)gr[0].x;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nl + nr) return;

@@ -26,6 +26,11 @@ def main():
     ring.upload(cfg["x"], cfg["diam"], velocities=v0)
     t1 = ring.run_nvt(400, 1e-3, 1.4737, 0.1)
     t2 = ring.run_nve(200, 1e-3)
+    st = ring.lead.stats()
+    expect = os.environ.get("MDB200_EXPECT_TRANSPORT")
+    if expect and int(expect) != st["slab_transport"]:
+        print("MULTIRANK FAIL transport %d, expected %s" % (st["slab_transport"], expect), flush=True)
+        sys.exit(1)
     ids, x, v, f, img = ring.download_local()
     parts = [None] * world
     dist.all_gather_object(parts, (ids, x, v, f, img))

@@ -15,12 +15,19 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_slabs_match_single_domain(world):
+def test_nccl_slabs_match_single_domain(world, transport):
+    """transport = peer: mailboxes in cudaIpc-mapped peer memory, step replayed as a CUDA graph (the default);
+    nccl: ncclSend/ncclRecv + ncclAllReduce with eager launches (MDB200_NO_PEER=1)"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ)
+    if transport == "nccl":
+        env["MDB200_NO_PEER"] = "1"
+    env["MDB200_EXPECT_TRANSPORT"] = {"peer": "3", "nccl": "2"}[transport]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + world), os.path.join(ROOT, "tests", "mp_slab_worker.py")]
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, cwd=ROOT)
+           "--master-port", str(29600 + world + (10 if transport == "nccl" else 0)), os.path.join(ROOT, "tests", "mp_slab_worker.py")]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, cwd=ROOT, env=env)
     out = p.stdout.decode()
     assert p.returncode == 0 and "MULTIRANK OK" in out, out[-4000:]

@@ -8,6 +8,15 @@ from conftest import force_error, relerr
 
 pytestmark = pytest.mark.gpu
 
+# every test of this module runs over both in-process transports: 0 = device copies (stand-in for ncclSend/ncclRecv),
+# 2 = the peer-memory kernels of the multi-GPU path (mailboxes + epoch flags, the step replayed as one CUDA graph)
+TRANSPORTS = [0, 2]
+
+
+@pytest.fixture(params=TRANSPORTS, ids=["copies", "peer"])
+def tr(request):
+    return request.param
+
 
 def _cfg(md, n=8192, melt=1500):
     from mdjl_b200 import workloads
@@ -22,10 +31,10 @@ def _cfg(md, n=8192, melt=1500):
 
 
 @pytest.mark.parametrize("nranks", [2, 3, 4])
-def test_forces_match_single_domain_and_oracle(md, orc, nranks):
+def test_forces_match_single_domain_and_oracle(md, orc, nranks, tr):
     cfg, x, v, f, img = _cfg(md)
     n = x.shape[0]
-    ring = md.SlabRing.local(nranks, 3, n, cfg["box"], 1.5, 0, seed=5)
+    ring = md.SlabRing.local(nranks, 3, n, cfg["box"], 1.5, 0, seed=5, slab_transport=tr)
     ring.upload(x, cfg["diam"], velocities=v)
     E, W, npairs = ring.compute_forces()
     _, _, F, _ = ring.download()
@@ -38,12 +47,12 @@ def test_forces_match_single_domain_and_oracle(md, orc, nranks):
 
 
 @pytest.mark.parametrize("nranks,ensemble", [(2, "nve"), (4, "nve"), (3, "nvt"), (2, "brownian")])
-def test_dynamics_match_single_domain(md, orc, nranks, ensemble):
+def test_dynamics_match_single_domain(md, orc, nranks, ensemble, tr):
     cfg, x, v, f, img = _cfg(md)
     n = x.shape[0]
     single = md.Engine(3, n, cfg["box"], 1.5, 0, seed=77)
     single.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
-    ring = md.SlabRing.local(nranks, 3, n, cfg["box"], 1.5, 0, seed=77)
+    ring = md.SlabRing.local(nranks, 3, n, cfg["box"], 1.5, 0, seed=77, slab_transport=tr)
     ring.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
     nsteps = 150
     if ensemble == "nve":
@@ -64,14 +73,14 @@ def test_dynamics_match_single_domain(md, orc, nranks, ensemble):
     ring.close()
 
 
-def test_fused_slab_step_is_bit_identical(md, orc):
+def test_fused_slab_step_is_bit_identical(md, orc, tr):
     """slab NVE runs use the fused step too (the force kernel moves the owned particles for the next step before the
     ghost exchange): same bits as the reference kernel order, across rebuilds, migrations and several run calls"""
     cfg, x, v, f, img = _cfg(md)
     n = x.shape[0]
     out = []
     for no_fuse in (True, False):
-        ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=77, no_fuse=no_fuse)
+        ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=77, no_fuse=no_fuse, slab_transport=tr)
         ring.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
         rows = [ring.run_nve(k, 1e-3) for k in (1, 2, 120, 60)]
         out.append((np.concatenate(rows), ring.download(), ring.stats()))
@@ -82,14 +91,14 @@ def test_fused_slab_step_is_bit_identical(md, orc):
     assert all(s["rebuilds"] >= 2 for s in out[1][2])
 
 
-def test_upload_owned_round_trip(md, orc):
+def test_upload_owned_round_trip(md, orc, tr):
     """a rank can hand back the rows it owns (download_owned -> upload_owned) instead of the global arrays: the run
     continues exactly like after a global re-upload of the same state (slab sorts are canonical in particle id)"""
     cfg, x, v, f, img = _cfg(md)
     n = x.shape[0]
     out = []
     for owned in (False, True):
-        ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=21)
+        ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=21, slab_transport=tr)
         ring.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
         ring.run_nve(80, 1e-3)
         if owned:
@@ -115,12 +124,12 @@ def test_upload_owned_round_trip(md, orc):
     e.close()
 
 
-def test_migration_over_long_run(md, orc):
+def test_migration_over_long_run(md, orc, tr):
     """particles cross slab boundaries (and the periodic box face) during a longer run; ownership stays a partition,
     the pair count still matches an independent recount by the oracle at the end"""
     cfg, x, v, f, img = _cfg(md, n=4096)
     n = x.shape[0]
-    ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=9)
+    ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=9, slab_transport=tr)
     ring.upload(x, cfg["diam"], velocities=v * 1.5, forces=f, images=img)
     own0 = [s["n_owned"] for s in ring.stats()]
     ids0 = [e.download_owned()[0] for e in ring.engines]
@@ -148,7 +157,7 @@ def test_slab_errors(md):
     e.close()
 
 
-def test_2d_polydisperse_slabs(md, orc):
+def test_2d_polydisperse_slabs(md, orc, tr):
     """2-D non-additive mixture (BASELINE config 2 family) cut into slabs: forces vs oracle, dynamics vs single domain"""
     from mdjl_b200 import workloads
     p = workloads.poly2d(4900)
@@ -158,7 +167,7 @@ def test_2d_polydisperse_slabs(md, orc):
     x0 = e.download()[0]
     v0 = workloads.velocities(4900, 2, 0.11)
     e.upload(x0, p["diam"], velocities=v0)
-    ring = md.SlabRing.local(3, 2, 4900, p["box"], 1.5, md._capi.POT_POLY, (1.25, 0.2), seed=3)
+    ring = md.SlabRing.local(3, 2, 4900, p["box"], 1.5, md._capi.POT_POLY, (1.25, 0.2), seed=3, slab_transport=tr)
     ring.upload(x0, p["diam"], velocities=v0)
     E, W, npairs = ring.compute_forces()
     ref = orc.forces(x0, p["diam"], p["box"], 1.5, orc.POT_POLY, (1.25, 0.2))
@@ -171,4 +180,57 @@ def test_2d_polydisperse_slabs(md, orc):
     assert np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a[:, :3], b[:, :3], rtol=1e-9)
     assert np.max(np.abs(e.download()[0] - ring.download()[0])) < 1e-9
     e.close()
+    ring.close()
+
+
+@pytest.mark.parametrize("ensemble", ["nve", "nvt", "brownian"])
+def test_peer_transport_is_bit_identical_to_copies(md, orc, ensemble):
+    """the peer-memory transport (graph replay and eager launches) moves the same bytes as the copy transport: thermo rows,
+    final state, ownership and rebuild counts agree bit for bit, across rebuilds, migrations and several run calls"""
+    cfg, x, v, f, img = _cfg(md)
+    n = x.shape[0]
+    out = []
+    for kw in (dict(slab_transport=0), dict(slab_transport=2), dict(slab_transport=2, use_graph=False)):
+        ring = md.SlabRing.local(4, 3, n, cfg["box"], 1.5, 0, seed=31, **kw)
+        ring.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
+        rows = []
+        for k in (1, 130, 2, 90):
+            if ensemble == "nve":
+                rows.append(ring.run_nve(k, 1e-3))
+            elif ensemble == "nvt":
+                rows.append(ring.run_nvt(k, 1e-3, 1.4737, 0.1))
+            else:
+                rows.append(ring.run_brownian(k, 1e-5, 1.4737))
+        E, W, npairs = ring.compute_forces()
+        st = ring.stats()
+        out.append((np.concatenate(rows), ring.download(), [s["rebuilds"] for s in st], [s["n_owned"] for s in st], (E, W, npairs),
+                    st[0]["slab_transport"], st[0]["slab_graph"]))
+        ring.close()
+    assert (out[0][5], out[1][5], out[2][5]) == (1, 3, 3) and (out[0][6], out[1][6], out[2][6]) == (0, 1, 0)
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0])
+        for a, b in zip(out[0][1], o[1]):
+            assert np.array_equal(a, b)
+        assert out[0][2] == o[2] and out[0][3] == o[3] and out[0][4] == o[4]
+    assert min(out[0][2]) >= 2
+
+
+def test_peer_wait_times_out_instead_of_hanging(md, monkeypatch):
+    """a neighbour that never sends must end the run with MDB_ERR_STATE after MDB200_PEER_TIMEOUT_S, not hang the GPU
+    (fault injection: MDB200_PEER_TEST_MUTE_RANK makes one rank of the ring skip its head message)"""
+    import time
+    from mdjl_b200 import workloads, _capi
+    monkeypatch.setenv("MDB200_PEER_TIMEOUT_S", "0.25")
+    n = 4096
+    cfg = workloads.phs_fluid(n)
+    ring = md.SlabRing.local(2, 3, n, cfg["box"], 1.5, 0, seed=1, slab_transport=2)
+    ring.upload(cfg["x"], cfg["diam"], velocities=workloads.velocities(n, 3, 1.0))
+    assert np.all(np.isfinite(ring.run_nve(20, 1e-3)))       # healthy ring
+    monkeypatch.setenv("MDB200_PEER_TEST_MUTE_RANK", "1")
+    ring.upload(cfg["x"], cfg["diam"], velocities=workloads.velocities(n, 3, 1.0))
+    t0 = time.perf_counter()
+    with pytest.raises(md.MdbError) as ei:
+        ring.run_nve(50, 1e-3)
+    assert ei.value.code == _capi.ERR_STATE and "did not arrive" in str(ei.value)
+    assert time.perf_counter() - t0 < 10.0                     # one timeout per waiting rank, then sticky
     ring.close()
