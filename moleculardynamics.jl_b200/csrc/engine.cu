@@ -27,6 +27,9 @@
 using namespace mdb;
 
 #define MDB_EXPORT extern "C" __attribute__((visibility("default")))
+#ifndef MDB_DEFAULT_FORCE_VARIANT
+#define MDB_DEFAULT_FORCE_VARIANT 0  // see kernels.cuh "K4 (staged)" and profiles/r02_force_ab.md
+#endif
 
 static thread_local std::string g_create_error;
 
@@ -79,6 +82,7 @@ struct mdb_engine_s {
     int64_t alloc_ncell = -1, alloc_cap = -1;
     int alloc_kmax = -1, alloc_mode = -1;
     int force_cta_per_sm = 4, stream_cta_per_sm = 4, kick_cta_per_sm = 4;
+    int force_variant = 0;  // list-mode pair-force kernel: 0 = k_force_list (direct gathers), 1 = k_force_list_staged (cp.async staging)
     DevCtl *ctl = nullptr;
     DevCtl *h_ctl = nullptr;  // pinned mirror
     double *d_thermo = nullptr, *d_ktemp = nullptr, *d_scratch = nullptr;
@@ -170,9 +174,12 @@ static int fail(Engine *e, int code, const std::string &msg)
 static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
 // persistent grids: a multiple of the SM count, CTAs walk tiles with a grid stride
 // exactly one resident wave (occupancy API), so no CTA waits for a second wave
-static inline int force_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kForceBlock), e->nsm * e->force_cta_per_sm)); }
-static inline int stream_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * e->stream_cta_per_sm)); }
-static inline int kick_grid(const Engine *e) { return std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * e->kick_cta_per_sm)); }
+// slabs: sized by the slab CAPACITY, not by the momentary owned count (migration changes it at every rebuild): a captured
+// step graph bakes the grid in, and the grouping of the per-CTA partial sums must not depend on when it was captured
+static inline int64_t grid_particles(const Engine *e) { return e->slab ? (int64_t)e->cap_own : (int64_t)e->n; }
+static inline int force_grid(const Engine *e) { return std::max(1, std::min(nblk(grid_particles(e), kForceBlock), e->nsm * e->force_cta_per_sm)); }
+static inline int stream_grid(const Engine *e) { return std::max(1, std::min(nblk(grid_particles(e), kStreamBlock), e->nsm * e->stream_cta_per_sm)); }
+static inline int kick_grid(const Engine *e) { return std::max(1, std::min(nblk(grid_particles(e), kStreamBlock), e->nsm * e->kick_cta_per_sm)); }
 constexpr int kOverflowGrid = 8;
 
 template <class F>
@@ -620,6 +627,9 @@ static void enqueue_force(Engine *e, double dt)
             if (e->tri)
                 k_force_list<DIM, Pot, KICK2, false, true><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
                                                                                      e->r_grid + e->skin, pot, e->pp, dt, out, 0);
+            else if (e->force_variant == 1)
+                k_force_list_staged<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                      e->r_grid + e->skin, pot, e->pp, dt, out, 0);
             else
                 k_force_list<DIM, Pot, KICK2, false, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
                                                                                       e->r_grid + e->skin, pot, e->pp, dt, out, 0);
@@ -648,6 +658,22 @@ static void query_occupancy(Engine *e)
         if (e->brute) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_brute<DIM, Pot, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_brute<DIM, Pot, false>, kForceBlock, 0);
+        } else if (e->mode == MDB_MODE_LIST && e->force_variant == 1 && !e->tri) {
+            // the staged kernel: its shared-memory slots bound the residency
+            int q[4] = {0, 0, 0, 0};
+            if (e->slab) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_staged<DIM, Pot, 0, true>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_staged<DIM, Pot, 1, true>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_staged<DIM, Pot, 2, true>, kForceBlock, 0);
+                q[3] = q[2];
+            } else {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_staged<DIM, Pot, 0, false>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_staged<DIM, Pot, 1, false>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_staged<DIM, Pot, 2, false>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[3], k_force_list_staged<DIM, Pot, 3, false>, kForceBlock, 0);
+            }
+            a = std::min(std::min(q[0], q[1]), std::min(q[2], q[3]));
+            b = a;
         } else if (e->mode == MDB_MODE_LIST) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, 1, false>, kForceBlock, 0);
             if (e->slab) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_list<DIM, Pot, 1, true>, kForceBlock, 0);
@@ -1244,6 +1270,10 @@ static void enqueue_force_slab(Engine *e, double dt, int guard = 0)
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         if (e->mode == MDB_MODE_LIST) {
+            if (e->force_variant == 1)
+                k_force_list_staged<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                     e->r_grid + e->skin, pot, e->pp, dt, out, guard);
+            else
             k_force_list<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
                                                                        pot, e->pp, dt, out, guard);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
@@ -2026,6 +2056,10 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
             e->L[k] = 1.0 / std::sqrt(Ui9[3 * k] * Ui9[3 * k] + Ui9[3 * k + 1] * Ui9[3 * k + 1] + Ui9[3 * k + 2] * Ui9[3 * k + 2]);
     }
     memcpy(e->pp.p, cfg->pot_params, sizeof(e->pp.p));
+    {
+        const char *fv = getenv("MDB200_FORCE_VARIANT");
+        e->force_variant = fv ? atoi(fv) : MDB_DEFAULT_FORCE_VARIANT;
+    }
     memset(&e->stats, 0, sizeof(e->stats));
     memset(&e->grid, 0, sizeof(e->grid));
     auto bail = [&](int code) {

@@ -1163,6 +1163,248 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     cta_epilogue(acc, out, blockIdx.x);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4 (staged): the list-driven pair-force kernel with the NEIGHBOUR RECORDS STAGED IN SHARED MEMORY by asynchronous
+// copies (cp.async / LDGSTS) one tile ahead of their use.
+//   ncu on k_force_list (profiles/r01_s9_fused_ncu.md): 37 % of all warp-stall samples sit on the first use of a gathered
+//   neighbour record (long scoreboard), with 7 warps per scheduler nothing else is saturated.  Here every thread posts the
+//   gathers of tile t+1 (list indices prefetched one tile earlier still, into registers) as 16-byte asynchronous copies
+//   into its own shared-memory slots, then evaluates tile t out of the slots filled during tile t-1: the round trip to
+//   L2/HBM overlaps a whole tile of arithmetic instead of stalling the warp, and the parked-hit queue re-reads its records
+//   from shared memory instead of gathering them a second time.
+//   * slots: stage[2][kStageSlots][128] double4, private to the thread that filled them: no CTA barrier in the tile loop,
+//     cp.async.wait_group is all the synchronisation there is;
+//   * a particle with more than kStageSlots listed candidates (about 5 % on the inner list; every particle while the outer
+//     list is walked to refresh the inner one) takes the rest through direct gathers as before;
+//   * arithmetic, candidate order and reduction order are those of k_force_list: results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+#ifndef MDB_STAGE_SLOTS
+#define MDB_STAGE_SLOTS 4
+#endif
+#ifndef MDB_STAGED_MIN_CTAS
+#define MDB_STAGED_MIN_CTAS 6
+#endif
+constexpr int kStageSlots = MDB_STAGE_SLOTS;
+
+__device__ __forceinline__ void cp_async_rec(double4 *smem_dst, const double4 *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned long long s = (unsigned long long)__cvta_generic_to_global(gsrc);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.cg.shared.global [%0+16], [%1+16], 16;" ::"r"(d), "l"(s) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ double4 lds_rec(const double4 *p)
+{
+    double4 r;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%4];\n\tld.shared.v2.f64 {%2,%3}, [%4+16];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "r"(a) : "memory");
+    return r;
+}
+
+template <int DIM, class Pot, int KICK2, bool SLAB>
+__global__ void __launch_bounds__(kForceBlock, MDB_STAGED_MIN_CTAS)
+k_force_list_staged(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt,
+                    ForceOut out, int guard)
+{
+    if (guard && ctl->need_rebuild) return;
+    if (SLAB) g.gpos_m = ctl->gpos_m;
+    constexpr int KS = kStageSlots;
+    constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0);
+    __shared__ __align__(32) double4 stage[2][KS][kForceBlock];
+    __shared__ uint32_t queue[kPark ? kQueue : 1][kForceBlock];
+    const StatePtrs s = ctl->st[ctl->cur];
+    const double4 *__restrict__ pos = s.pos;
+    double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 >= 2 only
+    double vmax2 = 0.0, dref2 = 0.0;
+    const unsigned long long rng_step = ctl->rng_step;  // KICK2 == 3 only
+    const bool refresh = ctl->inner_refresh != 0;       // uniform over the grid
+    const uint32_t *__restrict__ nl = refresh ? lv.nl : lv.nl_in;
+    const int32_t *__restrict__ nnbr = refresh ? lv.nnbr : lv.nnbr_in;
+    const int kcap = refresh ? lv.kmax : lv.kmax_in;
+    const int64_t stride = lv.stride;
+    ThreadSums acc;
+    if (n < 0) n = ctl->n_own;
+    const int ntiles = (n + kForceBlock - 1) / kForceBlock;
+    const int tile_step = gridDim.x;
+    const int tid = threadIdx.x;
+    int max_in = 0;
+
+    // list head of one particle: which list it walks (a particle whose inner list overflowed keeps walking its outer list,
+    // a particle whose outer list overflowed is left to k_force_overflow), how many candidates, the first KS indices
+    auto fetch = [&](int tile, int &cnt, bool &outer, uint32_t (&idx)[KS]) {
+        const int i = tile * kForceBlock + tid;
+        cnt = 0;
+        outer = refresh;
+        if (tile < ntiles && i < n) {
+            int c = nnbr[i];
+            const uint32_t *__restrict__ src = nl;
+            if (!refresh && c > kcap) {
+                src = lv.nl;
+                c = lv.nnbr[i];
+                outer = true;
+            }
+            if (c > lv.kmax) c = -1;  // outer overflow: not ours
+#pragma unroll
+            for (int u = 0; u < KS; u++) idx[u] = (u < c) ? src[(int64_t)u * stride + i] : 0u;
+            cnt = c;
+        }
+    };
+    auto post = [&](int buf, int cnt, const uint32_t (&idx)[KS]) {
+#pragma unroll
+        for (int u = 0; u < KS; u++)
+            if (u < cnt) cp_async_rec(&stage[buf][u][tid], SLAB ? nbr_ptr(g, pos, idx[u]) : pos + idx[u]);
+        cp_async_commit();
+    };
+
+    int tile = blockIdx.x;
+    int cnt, cnt_s;
+    bool outer, outer_s;
+    uint32_t idx_s[KS];
+    double4 pi_n = make_double4(0, 0, 0, 1);
+    // prologue: stage the first tile, fetch the list heads of the second
+    fetch(tile, cnt, outer, idx_s);
+    post(0, cnt, idx_s);
+    {
+        const int i0 = tile * kForceBlock + tid;
+        if (tile < ntiles && i0 < n) pi_n = pos[i0];
+    }
+    fetch(tile + tile_step, cnt_s, outer_s, idx_s);
+    int buf = 0;
+    for (; tile < ntiles; tile += tile_step, buf ^= 1) {
+        const int i = tile * kForceBlock + tid;
+        const bool in_range = i < n;
+        const double4 pi = pi_n;
+        // the next tile's gathers go out now; its own record and the list heads of the tile after it follow
+        post(buf ^ 1, cnt_s, idx_s);
+        const int cnt_next = cnt_s;
+        const bool outer_next = outer_s;
+        {
+            const int in = (tile + tile_step) * kForceBlock + tid;
+            if (tile + tile_step < ntiles && in < n) pi_n = pos[in];
+        }
+        fetch(tile + 2 * tile_step, cnt_s, outer_s, idx_s);
+        double vel[3] = {0.0, 0.0, 0.0};
+        if ((KICK2 == 1 || KICK2 == 2) && in_range) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) vel[k] = s.vel[k * s.cap + i];
+        }
+        const bool active = in_range && cnt >= 0;
+        const int ncand = active ? cnt : 0;
+        const uint32_t *__restrict__ mynl = outer ? lv.nl : nl;
+        const bool write_inner = refresh;
+        double F[3] = {0.0, 0.0, 0.0};
+        int nq = 0, nin = 0;
+        bool wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
+        if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
+        const bool wrap_any = __any_sync(0xffffffffu, wrap);
+        cp_async_wait<1>();  // this tile's slots are filled (the group posted above may still be in flight)
+        auto candidate_record = [&](int k) -> double4 {
+            if (k < KS) return lds_rec(&stage[buf][k][tid]);
+            const uint32_t j = mynl[(int64_t)k * stride + i];
+            return ldg_pos(SLAB ? nbr_ptr(g, pos, j) : pos + j);
+        };
+        auto drain_one = [&]() {
+            if (nq > 0) {
+                const int k = (int)queue[--nq][tid];
+                const double4 pj = candidate_record(k);
+                double dx, dy, dz, d2;
+                if (wrap_any) d2 = separation_wrap<DIM, 0>(g, pi, pj, dx, dy, dz);
+                else d2 = separation_plain<DIM>(pi, pj, dx, dy, dz);
+                pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
+            }
+        };
+        auto consider = [&](int k, const double4 &pj, uint32_t j) {
+            double dx, dy, dz;
+            const double d2 = wrap ? separation_wrap<DIM, 0>(g, pi, pj, dx, dy, dz) : separation_plain<DIM>(pi, pj, dx, dy, dz);
+            if (write_inner && d2 <= lv.rin2) {
+                if (nin < lv.kmax_in) lv.nl_in[(int64_t)nin * stride + i] = j;
+                nin++;
+            }
+            if (d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj.w)) {
+                if (kPark) queue[nq++][tid] = (uint32_t)k;
+                else pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
+            }
+        };
+        // staged candidates: shared memory
+#pragma unroll
+        for (int u = 0; u < KS; u++) {
+            if (u < ncand) {
+                const double4 pj = lds_rec(&stage[buf][u][tid]);
+                // the index is only needed when the inner list is being rewritten: re-read it then (coalesced, L1/L2-resident)
+                const uint32_t j = write_inner ? mynl[(int64_t)u * stride + i] : 0u;
+                consider(u, pj, j);
+            }
+        }
+        if (kPark && nq > kQueue - kUnroll) {
+            while (nq > 0) drain_one();
+        }
+        // the rest of a long list: direct gathers, index chunk c+1 requested with the gathers of chunk c
+        if (ncand > KS) {
+            uint32_t jj[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) jj[u] = (KS + u < ncand) ? mynl[(int64_t)(KS + u) * stride + i] : (uint32_t)i;
+            for (int k0 = KS; k0 < ncand; k0 += kUnroll) {
+                double4 pj[kUnroll];
+                uint32_t jc[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    jc[u] = jj[u];
+                    pj[u] = make_double4(0.0, 0.0, 0.0, 1.0);
+                    if (k0 + u < ncand) pj[u] = ldg_pos(SLAB ? nbr_ptr(g, pos, jc[u]) : pos + jc[u]);
+                }
+                if (k0 + kUnroll < ncand) {
+#pragma unroll
+                    for (int u = 0; u < kUnroll; u++)
+                        jj[u] = (k0 + kUnroll + u < ncand) ? mynl[(int64_t)(k0 + kUnroll + u) * stride + i] : (uint32_t)i;
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++)
+                    if (k0 + u < ncand) consider(k0 + u, pj[u], jc[u]);
+                if (kPark && nq > kQueue - kUnroll) {
+                    while (nq > 0) drain_one();
+                }
+            }
+        }
+        if (kPark) {
+            while (__any_sync(0xffffffffu, nq > 0)) drain_one();
+        }
+        if (write_inner && in_range) {
+            lv.nnbr_in[i] = active ? nin : 0x7fffffff;  // outer-overflow particles never use the inner list
+            max_in = max(max_in, active ? nin : 0);
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
+            if (KICK2 == 1) {
+                double v2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; k++) {
+                    double v = vel[k];
+                    v += (F[k] * dt) * 0.5;
+                    s.vel[k * s.cap + i] = v;
+                    v2 = (k == 0) ? v * v : v2 + v * v;
+                }
+                acc.v2 += v2;
+            }
+            if (KICK2 == 2) leap_epilogue<DIM, 0>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
+            if (KICK2 == 3) brown_epilogue<DIM, 0>(i, F, pi, s, pos_next, g, dt, ctl, rng_step, vmax2, dref2);
+        }
+        cnt = cnt_next;
+        outer = outer_next;
+    }
+    cp_async_wait<0>();
+    if (KICK2 == 2) leap_report<kForceBlock>(vmax2, dt, ctl);
+    if (KICK2 == 3) brown_report<kForceBlock>(vmax2, dref2, ctl);
+    if (refresh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) max_in = max(max_in, __shfl_xor_sync(0xffffffffu, max_in, o));
+        if ((tid & 31) == 0 && max_in > 0) atomicMax(&ctl->max_nnbr_in, max_in);
+    }
+    cta_epilogue(acc, out, blockIdx.x);
+}
+
 // list overflow (more than kmax neighbours within r_list): exact fallback through the stale-but-conservative
 // build-time cells.  Slot order is the build-time cell order, so the home cell is found by bisection on `start`.
 // One warp-lane per overflowing particle; normally the overflow list is empty and this kernel exits at once.
