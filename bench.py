@@ -45,16 +45,36 @@ BYTES_FORCE_FUSED_3D = 136.0
 BYTES_KICK_KERNEL_3D = 144.0
 
 
-def measured_traffic(kernel, n):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
-    capture (profiles/r01_traffic.json), scaled by particle count when the run is not at the captured size"""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def traffic_file():
+    """the newest profiles/rNN_traffic.json (ncu-derived numbers of the dominant kernels, one file per round)"""
+    d = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(f for f in os.listdir(d) if f.startswith("r") and f.endswith("_traffic.json"))
+    except OSError:
+        names = []
+    return os.path.join(d, names[-1]) if names else None
+
+
+def measured_traffic(kernel, n, build=None):
+    """(bytes, note): dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    ncu --set full capture, scaled by particle count when the run is not at the captured size.  The capture names the
+    build it was taken on (registers, stack bytes, kernel variant of the fused force kernel); numbers captured on a
+    DIFFERENT build than the loaded library are refused (None), not quoted."""
+    p = traffic_file()
+    if not p:
+        return None, "no profiles/rNN_traffic.json"
     try:
         with open(p) as fh:
-            t = json.load(fh)[kernel]
-        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["n_particles"]
-    except Exception:
-        return None
+            doc = json.load(fh)
+        t = doc[kernel]
+    except Exception as exc:
+        return None, "%s: %s" % (os.path.basename(p), exc)
+    want = t.get("build")
+    if want is not None and build is not None:
+        diff = {k: (want[k], build.get(k)) for k in want if build.get(k) != want[k]}
+        if diff:
+            return None, "%s was captured on another build of the kernel (capture vs loaded: %s): stale, not quoted" % (os.path.basename(p), diff)
+    return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["n_particles"], os.path.basename(p)
 
 
 def peaks():
@@ -259,6 +279,51 @@ def run_reference(args, rank, world):
         "note": "Julia reference not executable in this image; reference-shaped C/OpenMP port (oracle/md_oracle.c)",
     }
     print(json.dumps(line), flush=True)
+
+
+def extra_configs(md, device):
+    """BASELINE.json configs 1-4 on this GPU (C5 is the headline workload): device-timed particle-steps/s of the production
+    step (graph replay / persistent small-system kernel), so that the driver's record carries every config, not just C5.
+    Synthetic inputs of SURVEY 8d, melted before timing; each entry says what ran."""
+    from mdjl_b200 import workloads
+    out = []
+
+    def case(name, dim, cfg, v0, tag, params, dt, kt, ens, steps, melt):
+        n = cfg["x"].shape[0]
+        e = md.Engine(dim, n, cfg["box"], CUTOFF, tag, params, seed=20261018, device=device)
+        e.upload(cfg["x"], cfg["diam"], velocities=v0)
+        if melt:
+            mdt = dt if ens != "brownian" else 1e-3
+            e.run_nvt(melt, mdt, kt, 100 * mdt, thermo=False)
+        run = {"nve": lambda k: e.run_nve(k, dt, thermo=False), "nvt": lambda k: e.run_nvt(k, dt, kt, 100 * dt, thermo=False),
+               "brownian": lambda k: e.run_brownian(k, dt, kt, thermo=False)}[ens]
+        run(max(20, steps // 10))
+        run(steps)
+        st = e.stats()
+        ms = st["last_run_ms"] / steps
+        bytes_step = {("nve", 3): 176.0, ("nvt", 3): 176.0, ("brownian", 3): 80.0, ("nve", 2): 120.0}[(ens, dim)]
+        hbm, _ = peaks()
+        out.append({"config": name, "n_particles": n, "ensemble": ens, "steps": steps, "us_per_step": 1e3 * ms,
+                    "particle_steps_per_s": n / ms * 1e3, "mode": {1: "cells", 2: "list", 3: "small-system persistent kernel"}[st["mode"]],
+                    "roofline_step_frac": bytes_step * n / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_particle_step": bytes_step})
+        e.close()
+
+    kt = workloads.KT_README
+    c1 = workloads.phs_fluid(1024)
+    case("C1 3-D PseudoHS N=1024 NVT (README)", 3, c1, workloads.velocities(1024, 3, kt), md._capi.POT_PSEUDOHS, (), DT, kt, "nvt", 5000, 2000)
+    case("C1 3-D PseudoHS N=1024 NVE (README)", 3, c1, workloads.velocities(1024, 3, kt), md._capi.POT_PSEUDOHS, (), DT, kt, "nve", 5000, 2000)
+    c2 = workloads.poly2d(1200)
+    e = md.Engine(2, 1200, c2["box"], CUTOFF, md._capi.POT_POLY, (1.25, 0.2), seed=1, device=device)
+    e.upload(c2["x"], c2["diam"])
+    e.fire_minimize(max_steps=3000, tol=1e-3, dt_initial=1e-4, dt_max=5e-3)   # the lattice start of the mixture overlaps
+    c2["x"] = e.download()[0]
+    e.close()
+    case("C2 2-D polydisperse N=1200 NVE", 2, c2, workloads.velocities(1200, 2, 0.11), md._capi.POT_POLY, (1.25, 0.2), 5e-3, 0.11, "nve", 5000, 2000)
+    c3 = workloads.phs_fluid(1 << 20)
+    v3 = workloads.velocities(1 << 20, 3, kt)
+    case("C3 3-D PseudoHS N=2^20 NVT", 3, c3, v3, md._capi.POT_PSEUDOHS, (), DT, kt, "nvt", 500, 1500)
+    case("C4 3-D PseudoHS N=2^20 Brownian", 3, c3, v3, md._capi.POT_PSEUDOHS, (), 1e-5, kt, "brownian", 500, 1500)
+    return out
 
 
 def slab_parity(md, dist, torch, rank, world, local_rank, uid, tr, n=65536, steps=(150, 150)):
@@ -484,6 +549,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1-C4 lines (extra_configs)")
     ap.add_argument("--cpu-sample", type=int, default=1 << 20)
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "peer"],
                     help="multi-GPU: auto = peer-memory mailboxes over NVLink (NCCL send/recv if cudaIpc is unavailable)")
@@ -567,19 +633,23 @@ def main():
         else:
             name, dur, bts = "k_kick_drift", kick, BYTES_KICK_KERNEL_3D
         achieved = bts * n / (dur * 1e-3) / 1e9
-        traffic = measured_traffic("k_kick_drift" if name == "k_kick_drift" else ("k_force_list_fused" if bts == BYTES_FORCE_FUSED_3D else "k_force_list"), n)
+        kinfo = eng.force_kernel_info()
+        traffic, traffic_note = measured_traffic("k_kick_drift" if name == "k_kick_drift" else ("k_force_list_fused" if bts == BYTES_FORCE_FUSED_3D else "k_force_list"), n,
+                                                 build=None if name == "k_kick_drift" else kinfo)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
-                    "traffic_source": "ncu --set full capture in profiles/ (dram read+write per launch)",
+                    "traffic_source": "ncu --set full capture, dram read+write per launch: %s" % traffic_note, "kernel_build": kinfo,
                     "kernel": name, "kernel_ms": dur, "algorithmic_bytes_per_particle": bts, "peak_source": peak_src}
     step_gbs = BYTES_STEP_3D * n * args.steps / (ms * 1e-3) / 1e9
     # FP64 pipe: DFMA peak measured live on this device; the dominant kernel's pipe utilisation comes from the committed
     # ncu --set full capture (sm__pipe_fp64_cycles_active), like roofline.traffic
     fp64 = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+        with open(traffic_file()) as fh:
             cap = json.load(fh).get("k_force_list_fused", {})
-        fp64 = {"peak_tflops_measured": eng.measure_fp64_peak(), "dominant_kernel_pipe_active_pct_ncu": cap.get("fp64_pipe_active_pct"),
-                "source": "mdb_measure_fp64_peak (DFMA chains, best of 5) / profiles/r01_s9_fused_ncu.md"}
+        stale = cap.get("build") is not None and any(eng.force_kernel_info().get(k) != v for k, v in cap["build"].items())
+        fp64 = {"peak_tflops_measured": eng.measure_fp64_peak(),
+                "dominant_kernel_pipe_active_pct_ncu": None if stale else cap.get("fp64_pipe_active_pct"),
+                "source": "mdb_measure_fp64_peak (DFMA chains, best of 5) / %s%s" % (os.path.basename(traffic_file()), " (stale capture: refused)" if stale else "")}
     except Exception:
         pass
 
@@ -629,6 +699,12 @@ def main():
         cpu = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
                "sample": "N=%d particles x 10 steps of the same fluid (after 22 untimed), reference-shaped OpenMP port, %.1f s" % (ns, t)}
 
+    extra = None
+    if not args.no_extra:
+        try:
+            extra = extra_configs(md, local_rank)
+        except Exception as exc:   # never lose the headline line over a side measurement
+            extra = [{"error": str(exc)}]
     nf = 3 * (n - 1.0)
     E = t_thermo[:, 0] + t_thermo[:, 2]
     line = {
@@ -648,6 +724,7 @@ def main():
         "cpu_baseline": cpu,
         "fp64": fp64,
         "kernels": prof,
+        "extra_configs": extra,
         "rebuilds_in_timed_region": int(rebuilds),
         "physics": {"T_mean": float(np.mean(2 * t_thermo[:, 2] / nf)), "U_per_particle": float(np.mean(t_thermo[:, 0]) / n),
                     "E_drift_rel": float((E.max() - E.min()) / abs(E[0])) if args.ensemble == "nve" else None,

@@ -203,7 +203,10 @@ int mdb_set_user_potential(mdb_handle h, const char *body, const double *params,
 /* ---- multi-GPU slabs (new; the reference is single-process) --------------------------------------------- */
 /* 128-byte NCCL unique id: rank 0 calls mdb_comm_unique_id and ships it to the others (torch.distributed broadcast) */
 int mdb_comm_unique_id(char id[128]);
-/* join the slab ring: ncclCommInitRank; ghost + migration exchange use ncclSend/ncclRecv, observables ncclAllReduce */
+/* join the slab ring: ncclCommInitRank.  The communicator bootstraps the peer-memory transport (the ranks' mailboxes are
+ * exchanged as cudaIpc handles with one ncclAllGather at the first run after every mdb_upload) and carries the chunk-end
+ * ncclAllReduce of the thermo rows; with mdb_config.slab_transport = 1 (or when the mailboxes cannot be mapped) ghost +
+ * migration exchange use ncclSend/ncclRecv and the per-step consensus ncclAllReduce */
 int mdb_comm_init(mdb_handle h, const char id[128]);
 /* in-process ring of handles on the same device (tests / single-GPU emulation of the slab protocol; no NCCL) */
 int mdb_comm_init_local(mdb_handle *handles, int32_t count);
@@ -213,7 +216,11 @@ int mdb_comm_init_local(mdb_handle *handles, int32_t count);
  * (src/simulation.jl:139-171).  mdb_frame_capture packs, on the device and in ORIGINAL particle order, one record per
  * particle {radius = diameter/2, x[dim] wrapped, xu[dim] = x + U*img (unwrapped, src/io.jl:62-70)} into frame slot
  * `slot` (0 .. MDB_FRAME_SLOTS-1) and starts its copy to pinned host memory on a second stream; it returns without waiting,
- * so the step loop continues while the frame travels (nranks == 1). */
+ * so the step loop continues while the frame travels.
+ * nranks > 1 (rank-local calls, no collective): the frame holds the particles the rank OWNS, in device slot order, with
+ * their original ids beside them; mdb_frame_write_lammps writes "<path>.<rank>", a complete LAMMPS dump of those atoms
+ * (ids = original index + 1) -- the one-file-per-processor layout of LAMMPS' `dump ... file.%`; mdb_frame_wait returns the
+ * rows of the owned particles (mdb_stats.n_owned of them at capture time). */
 #define MDB_FRAME_SLOTS 2
 int mdb_frame_capture(mdb_handle h, int32_t slot);
 /* waits for the copy; *frame = library-owned pinned array [n_particles][*width], *width = 2*dim + 1; valid until the next
@@ -229,7 +236,8 @@ int mdb_frame_flush(mdb_handle h);
 /* ---- device-side set-up and exact restart: the step before the path -------------------- */
 /* state.velocities = initialize_velocities(ktemp, rng, N, dim) (src/initialization.jl:32-47) on the device: standard normals
  * from the counter-based RNG keyed by (seed, original particle id, stream), centre-of-mass motion removed, rescaled so
- * that sum(v^2) / ((N-1) dim) == ktemp (nranks == 1) */
+ * that sum(v^2) / ((N-1) dim) == ktemp.  nranks > 1: collective over the slab ring; every rank draws for the particles it
+ * owns (same normals as a single domain, keyed by particle id), the two global sums are all-reduced. */
 int mdb_init_velocities(mdb_handle h, double ktemp, uint64_t stream);
 /* initialize_random (src/initialization.jl:20-30) on the device, first half: replaces the resident positions by uniform
  * random points of the cell (counter-based RNG keyed by seed, particle id, stream), resets the images.  Second half: a
@@ -238,7 +246,10 @@ int mdb_init_velocities(mdb_handle h, double ktemp, uint64_t stream);
 int mdb_random_positions(mdb_handle h, uint64_t stream);
 /* Exact binary checkpoint: positions, velocities, forces, images and ids in device slot order plus the RNG step counter.
  * Saving invalidates the resident Verlet list, so the saved run and a run restored with mdb_checkpoint_load on a handle
- * created with the same mdb_config continue bit-identically (nranks == 1). */
+ * created with the same mdb_config continue bit-identically.
+ * nranks > 1: COLLECTIVE by convention (every rank calls it at the same point of the run: the invalidated list must be
+ * invalid on all ranks at once); each rank writes / reads "<path>.<rank>" holding the particles it owns plus what a fresh
+ * handle needs to plan its slab, so a ring of new handles (mdb_create + mdb_comm_init*) restores without the global arrays. */
 int mdb_checkpoint_save(mdb_handle h, const char *path);
 int mdb_checkpoint_load(mdb_handle h, const char *path);
 
@@ -253,6 +264,11 @@ int mdb_synchronize(mdb_handle h);
 /* measured FP64 (DFMA) throughput of the device in TFLOP/s (8 independent FMA chains per thread, best of 5): the
  * denominator bench.py uses next to ncu's FP64-pipe utilisation; not part of the path */
 int mdb_measure_fp64_peak(mdb_handle h, double *tflops);
+/* identity of the dominant kernel as built into THIS library (the fused NVE pair-force kernel of the handle's dimension and
+ * potential): info[0] = registers per thread, [1] = static shared memory (bytes), [2] = resident CTAs per SM the engine
+ * launches, [3] = kernel variant (0 direct gathers, 1 cp.async staging), [4] = threads per CTA, [5] = local (stack) bytes per
+ * thread.  bench.py refuses ncu-derived numbers (profiles/rNN_traffic.json) captured on a different build. */
+int mdb_force_kernel_info(mdb_handle h, int32_t info[6]);
 
 #ifdef __cplusplus
 }

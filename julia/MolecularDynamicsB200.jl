@@ -11,7 +11,7 @@ module MolecularDynamicsB200
 using MolecularDynamics
 using MolecularDynamics: Parameters, SimulationState, Ensemble, NVE, NVT, Brownian, Potential, PseudoHS, LennardJones,
                          LennardJonesXPLOR, energy_lrc, pressure_lrc, compute_box_volume, open_files,
-                         write_to_file_lammps, finalize_simulation!
+                         write_to_file_lammps, finalize_simulation!, generate_log_times
 using StaticArrays, Printf, LinearAlgebra
 
 const libmdb = get(ENV, "MDB200_LIB", "libmdb200.so")
@@ -57,8 +57,10 @@ potential_tag(::PseudoHS) = (Int32(0), ())
 potential_tag(p::LennardJones) = (Int32(1), (p.epsilon, p.r_cut))
 potential_tag(p::LennardJonesXPLOR) = (Int32(2), (p.ϵ, p.r_on, p.r_cut))
 potential_tag(p::Potential) = error("evaluate not implemented on the device for potential type: $(typeof(p))")
-# the README's user-defined plugin (README.md:82-145) registers itself like this:
-#   MolecularDynamicsB200.potential_tag(p::Polydisperse) = (Int32(3), (1.25, 0.2))
+# The README's user-defined plugin (README.md:82-145) is a struct the USER defines, so its tag cannot be a method on a type of
+# this module; the user registers it with one line next to the struct (device functor 3 = PotPoly, params {rcut, non_additivity}):
+#   MolecularDynamicsB200.potential_tag(p::Polydisperse) = MolecularDynamicsB200.polydisperse_tag(p.rcut, p.non_additivity)
+polydisperse_tag(rcut::Real=1.25, non_additivity::Real=0.2) = (Int32(3), (Float64(rcut), Float64(non_additivity)))
 
 pad8(t) = ntuple(i -> i <= length(t) ? Float64(t[i]) : 0.0, 8)
 
@@ -165,8 +167,8 @@ Move a `SimulationState` produced by the stock `initialize_state` (src/initializ
 """
 function to_gpu(state::SimulationState, params::Parameters; cutoff=1.5, seed=rand(UInt64), device=0, mode=0, skin=0.0)
     D = state.dimension
-    U = state.unitcell
-    all(U[i, j] == 0 for i in 1:D, j in 1:D if i != j) || throw(MdbError(4, "only diagonal unit cells are supported"))
+    U = state.unitcell   # diagonal or general (to_unitcell's matrix branch, src/initialization.jl:13-15): the engine wraps,
+                         # images and bins through the fractional coordinates for a cell with off-diagonal entries
     tag, pp = potential_tag(params.potential)
     cell = ntuple(q -> (r = (q - 1) ÷ 3 + 1; c = (q - 1) % 3 + 1; (r <= D && c <= D) ? Float64(U[r, c]) : 0.0), 9)
     cfg = MdbConfig(D, tag, length(state.system.xpositions), cell, cutoff, pad8(pp), seed, device, mode, skin, 1, 0, 1,
@@ -264,7 +266,22 @@ function MolecularDynamics.run_simulation!(state::SimulationState{<:GPUSystem}, 
     volume = compute_box_volume(state.unitcell)
     isempty(state.velocities) || set_velocities!(sys, state.velocities)     # lazily assigned velocities (SURVEY Q12)
     virial, nprom, done = 0.0, 0, 0
-    for step in 0:frequency:(total_steps - 1)
+    # log-spaced snapshots (src/simulation.jl:81-85, 153-171): generate_log_times() (src/io.jl:17-36) with step 0 in front;
+    # the reference compares ONE pending entry per step, so a snapshot step is an output stop like a `frequency` step
+    snapshot_times = log_times ? insert!(generate_log_times(), 1, 0) : Int[]
+    snap_index = 1
+    stops = sort(unique(vcat(collect(0:frequency:(total_steps - 1)), filter(s -> s < total_steps, snapshot_times))))
+    frame_slot = Int32(0)
+    function emit_frame(path::String, step::Int, append::Bool)
+        # write_to_file_lammps (src/io.jl:78-170) without bringing the state back: the frame (unwrapped coordinates
+        # included) is packed on the device, copied on the engine's copy stream and written by its background thread
+        # while the next chunk of steps runs
+        check(sys.handle, ccall((:mdb_frame_capture, libmdb), Cint, (Handle, Int32), sys.handle, frame_slot))
+        check(sys.handle, ccall((:mdb_frame_write_lammps, libmdb), Cint, (Handle, Int32, Cstring, Int64, Int32),
+            sys.handle, frame_slot, path, step, append ? 1 : 0))
+        frame_slot = Int32(1) - frame_slot
+    end
+    for step in stops
         t = run_chunk!(sys, ensemble, params, done:step, done)               # steps done..step inclusive
         if ensemble isa Brownian
             for (k, s) in enumerate(done:step)
@@ -274,23 +291,24 @@ function MolecularDynamics.run_simulation!(state::SimulationState{<:GPUSystem}, 
             end
         end
         done = step + 1
-        U, W, KE = t[1, end], t[2, end], t[3, end]
-        if ensemble isa Brownian
-            row = (step, U / N, ensemble.ktemp, virial / (D * nprom * volume) + params.ρ * ensemble.ktemp)
-            virial, nprom = 0.0, 0
-        else
-            T = 2.0 * KE / state.nf
-            row = (step, (U + energy_lrc(params.potential, N, volume)) / N, T,
-                   W / (D * volume) + params.ρ * T + pressure_lrc(params.potential, N, volume))
+        if mod(step, frequency) == 0
+            U, W, KE = t[1, end], t[2, end], t[3, end]
+            if ensemble isa Brownian
+                # nprom == 0 gives 0.0/0 = NaN in the reference too (src/simulation.jl:252-262)
+                row = (step, U / N, ensemble.ktemp, virial / (D * nprom * volume) + params.ρ * ensemble.ktemp)
+                virial, nprom = 0.0, 0
+            else
+                T = 2.0 * KE / state.nf
+                row = (step, (U + energy_lrc(params.potential, N, volume)) / N, T,
+                       W / (D * volume) + params.ρ * T + pressure_lrc(params.potential, N, volume))
+            end
+            open(io -> Printf.format(io, Printf.Format("%d %.6f %.6f %.6f\n"), row...), thermo_file, "a")
+            emit_frame(trajectory_file, step, true)
         end
-        open(io -> Printf.format(io, Printf.Format("%d %.6f %.6f %.6f\n"), row...), thermo_file, "a")
-        # write_to_file_lammps (src/io.jl:78-170) without bringing the state back: the frame (unwrapped coordinates
-        # included) is packed on the device, copied on the engine's copy stream and written by its background thread
-        # while the next chunk of steps runs
-        slot = Int32(mod(fld(step, frequency), 2))
-        check(sys.handle, ccall((:mdb_frame_capture, libmdb), Cint, (Handle, Int32), sys.handle, slot))
-        check(sys.handle, ccall((:mdb_frame_write_lammps, libmdb), Cint, (Handle, Int32, Cstring, Int64, Int32),
-            sys.handle, slot, trajectory_file, step, 1))
+        if log_times && snap_index <= length(snapshot_times) && snapshot_times[snap_index] == step
+            emit_frame(joinpath(pathname, "snapshot.$(step)"), step, false)
+            snap_index += 1
+        end
     end
     done < total_steps && run_chunk!(sys, ensemble, params, done:(total_steps - 1), done)
     check(sys.handle, ccall((:mdb_frame_flush, libmdb), Cint, (Handle,), sys.handle))

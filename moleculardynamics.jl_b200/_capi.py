@@ -28,6 +28,7 @@ SYMBOLS = [
     "mdb_get_stats", "mdb_device_ptr", "mdb_stream", "mdb_synchronize",
     "mdb_frame_capture", "mdb_frame_wait", "mdb_frame_write_lammps", "mdb_frame_flush",
     "mdb_init_velocities", "mdb_random_positions", "mdb_checkpoint_save", "mdb_checkpoint_load", "mdb_measure_fp64_peak",
+    "mdb_force_kernel_info",
 ]
 FRAME_SLOTS = 2
 
@@ -119,6 +120,7 @@ def load():
     L.mdb_checkpoint_save.argtypes = [_H, C.c_char_p]
     L.mdb_checkpoint_load.argtypes = [_H, C.c_char_p]
     L.mdb_measure_fp64_peak.argtypes = [_H, _dp]
+    L.mdb_force_kernel_info.argtypes = [_H, _ip]
     for name in SYMBOLS:
         if name not in ("mdb_last_error",):
             getattr(L, name).restype = C.c_int
@@ -187,6 +189,7 @@ class Engine:
         cfg.nranks = nranks
         cfg.slab_transport = slab_transport
         self._lib = L
+        self._nranks = max(1, nranks)
         self.dim = dim
         self.n = n_particles
         self.box = np.array([cell[k, k] for k in range(dim)])
@@ -298,7 +301,8 @@ class Engine:
         """(n, 2*dim+1) view of the slot's pinned host frame once its copy has finished (valid until the next capture)"""
         ptr, w = _dp(), C.c_int32()
         self._check(self._lib.mdb_frame_wait(self._h, slot, C.byref(ptr), C.byref(w)))
-        return np.ctypeslib.as_array(ptr, shape=(self.n, w.value))
+        rows = self.n if self._nranks == 1 else int(self.stats()["n_owned"])   # slab handle: the rows it owned at capture time
+        return np.ctypeslib.as_array(ptr, shape=(rows, w.value))
 
     def frame_write_lammps(self, slot, path, step, append=True):
         """queue the frame for the library's writer thread (write_to_file_lammps layout, src/io.jl:78-170)"""
@@ -327,6 +331,12 @@ class Engine:
         t = C.c_double()
         self._check(self._lib.mdb_measure_fp64_peak(self._h, C.byref(t)))
         return t.value
+
+    def force_kernel_info(self):
+        """identity of the dominant (fused NVE pair-force) kernel as built into the loaded library"""
+        a = np.zeros(6, dtype=np.int32)
+        self._check(self._lib.mdb_force_kernel_info(self._h, _i(a)))
+        return dict(zip(("registers", "static_smem_bytes", "ctas_per_sm", "variant", "threads_per_cta", "local_bytes"), (int(v) for v in a)))
 
     def bussi_scale_from(self, ke, ktemp, nf, dt, tau, r1, r2):
         s = C.c_double()
@@ -480,6 +490,32 @@ class SlabRing:
 
     def stats(self):
         return [e.stats() for e in self.engines]
+
+    def init_velocities(self, ktemp, stream=0):
+        """initialize_velocities on the device, collective over the ring"""
+        self.lead.init_velocities(ktemp, stream)
+
+    def checkpoint_save(self, path):
+        """every slab writes <path>.<rank> (collective by convention)"""
+        for e in self.engines:
+            e.checkpoint_save(path)
+
+    def checkpoint_load(self, path):
+        for e in self.engines:
+            e.checkpoint_load(path)
+
+    def frame_capture(self, slot=0):
+        for e in self.engines:
+            e.frame_capture(slot)
+
+    def frame_write_lammps(self, slot, path, step, append=True):
+        """one LAMMPS dump per slab: <path>.<rank>"""
+        for e in self.engines:
+            e.frame_write_lammps(slot, path, step, append)
+
+    def frame_flush(self):
+        for e in self.engines:
+            e.frame_flush()
 
     def close(self):
         for e in self.engines:

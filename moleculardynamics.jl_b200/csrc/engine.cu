@@ -575,6 +575,8 @@ static ListView list_view(const Engine *e)
     lv.stride = e->nl_stride; lv.kmax = e->kmax; lv.kmax_in = e->kmax_in;
     double ri = e->r_search + e->skin_in;
     lv.rin2 = ri * ri;
+    double rh = e->r_search + 0.25 * e->skin_in;
+    lv.rhot2 = rh * rh;
     return lv;
 }
 

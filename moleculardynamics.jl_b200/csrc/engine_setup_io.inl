@@ -19,6 +19,12 @@ struct FrameJob {
 struct FrameIO {
     double *d_frame[MDB_FRAME_SLOTS] = {};
     double *h_frame[MDB_FRAME_SLOTS] = {};
+    // x-slab handles: rows are the rank's owned particles in slot order, ids travel beside them, one file per rank
+    int32_t *d_ids[MDB_FRAME_SLOTS] = {};
+    int32_t *h_ids[MDB_FRAME_SLOTS] = {};
+    int64_t count[MDB_FRAME_SLOTS] = {};
+    bool slab = false;
+    int rank = 0;
     cudaEvent_t copied[MDB_FRAME_SLOTS] = {};
     bool captured[MDB_FRAME_SLOTS] = {};
     int writing[MDB_FRAME_SLOTS] = {};  // jobs queued or running on the slot
@@ -40,13 +46,17 @@ struct FrameIO {
 // write_to_file_lammps for a diagonal cell: same header lines, same "%lf" columns (src/io.jl:97-167)
 static bool write_lammps_frame(const FrameIO *f, const FrameJob &job, std::string &err)
 {
-    FILE *fp = fopen(job.path.c_str(), job.append ? "a" : "w");
+    // slab handles write "<path>.<rank>": a complete LAMMPS dump of the rank's own atoms (the "%"-per-processor multi-file
+    // convention of LAMMPS' dump command; readers glob <path>.*)
+    const std::string path = f->slab ? job.path + "." + std::to_string(f->rank) : job.path;
+    FILE *fp = fopen(path.c_str(), job.append ? "a" : "w");
     if (!fp) {
-        err = "cannot open " + job.path;
+        err = "cannot open " + path;
         return false;
     }
     const int dim = f->dim, W = f->width;
-    const int64_t n = f->n;
+    const int64_t n = f->slab ? f->count[job.slot] : f->n;
+    const int32_t *ids = f->slab ? f->h_ids[job.slot] : nullptr;
     fprintf(fp, "ITEM: TIMESTEP\n%lld\n", (long long)job.step);
     fprintf(fp, "ITEM: NUMBER OF ATOMS\n%lld\n", (long long)n);
     // box bounds = norms of the lattice vectors (columns), tilt factors xy = U[1,2], xz = U[1,3], yz = U[2,3] (src/io.jl:104-128)
@@ -86,7 +96,7 @@ static bool write_lammps_frame(const FrameIO *f, const FrameJob &job, std::strin
                 char col[352];
                 for (int64_t i = lo; i < hi; i++) {
                     const double *r = fr + i * W;
-                    int len = snprintf(col, sizeof(col), "%lld %d", (long long)(i + 1), 1);
+                    int len = snprintf(col, sizeof(col), "%lld %d", (long long)((ids ? (int64_t)ids[i] : i) + 1), 1);
                     out.append(col, (size_t)std::min<int>(len, (int)sizeof(col) - 1));
                     for (int c = 0; c < W; c++) {
                         len = snprintf(col, sizeof(col), " %lf", r[c]);
@@ -101,7 +111,7 @@ static bool write_lammps_frame(const FrameIO *f, const FrameJob &job, std::strin
             if (!bufs[t].empty() && fwrite(bufs[t].data(), 1, bufs[t].size(), fp) != bufs[t].size()) ok = false;
     }
     if (fclose(fp) != 0) ok = false;
-    if (!ok) err = "short write to " + job.path;
+    if (!ok) err = "short write to " + path;
     return ok;
 }
 
@@ -144,6 +154,8 @@ static void free_frames(Engine *e)
     for (int q = 0; q < MDB_FRAME_SLOTS; q++) {
         cudaFree(f->d_frame[q]);
         if (f->h_frame[q]) cudaFreeHost(f->h_frame[q]);
+        cudaFree(f->d_ids[q]);
+        if (f->h_ids[q]) cudaFreeHost(f->h_ids[q]);
         if (f->copied[q]) cudaEventDestroy(f->copied[q]);
     }
     if (f->packed) cudaEventDestroy(f->packed);
@@ -154,11 +166,14 @@ static void free_frames(Engine *e)
 
 static int ensure_frames(Engine *e)
 {
-    if (e->fio && e->fio->n == e->N && e->fio->dim == e->dim) return MDB_OK;
+    const int64_t rows = e->slab ? (int64_t)e->cap_own : e->N;
+    if (e->fio && e->fio->n == rows && e->fio->dim == e->dim) return MDB_OK;
     free_frames(e);
     FrameIO *f = new FrameIO();
     e->fio = f;
-    f->n = e->N;
+    f->n = rows;
+    f->slab = e->slab;
+    f->rank = e->rank;
     f->dim = e->dim;
     f->width = 2 * e->dim + 1;
     f->device = e->cfg.device;
@@ -168,6 +183,10 @@ static int ensure_frames(Engine *e)
     for (int q = 0; q < MDB_FRAME_SLOTS; q++) {
         CU(cudaMalloc(&f->d_frame[q], bytes));
         CU(cudaMallocHost(&f->h_frame[q], bytes));
+        if (e->slab) {
+            CU(cudaMalloc(&f->d_ids[q], sizeof(int32_t) * (size_t)rows));
+            CU(cudaMallocHost(&f->h_ids[q], sizeof(int32_t) * (size_t)rows));
+        }
         CU(cudaEventCreateWithFlags(&f->copied[q], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&f->packed, cudaEventDisableTiming));
@@ -181,11 +200,15 @@ MDB_EXPORT int mdb_frame_capture(mdb_handle e, int32_t slot)
     if (!e) return MDB_ERR_INVALID_ARG;
     if (slot < 0 || slot >= MDB_FRAME_SLOTS) return fail(e, MDB_ERR_INVALID_ARG, "frame slot out of range");
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
-    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: frames are assembled from mdb_download_owned of every rank");
     CU(cudaSetDevice(e->cfg.device));
     int rc = ensure_frames(e);
     if (rc) return rc;
     FrameIO *f = e->fio;
+    if (e->slab) {  // the owned count changes at rebuilds: read it (rank-local call, no collective)
+        if ((rc = sync_ctl(e))) return rc;
+        e->n = e->h_ctl->n_own;
+        e->stats.n_owned = e->n;
+    }
     {
         // the slot's host image must be on disk before it is overwritten
         std::unique_lock<std::mutex> lk(f->mu);
@@ -195,12 +218,18 @@ MDB_EXPORT int mdb_frame_capture(mdb_handle e, int32_t slot)
     // (the previous copy out of this slot's device buffer was awaited above or by mdb_frame_wait; order it anyway)
     if (f->captured[slot]) CU(cudaStreamWaitEvent(s, f->copied[slot], 0));
     const int blocks = std::max(1, std::min(nblk(e->n, kStreamBlock), e->nsm * 8));
-    if (e->dim == 3) k_pack_frame<3><<<blocks, kStreamBlock, 0, s>>>(e->n, e->ctl, e->grid, f->d_frame[slot]);
+    if (e->slab) {
+        if (e->dim == 3) k_pack_frame_slab<3><<<blocks, kStreamBlock, 0, s>>>(e->ctl, e->grid, f->d_frame[slot], f->d_ids[slot]);
+        else k_pack_frame_slab<2><<<blocks, kStreamBlock, 0, s>>>(e->ctl, e->grid, f->d_frame[slot], f->d_ids[slot]);
+        f->count[slot] = e->n;
+    } else if (e->dim == 3) k_pack_frame<3><<<blocks, kStreamBlock, 0, s>>>(e->n, e->ctl, e->grid, f->d_frame[slot]);
     else k_pack_frame<2><<<blocks, kStreamBlock, 0, s>>>(e->n, e->ctl, e->grid, f->d_frame[slot]);
     e->stats.kernel_launches += 1;
     CU(cudaEventRecord(f->packed, s));
     CU(cudaStreamWaitEvent(f->copy_stream, f->packed, 0));
-    CU(cudaMemcpyAsync(f->h_frame[slot], f->d_frame[slot], sizeof(double) * (size_t)f->n * f->width, cudaMemcpyDeviceToHost, f->copy_stream));
+    const int64_t rows = e->slab ? (int64_t)e->n : f->n;
+    CU(cudaMemcpyAsync(f->h_frame[slot], f->d_frame[slot], sizeof(double) * (size_t)rows * f->width, cudaMemcpyDeviceToHost, f->copy_stream));
+    if (e->slab) CU(cudaMemcpyAsync(f->h_ids[slot], f->d_ids[slot], sizeof(int32_t) * (size_t)rows, cudaMemcpyDeviceToHost, f->copy_stream));
     CU(cudaEventRecord(f->copied[slot], f->copy_stream));
     f->captured[slot] = true;
     CU(cudaGetLastError());
@@ -259,21 +288,44 @@ MDB_EXPORT int mdb_init_velocities(mdb_handle e, double ktemp, uint64_t stream)
 {
     if (!e) return MDB_ERR_INVALID_ARG;
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload first");
-    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: draw the velocities on one handle (or the host) and upload them");
     if (!(ktemp > 0) || e->N < 2) return fail(e, MDB_ERR_INVALID_ARG, "ktemp must be > 0 and n_particles >= 2");
     CU(cudaSetDevice(e->cfg.device));
-    cudaStream_t s = e->stream;
-    const int64_t n = e->n;
-    const int blocks = std::max(1, std::min(std::min(nblk(n, kStreamBlock), e->nsm * 8), kMaxPartials));
-    for (int stage = 0; stage < 3; stage++) {
-        if (e->dim == 3) k_vel_init<3><<<blocks, kStreamBlock, 0, s>>>(stage, n, e->cfg.seed, stream, e->ctl, e->part);
-        else k_vel_init<2><<<blocks, kStreamBlock, 0, s>>>(stage, n, e->cfg.seed, stream, e->ctl, e->part);
-        if (stage < 2) k_vel_reduce<<<1, kStreamBlock, 0, s>>>(stage, blocks, e->part, (double)e->N, e->dim, ktemp, e->ctl);
+    // x-slabs: collective over the ring (every rank, or the rank-0 handle of an in-process ring).  The normals are keyed by
+    // particle id, so every rank draws exactly what a single domain would draw for its particles; the centre-of-mass and
+    // temperature sums are all-reduced between the sweeps.
+    Group storage, *G = nullptr;
+    if (e->slab) {
+        int rc = slab_group(e, storage, &G);
+        if (rc) return rc;
+        for (Engine *m : *G)
+            if (!m->uploaded) return fail(e, MDB_ERR_STATE, "mdb_upload has not been called on every slab");
+    } else {
+        storage.assign(1, e);
+        G = &storage;
     }
-    e->stats.kernel_launches += 5;
-    CU(cudaStreamSynchronize(s));
+    for (int stage = 0; stage < 3; stage++) {
+        for (Engine *m : *G) {
+            const int64_t n = m->slab ? -1 : (int64_t)m->n;
+            const int blocks = std::max(1, std::min(std::min(nblk(grid_particles(m), kStreamBlock), m->nsm * 8), kMaxPartials));
+            if (m->dim == 3) k_vel_init<3><<<blocks, kStreamBlock, 0, m->stream>>>(stage, n, m->cfg.seed, stream, m->ctl, m->part);
+            else k_vel_init<2><<<blocks, kStreamBlock, 0, m->stream>>>(stage, n, m->cfg.seed, stream, m->ctl, m->part);
+            if (stage < 2) k_vel_reduce<<<1, kStreamBlock, 0, m->stream>>>(stage, blocks, m->part, (double)m->N, m->dim, ktemp, m->ctl, m->slab ? 1 : 0);
+            m->stats.kernel_launches += stage < 2 ? 2 : 1;
+        }
+        if (e->slab && stage < 2) {
+            int rc = group_allreduce(*G, 4, false, [](Engine *m) { return m->ctl->red; });
+            if (rc) return rc;
+            for (Engine *m : *G) {
+                k_vel_reduce<<<1, kStreamBlock, 0, m->stream>>>(stage, 0, m->part, (double)m->N, m->dim, ktemp, m->ctl, 2);
+                m->stats.kernel_launches += 1;
+            }
+        }
+    }
+    for (Engine *m : *G) {
+        CU(cudaStreamSynchronize(m->stream));
+        m->have_vel = true;
+    }
     CU(cudaGetLastError());
-    e->have_vel = true;
     return MDB_OK;
 }
 
@@ -313,6 +365,15 @@ struct CkptHeader {
     int32_t reserved[7];
 };
 static const char kCkptMagic[8] = {'M', 'D', 'B', '2', '0', '0', 'C', 'K'};
+// x-slab handles write one file per rank, "<path>.<rank>", version 2: the header above followed by this block.  The global
+// diameter range travels with every file so that a fresh handle can plan its slab (cell grid, capacities, mailbox) from
+// the file alone; restoring is collective (every rank loads its file, then the ring reconnects at the next run).
+struct CkptSlab {
+    int32_t rank, nranks;
+    int64_t n_local;
+    double smin, smax;
+    int64_t reserved[4];
+};
 
 struct CkptBuffers {
     double4 *pos = nullptr;
@@ -337,9 +398,15 @@ MDB_EXPORT int mdb_checkpoint_save(mdb_handle e, const char *path)
 {
     if (!e || !path) return MDB_ERR_INVALID_ARG;
     if (!e->uploaded) return fail(e, MDB_ERR_STATE, "nothing uploaded");
-    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: checkpoint through mdb_download_owned of every rank");
     CU(cudaSetDevice(e->cfg.device));
     cudaStream_t s = e->stream;
+    if (e->slab) {  // rank-local: the owned count changes at rebuilds
+        int rc0 = sync_ctl(e);
+        if (rc0) return rc0;
+        e->n = e->h_ctl->n_own;
+        e->stats.n_owned = e->n;
+    }
+    const std::string file = e->slab ? std::string(path) + "." + std::to_string(e->rank) : std::string(path);
     const int64_t n = e->n;
     const int d = e->dim;
     CkptBuffers b;
@@ -363,42 +430,58 @@ MDB_EXPORT int mdb_checkpoint_save(mdb_handle e, const char *path)
     CkptHeader h;
     memset(&h, 0, sizeof(h));
     memcpy(h.magic, kCkptMagic, 8);
-    h.version = 1;
+    h.version = e->slab ? 2 : 1;
     h.dim = d;
     h.n_particles = e->N;
     memcpy(h.unitcell, e->cfg.unitcell, sizeof(h.unitcell));
     h.seed = e->cfg.seed;
     h.rng_step = e->h_ctl->rng_step;
     h.have_vel = e->have_vel ? 1 : 0;
-    FILE *fp = fopen(path, "wb");
-    if (!fp) return fail(e, MDB_ERR_IO, std::string("cannot open ") + path);
-    bool ok = fwrite(&h, sizeof(h), 1, fp) == 1 && fwrite(hpos.data(), sizeof(double4), n, fp) == (size_t)n &&
+    FILE *fp = fopen(file.c_str(), "wb");
+    if (!fp) return fail(e, MDB_ERR_IO, std::string("cannot open ") + file);
+    bool ok = fwrite(&h, sizeof(h), 1, fp) == 1;
+    if (e->slab) {
+        CkptSlab sl;
+        memset(&sl, 0, sizeof(sl));
+        sl.rank = e->rank; sl.nranks = e->nranks; sl.n_local = n; sl.smin = e->smin; sl.smax = e->smax;
+        ok = ok && fwrite(&sl, sizeof(sl), 1, fp) == 1;
+    }
+    ok = ok && fwrite(hpos.data(), sizeof(double4), n, fp) == (size_t)n &&
               fwrite(hvel.data(), sizeof(double), (size_t)n * d, fp) == (size_t)n * d &&
               fwrite(hfrc.data(), sizeof(double), (size_t)n * d, fp) == (size_t)n * d &&
               fwrite(himg.data(), sizeof(int32_t), (size_t)n * d, fp) == (size_t)n * d &&
               fwrite(hid.data(), sizeof(int32_t), n, fp) == (size_t)n;
     ok = (fclose(fp) == 0) && ok;
-    if (!ok) return fail(e, MDB_ERR_IO, std::string("short write to ") + path);
+    if (!ok) return fail(e, MDB_ERR_IO, std::string("short write to ") + file);
     return MDB_OK;
 }
 
 MDB_EXPORT int mdb_checkpoint_load(mdb_handle e, const char *path)
 {
     if (!e || !path) return MDB_ERR_INVALID_ARG;
-    if (e->slab) return fail(e, MDB_ERR_STATE, "nranks > 1: restore through mdb_upload");
     CU(cudaSetDevice(e->cfg.device));
-    FILE *fp = fopen(path, "rb");
-    if (!fp) return fail(e, MDB_ERR_IO, std::string("cannot open ") + path);
+    // x-slab handles read "<path>.<rank>" (collective: every rank restores its own file; the ring reconnects at the next run)
+    const std::string file = e->slab ? std::string(path) + "." + std::to_string(e->rank) : std::string(path);
+    FILE *fp = fopen(file.c_str(), "rb");
+    if (!fp) return fail(e, MDB_ERR_IO, std::string("cannot open ") + file);
     CkptHeader h;
-    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0 || h.version != 1) {
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0 || h.version != (uint32_t)(e->slab ? 2 : 1)) {
         fclose(fp);
-        return fail(e, MDB_ERR_IO, std::string(path) + " is not an mdb200 checkpoint");
+        return fail(e, MDB_ERR_IO, file + (e->slab ? " is not an mdb200 slab checkpoint" : " is not an mdb200 checkpoint"));
     }
     if (h.dim != e->dim || h.n_particles != e->N || memcmp(h.unitcell, e->cfg.unitcell, sizeof(h.unitcell)) != 0) {
         fclose(fp);
         return fail(e, MDB_ERR_INVALID_ARG, "checkpoint was written for a different system (dimension, particle count or unit cell)");
     }
-    const int64_t n = e->N;
+    CkptSlab sl;
+    memset(&sl, 0, sizeof(sl));
+    if (e->slab) {
+        if (fread(&sl, sizeof(sl), 1, fp) != 1 || sl.rank != e->rank || sl.nranks != e->nranks || sl.n_local < 0 || sl.n_local > e->N) {
+            fclose(fp);
+            return fail(e, MDB_ERR_INVALID_ARG, file + " was written by another rank or for another number of slabs");
+        }
+    }
+    const int64_t n = e->slab ? sl.n_local : e->N;
     const int d = e->dim;
     std::vector<double4> hpos(n);
     std::vector<double> hvel((size_t)n * d), hfrc((size_t)n * d);
@@ -407,42 +490,55 @@ MDB_EXPORT int mdb_checkpoint_load(mdb_handle e, const char *path)
               fread(hfrc.data(), sizeof(double), (size_t)n * d, fp) == (size_t)n * d &&
               fread(himg.data(), sizeof(int32_t), (size_t)n * d, fp) == (size_t)n * d && fread(hid.data(), sizeof(int32_t), n, fp) == (size_t)n;
     fclose(fp);
-    if (!ok) return fail(e, MDB_ERR_IO, std::string("truncated checkpoint ") + path);
-    double smin = hpos[0].w, smax = hpos[0].w;
-    for (int64_t i = 1; i < n; i++) {
-        smin = std::min(smin, hpos[i].w);
-        smax = std::max(smax, hpos[i].w);
+    if (!ok) return fail(e, MDB_ERR_IO, std::string("truncated checkpoint ") + file);
+    double smin = e->slab ? sl.smin : 0.0, smax = e->slab ? sl.smax : 0.0;
+    if (!e->slab) {
+        smin = smax = hpos[0].w;
+        for (int64_t i = 1; i < n; i++) {
+            smin = std::min(smin, hpos[i].w);
+            smax = std::max(smax, hpos[i].w);
+        }
     }
     if (!(smin > 0) || !std::isfinite(smax)) return fail(e, MDB_ERR_IO, "checkpoint holds invalid diameters");
-    // the kernels scatter through id[] (export, frames, velocity import): it must be a permutation of 0..n-1, and a state
-    // with non-finite entries is a corrupted file, not something to step
+    // the kernels scatter through id[] (export, frames, velocity import): it must be a permutation of 0..n-1 (a subset
+    // without repeats for a slab), and a state with non-finite entries is a corrupted file, not something to step
     {
-        std::vector<uint8_t> seen((size_t)n, 0);
+        std::vector<uint8_t> seen((size_t)e->N, 0);
         for (int64_t i = 0; i < n; i++) {
             const int32_t q = hid[i];
-            if (q < 0 || q >= n || seen[q]) return fail(e, MDB_ERR_IO, std::string("corrupted checkpoint ") + path + ": particle ids are not a permutation of 0..n-1");
+            if (q < 0 || q >= e->N || seen[q])
+                return fail(e, MDB_ERR_IO, std::string("corrupted checkpoint ") + file + ": particle ids are not a permutation of 0..n-1");
             seen[q] = 1;
         }
         bool finite = true;
         for (int64_t i = 0; i < n && finite; i++) finite = std::isfinite(hpos[i].x) && std::isfinite(hpos[i].y) && std::isfinite(hpos[i].z);
         for (size_t i = 0; i < (size_t)n * d && finite; i++) finite = std::isfinite(hvel[i]) && std::isfinite(hfrc[i]);
-        if (!finite) return fail(e, MDB_ERR_IO, std::string("corrupted checkpoint ") + path + ": non-finite positions, velocities or forces");
+        if (!finite) return fail(e, MDB_ERR_IO, std::string("corrupted checkpoint ") + file + ": non-finite positions, velocities or forces");
     }
     e->smin = smin; e->smax = smax;
     int rc;
     if ((rc = plan_neighbors(e))) return rc;
     e->n = (int)n;
-    if (e->cap < n || !e->st[0].pos) {
-        if ((rc = alloc_state(e, n))) return rc;
+    int64_t need_cap = n;
+    if (e->slab) {  // the capacities mdb_upload would have planned
+        const int64_t n_est = std::max<int64_t>(n, e->N / e->nranks);
+        e->cap_own = (int)(((int64_t)(n_est * 1.25) + 4096 + 31) & ~(int64_t)31);
+        need_cap = e->cap_own;
     }
+    if (e->cap < need_cap || !e->st[0].pos) {
+        if ((rc = alloc_state(e, need_cap))) return rc;
+    }
+    if (e->slab) e->cap_own = (int)e->cap;
     if ((rc = ensure_stage(e, std::max<int64_t>(n, 1)))) return rc;
     if ((rc = alloc_neighbors(e))) return rc;
     drop_graph(e);
+    if (e->slab && (rc = alloc_slab(e))) return rc;
+    if (e->group && (*e->group)[0]) drop_graph((*e->group)[0]);
     if (d == 3) query_occupancy<3>(e);
     else query_occupancy<2>(e);
     cudaStream_t s = e->stream;
     CkptBuffers b;
-    CU(b.alloc(n, d));
+    CU(b.alloc(std::max<int64_t>(n, 1), d));
     CU(cudaMemcpyAsync(b.pos, hpos.data(), sizeof(double4) * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b.vel, hvel.data(), sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b.frc, hfrc.data(), sizeof(double) * n * d, cudaMemcpyHostToDevice, s));
@@ -457,6 +553,8 @@ MDB_EXPORT int mdb_checkpoint_load(mdb_handle e, const char *path)
     c.n_tmp = (int)n;
     c.st[0] = e->st[0];
     c.st[1] = e->st[1];
+    c.epoch = 0;
+    c.gpos_m = e->grid.gpos_m;
     *e->h_ctl = c;
     CU(cudaMemcpyAsync(e->ctl, e->h_ctl, sizeof(DevCtl), cudaMemcpyHostToDevice, s));
     const int blocks = std::max(1, std::min(nblk(n, kStreamBlock), e->nsm * 8));
@@ -468,6 +566,29 @@ MDB_EXPORT int mdb_checkpoint_load(mdb_handle e, const char *path)
     e->uploaded = true;
     e->have_vel = h.have_vel != 0;
     e->stats.n_owned = e->n;
+    return MDB_OK;
+}
+
+MDB_EXPORT int mdb_force_kernel_info(mdb_handle e, int32_t info[6])
+{
+    if (!e || !info) return MDB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(e->cfg.device));
+    cudaFuncAttributes a;
+    memset(&a, 0, sizeof(a));
+    cudaError_t ce = cudaErrorInvalidValue;
+    const bool staged = e->force_variant == 1 && !e->tri;
+    dispatch_pot(e->cfg.potential, [&](auto pot) {
+        typedef decltype(pot) Pot;
+        if (e->dim == 3) ce = staged ? cudaFuncGetAttributes(&a, k_force_list_staged<3, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<3, Pot, 2, false, false>);
+        else ce = staged ? cudaFuncGetAttributes(&a, k_force_list_staged<2, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<2, Pot, 2, false, false>);
+    });
+    if (ce != cudaSuccess) return fail(e, MDB_ERR_CUDA, std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(ce));
+    info[0] = a.numRegs;
+    info[1] = (int32_t)a.sharedSizeBytes;
+    info[2] = e->force_cta_per_sm;
+    info[3] = staged ? 1 : 0;
+    info[4] = kForceBlock;
+    info[5] = (int32_t)a.localSizeBytes;
     return MDB_OK;
 }
 

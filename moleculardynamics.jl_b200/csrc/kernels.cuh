@@ -969,6 +969,13 @@ __device__ __forceinline__ double separation_plain(const double4 &pi, const doub
 #define MDB_FORCE_MIN_CTAS 7  // 72 registers, 28 warps/SM
 #endif
 constexpr int kUnroll = MDB_UNROLL;  // independent neighbour gathers in flight per thread
+// MDB_HOTFIRST = 1: the inner list is written TWO-ENDED when it is refreshed -- candidates that interact (or are about to:
+// d2 <= rhot2) from row 0 upwards, the rest from row kmax_in-1 downwards; nnbr_in = total | hot << 16 -- and interacting
+// candidates are evaluated where the walk finds them (no parked-hit queue, no second gather of the record).  With the hits
+// at the front of every list the lanes of a warp evaluate together in the first rows instead of scattered over all of them.
+#ifndef MDB_HOTFIRST
+#define MDB_HOTFIRST 0
+#endif
 #ifndef MDB_PARK
 #define MDB_PARK 1    // 0: evaluate every hit where the list walk finds it (no queue, no second gather)
 #endif
@@ -991,6 +998,7 @@ struct ListView {
     int64_t stride;
     int kmax, kmax_in;
     double rin2;            // (r_search + skin_in)^2
+    double rhot2;           // MDB_HOTFIRST: candidates closer than this at refresh time go to the front of the inner list
 };
 
 // SLAB: neighbour indices >= g.g0 address the ghost buffer of an x-slab (single domain: no such indices, no select)
@@ -1003,7 +1011,8 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
     if (guard && ctl->need_rebuild) return;
     if (SLAB) g.gpos_m = ctl->gpos_m;
-    constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0);  // park hits in a queue, or evaluate them where they are found
+    constexpr bool kHot = (MDB_HOTFIRST != 0);  // two-ended inner list, hits evaluated in place
+    constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0) && !kHot;  // park hits in a queue, or evaluate them where they are found
     __shared__ uint32_t queue[kPark ? kQueue : 1][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
@@ -1019,6 +1028,14 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     if (n < 0) n = ctl->n_own;
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
     int max_in = 0;
+    // two-ended inner list (kHot, only while the inner list is walked): row of the k-th candidate
+    const bool two_ended = kHot && !refresh;
+    auto total_of = [&](int v) { return two_ended ? (v == 0x7fffffff ? v : (v & 0xffff)) : v; };
+    auto row_of = [&](int k, int v) {
+        if (!two_ended) return k;
+        const int tot = v & 0xffff, hot = (v >> 16) & 0x7fff;
+        return k + ((k >= hot) ? (kcap - tot) : 0);
+    };
     // prologue: first tile's operands
     // grid-strided tiles: CTAs that run at the same time work on adjacent tiles, so one SM's gathers are another's L2
     // hits (a contiguous range of tiles per CTA measured 24% slower)
@@ -1035,13 +1052,14 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         pi_n = pos[i];
         cnt_n = nnbr[i];
 #pragma unroll
-        for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)u * stride + i];  // rows < kUnroll always exist
+        for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)((two_ended && cnt_n != 0x7fffffff) ? max(0, min(row_of(u, cnt_n), kcap - 1)) : u) * stride + i];  // rows < kUnroll always exist
     }
     for (; tile < tile_end; tile += tile_step) {
         i = tile * kForceBlock + threadIdx.x;
         bool active = i < n;
         const double4 pi = pi_n;
-        int cnt = cnt_n;
+        const int cnt_packed = cnt_n;
+        int cnt = total_of(cnt_n);
         uint32_t jj[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) jj[u] = jn[u];
@@ -1059,15 +1077,17 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 pi_n = pos[in];
                 cnt_n = nnbr[in];
 #pragma unroll
-                for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)u * stride + in];
+                for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)((two_ended && cnt_n != 0x7fffffff) ? max(0, min(row_of(u, cnt_n), kcap - 1)) : u) * stride + in];
             }
         }
         // which list this particle walks: normally the grid-uniform choice; a particle whose inner list overflowed
         // keeps walking its outer list (exact either way)
         const uint32_t *__restrict__ mynl = nl;
         bool write_inner = refresh;
+        bool mapped = two_ended;
         if (active && !refresh && cnt > kcap) {
             mynl = lv.nl;
+            mapped = false;
             cnt = lv.nnbr[i];
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) jj[u] = mynl[(int64_t)u * stride + i];
@@ -1077,7 +1097,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         }
         if (!active) cnt = 0;
         double F[3] = {0.0, 0.0, 0.0};
-        int nq = 0, nin = 0;
+        int nq = 0, nin = 0, nhot = 0;
         // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
         bool wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
         if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
@@ -1108,7 +1128,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
             if (k0 + kUnroll < cnt) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++)
-                    jj[u] = (k0 + kUnroll + u < cnt) ? mynl[(int64_t)(k0 + kUnroll + u) * stride + i] : (uint32_t)i;
+                    jj[u] = (k0 + kUnroll + u < cnt) ? mynl[(int64_t)(mapped ? row_of(k0 + kUnroll + u, cnt_packed) : k0 + kUnroll + u) * stride + i] : (uint32_t)i;
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
@@ -1116,7 +1136,13 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 double d2 = wrap ? separation_wrap<DIM, TRI ? 1 : 0>(g, pi, pj[u], dx, dy, dz) : separation_plain<DIM>(pi, pj[u], dx, dy, dz);
                 const bool valid = k0 + u < cnt;
                 if (write_inner && valid && d2 <= lv.rin2) {
-                    if (nin < lv.kmax_in) lv.nl_in[(int64_t)nin * stride + i] = jc[u];
+                    if (kHot) {
+                        const bool hot = d2 <= lv.rhot2;
+                        const int row = hot ? nhot : lv.kmax_in - 1 - (nin - nhot);
+                        if (nin < lv.kmax_in) lv.nl_in[(int64_t)row * stride + i] = jc[u];
+                        nhot += hot ? 1 : 0;
+                    } else if (nin < lv.kmax_in)
+                        lv.nl_in[(int64_t)nin * stride + i] = jc[u];
                     nin++;
                 }
                 if (valid && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
@@ -1132,7 +1158,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
             while (__any_sync(0xffffffffu, nq > 0)) drain_one();
         }
         if (write_inner && i < n) {
-            lv.nnbr_in[i] = active ? nin : 0x7fffffff;  // outer-overflow particles never use the inner list
+            lv.nnbr_in[i] = active ? (kHot ? (nin | (nhot << 16)) : nin) : 0x7fffffff;  // outer-overflow particles never use the inner list
             max_in = max(max_in, active ? nin : 0);
         }
         if (active) {

@@ -37,6 +37,34 @@ k_pack_frame(int64_t n, const DevCtl *__restrict__ ctl, Grid g, double *__restri
     }
 }
 
+// x-slab handles: the rank's owned particles in SLOT order plus their original ids (the writer prints id + 1 per row; a frame
+// is one file per rank, LAMMPS' "file.%" multi-file dump convention)
+template <int DIM>
+__global__ void __launch_bounds__(kStreamBlock)
+k_pack_frame_slab(const DevCtl *__restrict__ ctl, Grid g, double *__restrict__ frame, int32_t *__restrict__ ids)
+{
+    const StatePtrs s = ctl->st[ctl->cur];
+    const int64_t n = ctl->n_own;
+    constexpr int W = 2 * DIM + 1;
+    for (int64_t i = blockIdx.x * (int64_t)kStreamBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStreamBlock) {
+        const double4 p = ld_pos(&s.pos[i]);
+        const double x[3] = {p.x, p.y, p.z};
+        double *out = frame + i * W;
+        out[0] = p.w / 2.0;
+        int32_t im[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < DIM; k++) im[k] = s.img[k * s.cap + i];
+        double xu[3];
+        unwrap_point<DIM>(g, x, im, xu);
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            out[1 + k] = x[k];
+            out[1 + DIM + k] = xu[k];
+        }
+        ids[i] = s.id[i];
+    }
+}
+
 // standard normals keyed by (particle id, stream): ctr = (id, stream_lo, stream_hi, kTagVel<<8 | block), Box-Muller on
 // (u53_open(w0,w1), u53(w2,w3)); block 0 gives (v_x, v_y), block 1 gives v_z
 template <int DIM>
@@ -67,6 +95,7 @@ k_vel_init(int stage, int64_t n, uint64_t seed, uint64_t stream, DevCtl *__restr
     double acc[3] = {0.0, 0.0, 0.0};
     const double m[3] = {ctl->scratch[0], ctl->scratch[1], ctl->scratch[2]};
     const double fs = ctl->scratch[3];
+    if (n < 0) n = ctl->n_own;  // x-slab handles
     for (int64_t i = blockIdx.x * (int64_t)kStreamBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStreamBlock) {
         double v[3] = {0.0, 0.0, 0.0};
         if (stage == 0) {
@@ -97,15 +126,26 @@ k_vel_init(int stage, int64_t n, uint64_t seed, uint64_t stream, DevCtl *__restr
     }
 }
 // stage 0: scratch[0..2] = mean per component; stage 1: scratch[3] = fs = sqrt(ktemp / (sum_v2 / ((N-1) dim)))
-__global__ void k_vel_reduce(int stage, int nslots, const double *__restrict__ part, double n_particles, int dim, double ktemp, DevCtl *ctl)
+// slab: 1 = leave this rank's sums in ctl->red[0..2] for the all-reduce, 2 = continue from the globally summed ctl->red
+__global__ void k_vel_reduce(int stage, int nslots, const double *__restrict__ part, double n_particles, int dim, double ktemp, DevCtl *ctl,
+                             int slab = 0)
 {
     double r[3] = {0.0, 0.0, 0.0};
-    for (int q = threadIdx.x; q < nslots; q += blockDim.x) {
+    if (slab != 2) {
+        for (int q = threadIdx.x; q < nslots; q += blockDim.x) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) r[k] += part[k * kMaxPartials + q];
+            for (int k = 0; k < 3; k++) r[k] += part[k * kMaxPartials + q];
+        }
+        block_reduce<3, kStreamBlock>(r);
     }
-    block_reduce<3, kStreamBlock>(r);
+    if (threadIdx.x == 0 && slab == 1) {
+        for (int k = 0; k < 3; k++) ctl->red[k] = r[k];
+        ctl->red[3] = 0.0;
+        return;
+    }
     if (threadIdx.x == 0) {
+        if (slab == 2)
+            for (int k = 0; k < 3; k++) r[k] = ctl->red[k];
         if (stage == 0) {
             for (int k = 0; k < 3; k++) ctl->scratch[k] = r[k] / n_particles;
         } else {

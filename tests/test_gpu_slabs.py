@@ -234,3 +234,94 @@ def test_peer_wait_times_out_instead_of_hanging(md, monkeypatch):
     assert ei.value.code == _capi.ERR_STATE and "did not arrive" in str(ei.value)
     assert time.perf_counter() - t0 < 10.0                     # one timeout per waiting rank, then sticky
     ring.close()
+
+
+def test_slab_init_velocities_match_single_domain(md, orc, tr):
+    """initialize_velocities (src/initialization.jl:32-47) on a ring: every rank draws the normals of the particles it owns
+    (keyed by particle id), the centre-of-mass and temperature sums are all-reduced; same velocities as one domain"""
+    cfg, x, v, f, img = _cfg(md, n=4096, melt=200)
+    n = x.shape[0]
+    single = md.Engine(3, n, cfg["box"], 1.5, 0, seed=12)
+    single.upload(x, cfg["diam"])
+    single.init_velocities(1.3, stream=5)
+    vs = single.download()[1]
+    single.close()
+    ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=12, slab_transport=tr)
+    ring.upload(x, cfg["diam"])
+    ring.init_velocities(1.3, stream=5)
+    vr = ring.download()[1]
+    assert np.max(np.abs(vr - vs)) < 1e-13
+    assert np.max(np.abs(vr.sum(axis=0))) < 1e-10 and abs((vr ** 2).sum() / (3 * (n - 1.0)) - 1.3) < 1e-12
+    t = ring.run_nve(30, 1e-3)      # the ring steps with them (have_vel set on every member)
+    assert np.all(np.isfinite(t))
+    ring.close()
+
+
+@pytest.mark.parametrize("ensemble", ["nve", "nvt"])
+def test_slab_checkpoint_restart_is_bit_identical(md, orc, tr, tmp_path, ensemble):
+    """one checkpoint file per slab (<path>.<rank>); a ring of FRESH handles restores from the files alone (no global
+    arrays) and continues exactly like the run that was saved: thermo rows and final state bit for bit"""
+    cfg, x, v, f, img = _cfg(md)
+    n = x.shape[0]
+    path = str(tmp_path / "ring.ckpt")
+
+    def step(ring, k):
+        return ring.run_nve(k, 1e-3) if ensemble == "nve" else ring.run_nvt(k, 1e-3, 1.4737, 0.1)
+
+    a = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=44, slab_transport=tr)
+    a.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
+    step(a, 70)
+    a.checkpoint_save(path)
+    ta = step(a, 110)
+    fa = a.download()
+    own_a = [s["n_owned"] for s in a.stats()]
+    a.close()
+    b = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=44, slab_transport=tr)
+    b.checkpoint_load(path)
+    tb = step(b, 110)
+    fb = b.download()
+    assert np.array_equal(ta, tb)
+    for p, q in zip(fa, fb):
+        assert np.array_equal(p, q)
+    assert own_a == [s["n_owned"] for s in b.stats()]
+    with pytest.raises(md.MdbError):      # a file of another rank is refused
+        import shutil
+        shutil.copy(path + ".1", str(tmp_path / "swap.ckpt.0"))
+        b.engines[0].checkpoint_load(str(tmp_path / "swap.ckpt"))
+    b.close()
+
+
+def test_slab_frames_one_lammps_file_per_rank(md, orc, tr, tmp_path):
+    """trajectory frames of a ring: every slab writes <path>.<rank> with the atoms it owns (ids = original index + 1); the
+    union of the files is the single-domain frame (radius, wrapped and unwrapped coordinates)"""
+    cfg, x, v, f, img = _cfg(md, n=4096, melt=300)
+    n = x.shape[0]
+    ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=2, slab_transport=tr)
+    ring.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
+    ring.run_nve(40, 1e-3)
+    path = str(tmp_path / "ring.lammpstrj")
+    ring.frame_capture(0)
+    ring.frame_write_lammps(0, path, 40, append=False)
+    ring.run_nve(10, 1e-3)              # the step loop goes on while the frame is written
+    ring.frame_flush()
+    xr, vr, fr, ir = ring.download()
+    rows = {}
+    for r in range(3):
+        lines = open("%s.%d" % (path, r)).read().splitlines()
+        assert lines[1] == "40" and lines[2] == "ITEM: NUMBER OF ATOMS"
+        k = lines.index([l for l in lines if l.startswith("ITEM: ATOMS")][0])
+        assert int(lines[3]) == len(lines) - k - 1
+        for l in lines[k + 1:]:
+            c = l.split()
+            rows[int(c[0]) - 1] = [float(t) for t in c[2:]]
+    assert sorted(rows) == list(range(n))
+    # the frame was taken at step 40: compare with a single-domain engine stepped the same way
+    single = md.Engine(3, n, cfg["box"], 1.5, 0, seed=2, mode=md._capi.MODE_LIST)
+    single.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
+    single.run_nve(40, 1e-3)
+    single.frame_capture(0)
+    fr0 = np.array(single.frame_wait(0))
+    single.close()
+    got = np.array([rows[i] for i in range(n)])
+    assert np.max(np.abs(got - fr0)) < 2e-6      # "%lf" keeps six decimals
+    ring.close()

@@ -57,6 +57,15 @@ for v in variants:
     fin = g.download()
     g.close()
     same = None
+    cross = None
+    # across build variants (separate processes): AB_SAVE=path keeps variant 0's final state, AB_REF=path compares with it
+    if os.environ.get("AB_SAVE") and ref is None:
+        np.savez(os.environ["AB_SAVE"], x=fin[0], v=fin[1], f=fin[2], img=fin[3], t=t)
+    if os.environ.get("AB_REF"):
+        r = np.load(os.environ["AB_REF"])
+        cross = {"x_max_abs_diff": float(np.max(np.abs(r["x"] - fin[0]))), "v_max_abs_diff": float(np.max(np.abs(r["v"] - fin[1]))),
+                 "img_equal": bool(np.array_equal(r["img"], fin[3])), "pair_counts_equal": bool(np.array_equal(r["t"][:, 3], t[:, 3])),
+                 "thermo_max_rel_diff": float(np.max(np.abs(r["t"][:, :3] - t[:, :3]) / np.abs(r["t"][:, :3])))}
     if ref is None:
         ref = (fin, t)
     else:
@@ -65,4 +74,4 @@ for v in variants:
     print(json.dumps({"lib": os.path.basename(md._capi.lib_path()), "variant": v, "n": n, "ensemble": ensemble,
                       "force_kernel_ms": p["prof_force_ms"] / 60, "kick_ms": p["prof_kick_ms"] / 60, "rebuild_ms_per_step": p["prof_rebuild_ms"] / 60,
                       "step_ms_graph": s["last_run_ms"] / 200, "rate": n / (s["last_run_ms"] / 200) * 1e3,
-                      "bit_identical_to_first": same, "rebuilds": int(s["rebuilds"])}), flush=True)
+                      "bit_identical_to_first": same, "vs_saved_reference": cross, "rebuilds": int(s["rebuilds"])}), flush=True)

@@ -26,7 +26,7 @@
     } while (0)
 
 constexpr int kTile = 128;
-constexpr int kMaxSeg = 48;
+constexpr int kMaxSeg = 48;   // <= 64: the issuing warp takes two segments per lane
 constexpr int kStageRecords = 1792;  // 56 KB per stage; 2 stages = 112 KB per CTA -> 2 CTAs per SM
 
 struct Seg {
@@ -74,21 +74,38 @@ __global__ void __launch_bounds__(kTile) k_stage(int ntiles, const double4 *__re
     __syncthreads();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     double acc = 0.0;
+    // warp 0 issues a tile: lane q owns segment q (kMaxSeg <= 64: two passes), offsets by a warp prefix sum, ONE expect_tx
+    // for the whole tile, then every lane posts its own bulk copy -- no serial loop over the segments
     auto issue = [&](int tile, int buf) {
-        if (tid == 0 && tile < ntiles) {
+        if (tid < 32 && tile < ntiles) {
             const int ns = nseg[tile];
             const Seg *sg = segs + (size_t)tile * kMaxSeg;
-            uint32_t recs = 0;
-            for (int q = 0; q < ns; q++) recs += sg[q].count;
-            recs = min(recs, (uint32_t)kStageRecords);
-            total[buf] = recs;
-            mbar_expect_tx(&bar[buf], recs * 32u);
+            Seg mine[2];
+            uint32_t cnt[2], off[2], run = 0;
+            for (int h = 0; h < 2; h++) {
+                const int q = h * 32 + tid;
+                mine[h] = q < ns ? sg[q] : Seg{0u, 0u};
+                cnt[h] = mine[h].count;
+                uint32_t incl = cnt[h];
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                off[h] = run + incl - cnt[h];
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            const uint32_t recs = min(run, (uint32_t)kStageRecords);
+            if (tid == 0) {
+                total[buf] = recs;
+                mbar_expect_tx(&bar[buf], recs * 32u);
+            }
+            __syncwarp();
             double4 *dst = buf ? stage1 : stage0;
-            uint32_t off = 0;
-            for (int q = 0; q < ns && off < recs; q++) {
-                const uint32_t c = min(sg[q].count, recs - off);
-                if (c) bulk_g2s(dst + off, pos + sg[q].begin, c * 32u, &bar[buf]);
-                off += c;
+            for (int h = 0; h < 2; h++) {
+                if (off[h] < recs) {
+                    const uint32_t c = min(cnt[h], recs - off[h]);
+                    if (c) bulk_g2s(dst + off[h], pos + mine[h].begin, c * 32u, &bar[buf]);
+                }
             }
         }
     };
