@@ -266,7 +266,7 @@ int mdb_synchronize(mdb_handle h);
 int mdb_measure_fp64_peak(mdb_handle h, double *tflops);
 /* identity of the dominant kernel as built into THIS library (the fused NVE pair-force kernel of the handle's dimension and
  * potential): info[0] = registers per thread, [1] = static shared memory (bytes), [2] = resident CTAs per SM the engine
- * launches, [3] = kernel variant (0 direct gathers, 1 cp.async staging), [4] = threads per CTA, [5] = local (stack) bytes per
+ * launches, [3] = kernel variant (0 direct gathers, 1 cp.async-staged gathers, 2 TMA operand ring), [4] = threads per CTA, [5] = local (stack) bytes per
  * thread.  bench.py refuses ncu-derived numbers (profiles/rNN_traffic.json) captured on a different build. */
 int mdb_force_kernel_info(mdb_handle h, int32_t info[6]);
 

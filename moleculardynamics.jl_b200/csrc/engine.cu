@@ -27,6 +27,9 @@
 using namespace mdb;
 
 #define MDB_EXPORT extern "C" __attribute__((visibility("default")))
+#ifndef MDB_DEFAULT_GRAPH_BATCH
+#define MDB_DEFAULT_GRAPH_BATCH 1  // steps per launch of the captured peer-memory slab step
+#endif
 #ifndef MDB_DEFAULT_FORCE_VARIANT
 #define MDB_DEFAULT_FORCE_VARIANT 0  // see kernels.cuh "K4 (staged)" and profiles/r02_force_ab.md
 #endif
@@ -82,7 +85,7 @@ struct mdb_engine_s {
     int64_t alloc_ncell = -1, alloc_cap = -1;
     int alloc_kmax = -1, alloc_mode = -1;
     int force_cta_per_sm = 4, stream_cta_per_sm = 4, kick_cta_per_sm = 4;
-    int force_variant = 0;  // list-mode pair-force kernel: 0 = k_force_list (direct gathers), 1 = k_force_list_staged (cp.async staging)
+    int force_variant = 0;  // list-mode pair-force kernel: 0 = k_force_list, 1 = k_force_list_staged (cp.async gathers), 2 = k_force_list_tma (TMA operand ring)
     DevCtl *ctl = nullptr;
     DevCtl *h_ctl = nullptr;  // pinned mirror
     double *d_thermo = nullptr, *d_ktemp = nullptr, *d_scratch = nullptr;
@@ -99,6 +102,10 @@ struct mdb_engine_s {
     // hold the fused middle step
     cudaGraphExec_t gexec_last = nullptr;
     cudaGraph_t graph_last = nullptr;
+    // peer-memory slab step: graph_batch consecutive steps captured into one graph (MDB200_GRAPH_BATCH)
+    cudaGraphExec_t gexec_b = nullptr;
+    cudaGraph_t graph_b = nullptr;
+    int graph_batch = 1;
     GraphKey gkey;
     int graph_kernels_fixed = 0, graph_kernels_rebuild = 0;
 
@@ -256,7 +263,10 @@ static void drop_graph(Engine *e)
     if (e->graph) cudaGraphDestroy(e->graph);
     if (e->gexec_last) cudaGraphExecDestroy(e->gexec_last);
     if (e->graph_last) cudaGraphDestroy(e->graph_last);
+    if (e->gexec_b) cudaGraphExecDestroy(e->gexec_b);
+    if (e->graph_b) cudaGraphDestroy(e->graph_b);
     e->gexec = nullptr; e->graph = nullptr; e->gexec_last = nullptr; e->graph_last = nullptr; e->gkey = GraphKey{};
+    e->gexec_b = nullptr; e->graph_b = nullptr;
 }
 
 // inverse of the 3x3 cell matrix by the adjugate (same formula, same operation order as oracle/md_oracle.c
@@ -575,8 +585,6 @@ static ListView list_view(const Engine *e)
     lv.stride = e->nl_stride; lv.kmax = e->kmax; lv.kmax_in = e->kmax_in;
     double ri = e->r_search + e->skin_in;
     lv.rin2 = ri * ri;
-    double rh = e->r_search + 0.25 * e->skin_in;
-    lv.rhot2 = rh * rh;
     return lv;
 }
 
@@ -632,6 +640,9 @@ static void enqueue_force(Engine *e, double dt)
             else if (e->force_variant == 1)
                 k_force_list_staged<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
                                                                                       e->r_grid + e->skin, pot, e->pp, dt, out, 0);
+            else if (e->force_variant == 2)
+                k_force_list_tma<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                   e->r_grid + e->skin, pot, e->pp, dt, out, 0);
             else
                 k_force_list<DIM, Pot, KICK2, false, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
                                                                                       e->r_grid + e->skin, pot, e->pp, dt, out, 0);
@@ -660,6 +671,22 @@ static void query_occupancy(Engine *e)
         if (e->brute) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_brute<DIM, Pot, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_brute<DIM, Pot, false>, kForceBlock, 0);
+        } else if (e->mode == MDB_MODE_LIST && e->force_variant == 2 && !e->tri) {
+            // TMA-operand kernel: the operand ring's shared memory counts
+            int q[4] = {0, 0, 0, 0};
+            if (e->slab) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_tma<DIM, Pot, 0, true>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_tma<DIM, Pot, 1, true>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_tma<DIM, Pot, 2, true>, kForceBlock, 0);
+                q[3] = q[2];
+            } else {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_tma<DIM, Pot, 0, false>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_tma<DIM, Pot, 1, false>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_tma<DIM, Pot, 2, false>, kForceBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[3], k_force_list_tma<DIM, Pot, 3, false>, kForceBlock, 0);
+            }
+            a = std::min(std::min(q[0], q[1]), std::min(q[2], q[3]));
+            b = a;
         } else if (e->mode == MDB_MODE_LIST && e->force_variant == 1 && !e->tri) {
             // the staged kernel: its shared-memory slots bound the residency
             int q[4] = {0, 0, 0, 0};
@@ -1275,6 +1302,9 @@ static void enqueue_force_slab(Engine *e, double dt, int guard = 0)
             if (e->force_variant == 1)
                 k_force_list_staged<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2,
                                                                                      e->r_grid + e->skin, pot, e->pp, dt, out, guard);
+            else if (e->force_variant == 2)
+                k_force_list_tma<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                  e->r_grid + e->skin, pot, e->pp, dt, out, guard);
             else
             k_force_list<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
                                                                        pot, e->pp, dt, out, guard);
@@ -1502,18 +1532,15 @@ static int build_graph_slab(Group &G, const GraphKey &key, bool per_step_reduce)
 // ONE conditional node with the whole rebuild (both exchanges inside), tail -- and replays without any host round trip.
 // kind: kStepFull (kick-drift + forces + second kick; NVT, Brownian, unfused NVE), kStepFused / kStepLast (NVE, see StepKind).
 template <int DIM>
-static int build_one_graph_peer(Group &G, const GraphKey &key, int kind, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out)
+static int build_one_graph_peer(Group &G, const GraphKey &key, int kind, int batch, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out)
 {
+    // batch > 1: that many consecutive steps in ONE graph (each with its own conditional rebuild node), so that a launch
+    // amortises the per-launch cost of a graph with conditional nodes over several steps
     Engine *e = G[0];
     cudaStream_t s = e->stream;
     cudaGraph_t &graph = *graph_out;
     CU(cudaGraphCreate(&graph, 0));
     const bool conditional = (e->mode == MDB_MODE_LIST);
-    CondHandles hs{{0, 0, 0}, 0};
-    if (conditional) {
-        CU(cudaGraphConditionalHandleCreate(&hs.h[0], graph, 0, cudaGraphCondAssignDefault));
-        hs.n = 1;
-    }
     cudaGraph_t g2 = nullptr;
     auto abort_capture = [&](int code, const char *what = nullptr) {
         cudaError_t last = cudaGetLastError();
@@ -1535,54 +1562,56 @@ static int build_one_graph_peer(Group &G, const GraphKey &key, int kind, cudaGra
     int rc = MDB_OK;
     if (cudaStreamBeginCaptureToGraph(s, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
         return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph");
-    if (key.ensemble != MDB_BROWNIAN && kind == kStepFull)
-        for (Engine *g : G) {
-            k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, key.dt, g->ctl);
-            g->stats.kernel_launches += 1;
-        }
-    if ((rc = slab_head<DIM>(G, hs))) return abort_capture(rc);
     int64_t n_rebuild = 0;
-    if (conditional) {
-        cudaStreamCaptureStatus status;
-        const cudaGraphNode_t *d = nullptr;
-        size_t nd = 0;
-        if (cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &d, &nd) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamGetCaptureInfo");
-        std::vector<cudaGraphNode_t> deps(d, d + nd);
-        if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture");
-        cudaGraphNodeParams cp = {};
-        cp.type = cudaGraphNodeTypeConditional;
-        cp.conditional.handle = hs.h[0];
-        cp.conditional.type = cudaGraphCondTypeIf;
-        cp.conditional.size = 1;
-        cudaGraphNode_t cnode;
-        if (cudaGraphAddNode(&cnode, graph, deps.data(), deps.size(), &cp) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaGraphAddNode");
-        cudaGraph_t body = cp.conditional.phGraph_out[0];
-        if (cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
-            return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph(body)");
+    for (int step = 0; step < batch; step++) {
+        CondHandles hs{{0, 0, 0}, 0};
+        if (conditional) {
+            if (cudaGraphConditionalHandleCreate(&hs.h[0], graph, 0, cudaGraphCondAssignDefault) != cudaSuccess)
+                return abort_capture(MDB_ERR_CUDA, "cudaGraphConditionalHandleCreate");
+            hs.n = 1;
+        }
+        if (key.ensemble != MDB_BROWNIAN && kind == kStepFull)
+            for (Engine *g : G) {
+                k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, key.dt, g->ctl);
+                g->stats.kernel_launches += 1;
+            }
+        if ((rc = slab_head<DIM>(G, hs))) return abort_capture(rc);
         const int64_t before = launched();
-        if ((rc = group_rebuild<DIM>(G))) return abort_capture(rc);
-        n_rebuild = launched() - before;
-        if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture(body)");
-        if (cudaStreamBeginCaptureToGraph(s, graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
-            return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph(tail)");
-    } else {
-        const int64_t before = launched();
-        if ((rc = group_rebuild<DIM>(G))) return abort_capture(rc);
-        n_rebuild = launched() - before;
+        if (conditional) {
+            cudaStreamCaptureStatus status;
+            const cudaGraphNode_t *d = nullptr;
+            size_t nd = 0;
+            if (cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &d, &nd) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamGetCaptureInfo");
+            std::vector<cudaGraphNode_t> deps(d, d + nd);
+            if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture");
+            cudaGraphNodeParams cp = {};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = hs.h[0];
+            cp.conditional.type = cudaGraphCondTypeIf;
+            cp.conditional.size = 1;
+            cudaGraphNode_t cnode;
+            if (cudaGraphAddNode(&cnode, graph, deps.data(), deps.size(), &cp) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaGraphAddNode");
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            if (cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+                return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph(body)");
+            if ((rc = group_rebuild<DIM>(G))) return abort_capture(rc);
+            if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture(body)");
+            if (cudaStreamBeginCaptureToGraph(s, graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+                return abort_capture(MDB_ERR_CUDA, "cudaStreamBeginCaptureToGraph(tail)");
+        } else if ((rc = group_rebuild<DIM>(G)))
+            return abort_capture(rc);
+        n_rebuild += launched() - before;
+        const bool reduce_now = key.ensemble == MDB_NVT;
+        if (key.ensemble == MDB_BROWNIAN) rc = slab_tail<DIM, 0>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
+        else if (kind == kStepFused) rc = slab_tail<DIM, 2>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
+        else rc = slab_tail<DIM, 1>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
+        if (rc) return abort_capture(rc);
     }
-    const bool reduce_now = key.ensemble == MDB_NVT;
-    if (key.ensemble == MDB_BROWNIAN) rc = slab_tail<DIM, 0>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
-    else if (kind == kStepFused) rc = slab_tail<DIM, 2>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
-    else rc = slab_tail<DIM, 1>(G, key.ensemble, key.dt, key.tau, key.ktemp, 1, 1, reduce_now);
-    if (rc) return abort_capture(rc);
     if (cudaStreamEndCapture(s, &g2) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaStreamEndCapture");
     if (cudaGraphInstantiate(exec_out, graph, 0) != cudaSuccess) return abort_capture(MDB_ERR_CUDA, "cudaGraphInstantiate");
-    e->graph_launches_rebuild = (int)n_rebuild;
-    e->graph_launches_fixed = (int)(launched() - n_rebuild) - (conditional ? 0 : 0);
-    if (!conditional) {  // cell mode: the rebuild is part of every step
-        e->graph_launches_fixed += (int)n_rebuild;
-        e->graph_launches_rebuild = 0;
-    }
+    // per STEP: kernels of the fixed part, and of the conditional body (cell mode: the rebuild is part of every step)
+    e->graph_launches_rebuild = conditional ? (int)(n_rebuild / batch) : 0;
+    e->graph_launches_fixed = (int)((launched() - (conditional ? n_rebuild : 0)) / batch);
     for (size_t q = 0; q < G.size(); q++) G[q]->stats.kernel_launches = saved[q];
     return MDB_OK;
 }
@@ -1593,11 +1622,10 @@ static int build_graph_peer(Group &G, const GraphKey &key)
     Engine *e = G[0];
     drop_graph(e);
     int rc;
-    if (key.fused) {
-        if ((rc = build_one_graph_peer<DIM>(G, key, kStepLast, &e->graph_last, &e->gexec_last))) return rc;
-        if ((rc = build_one_graph_peer<DIM>(G, key, kStepFused, &e->graph, &e->gexec))) return rc;
-    } else if ((rc = build_one_graph_peer<DIM>(G, key, kStepFull, &e->graph, &e->gexec)))
-        return rc;
+    const int kind = key.fused ? kStepFused : kStepFull;
+    if (key.fused && (rc = build_one_graph_peer<DIM>(G, key, kStepLast, 1, &e->graph_last, &e->gexec_last))) return rc;
+    if (e->graph_batch > 1 && (rc = build_one_graph_peer<DIM>(G, key, kind, e->graph_batch, &e->graph_b, &e->gexec_b))) return rc;
+    if ((rc = build_one_graph_peer<DIM>(G, key, kind, 1, &e->graph, &e->gexec))) return rc;
     e->gkey = key;
     return MDB_OK;
 }
@@ -1711,15 +1739,27 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
         // only the thermostat needs the global kinetic energy inside the step
         const bool per_step_reduce = (ensemble == MDB_NVT);
         if (peer_graph) {
-            for (int64_t q = 0; q < m; q++) {
-                const bool first = done + q == 0, last = done + q == nsteps - 1;
+            for (int64_t q = 0; q < m;) {
+                const bool first = done + q == 0;
                 if (fused && first) {
                     for (Engine *g : G) {
                         k_kick_drift<DIM><<<kick_grid(g), kStreamBlock, 0, g->stream>>>(-1, g->grid, dt, g->ctl);
                         g->stats.kernel_launches += 1;
                     }
                 }
-                CU(cudaGraphLaunch((fused && last) ? lead->gexec_last : lead->gexec, s));
+                // steps of this chunk that run the regular (fused or full) step; the run's very last step of a fused run
+                // is the plain one
+                const int64_t regular_left = std::min(m, fused ? (nsteps - 1 - done) : m) - q;
+                if (lead->gexec_b && regular_left >= lead->graph_batch) {
+                    CU(cudaGraphLaunch(lead->gexec_b, s));
+                    q += lead->graph_batch;
+                } else if (regular_left > 0) {
+                    CU(cudaGraphLaunch(lead->gexec, s));
+                    q += 1;
+                } else {
+                    CU(cudaGraphLaunch(lead->gexec_last, s));
+                    q += 1;
+                }
             }
         } else if (use_graph) {
             for (int64_t q = 0; q < m; q++) CU(cudaGraphLaunch(lead->gexec, s));
@@ -2061,6 +2101,8 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
     {
         const char *fv = getenv("MDB200_FORCE_VARIANT");
         e->force_variant = fv ? atoi(fv) : MDB_DEFAULT_FORCE_VARIANT;
+        const char *gb = getenv("MDB200_GRAPH_BATCH");
+        e->graph_batch = gb ? std::max(1, std::min(64, atoi(gb))) : MDB_DEFAULT_GRAPH_BATCH;
     }
     memset(&e->stats, 0, sizeof(e->stats));
     memset(&e->grid, 0, sizeof(e->grid));

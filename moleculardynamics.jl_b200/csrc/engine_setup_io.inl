@@ -576,17 +576,21 @@ MDB_EXPORT int mdb_force_kernel_info(mdb_handle e, int32_t info[6])
     cudaFuncAttributes a;
     memset(&a, 0, sizeof(a));
     cudaError_t ce = cudaErrorInvalidValue;
-    const bool staged = e->force_variant == 1 && !e->tri;
+    const int var = e->tri ? 0 : e->force_variant;
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
-        if (e->dim == 3) ce = staged ? cudaFuncGetAttributes(&a, k_force_list_staged<3, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<3, Pot, 2, false, false>);
-        else ce = staged ? cudaFuncGetAttributes(&a, k_force_list_staged<2, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<2, Pot, 2, false, false>);
+        if (e->dim == 3)
+            ce = var == 1 ? cudaFuncGetAttributes(&a, k_force_list_staged<3, Pot, 2, false>)
+               : var == 2 ? cudaFuncGetAttributes(&a, k_force_list_tma<3, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<3, Pot, 2, false, false>);
+        else
+            ce = var == 1 ? cudaFuncGetAttributes(&a, k_force_list_staged<2, Pot, 2, false>)
+               : var == 2 ? cudaFuncGetAttributes(&a, k_force_list_tma<2, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<2, Pot, 2, false, false>);
     });
     if (ce != cudaSuccess) return fail(e, MDB_ERR_CUDA, std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(ce));
     info[0] = a.numRegs;
     info[1] = (int32_t)a.sharedSizeBytes;
     info[2] = e->force_cta_per_sm;
-    info[3] = staged ? 1 : 0;
+    info[3] = var;
     info[4] = kForceBlock;
     info[5] = (int32_t)a.localSizeBytes;
     return MDB_OK;

@@ -969,13 +969,6 @@ __device__ __forceinline__ double separation_plain(const double4 &pi, const doub
 #define MDB_FORCE_MIN_CTAS 7  // 72 registers, 28 warps/SM
 #endif
 constexpr int kUnroll = MDB_UNROLL;  // independent neighbour gathers in flight per thread
-// MDB_HOTFIRST = 1: the inner list is written TWO-ENDED when it is refreshed -- candidates that interact (or are about to:
-// d2 <= rhot2) from row 0 upwards, the rest from row kmax_in-1 downwards; nnbr_in = total | hot << 16 -- and interacting
-// candidates are evaluated where the walk finds them (no parked-hit queue, no second gather of the record).  With the hits
-// at the front of every list the lanes of a warp evaluate together in the first rows instead of scattered over all of them.
-#ifndef MDB_HOTFIRST
-#define MDB_HOTFIRST 0
-#endif
 #ifndef MDB_PARK
 #define MDB_PARK 1    // 0: evaluate every hit where the list walk finds it (no queue, no second gather)
 #endif
@@ -998,7 +991,6 @@ struct ListView {
     int64_t stride;
     int kmax, kmax_in;
     double rin2;            // (r_search + skin_in)^2
-    double rhot2;           // MDB_HOTFIRST: candidates closer than this at refresh time go to the front of the inner list
 };
 
 // SLAB: neighbour indices >= g.g0 address the ghost buffer of an x-slab (single domain: no such indices, no select)
@@ -1011,8 +1003,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
     if (guard && ctl->need_rebuild) return;
     if (SLAB) g.gpos_m = ctl->gpos_m;
-    constexpr bool kHot = (MDB_HOTFIRST != 0);  // two-ended inner list, hits evaluated in place
-    constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0) && !kHot;  // park hits in a queue, or evaluate them where they are found
+    constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0);  // park hits in a queue, or evaluate them where they are found
     __shared__ uint32_t queue[kPark ? kQueue : 1][kForceBlock];
     const StatePtrs s = ctl->st[ctl->cur];
     const double4 *__restrict__ pos = s.pos;
@@ -1028,14 +1019,6 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     if (n < 0) n = ctl->n_own;
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
     int max_in = 0;
-    // two-ended inner list (kHot, only while the inner list is walked): row of the k-th candidate
-    const bool two_ended = kHot && !refresh;
-    auto total_of = [&](int v) { return two_ended ? (v == 0x7fffffff ? v : (v & 0xffff)) : v; };
-    auto row_of = [&](int k, int v) {
-        if (!two_ended) return k;
-        const int tot = v & 0xffff, hot = (v >> 16) & 0x7fff;
-        return k + ((k >= hot) ? (kcap - tot) : 0);
-    };
     // prologue: first tile's operands
     // grid-strided tiles: CTAs that run at the same time work on adjacent tiles, so one SM's gathers are another's L2
     // hits (a contiguous range of tiles per CTA measured 24% slower)
@@ -1052,14 +1035,13 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         pi_n = pos[i];
         cnt_n = nnbr[i];
 #pragma unroll
-        for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)((two_ended && cnt_n != 0x7fffffff) ? max(0, min(row_of(u, cnt_n), kcap - 1)) : u) * stride + i];  // rows < kUnroll always exist
+        for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)u * stride + i];  // rows < kUnroll always exist
     }
     for (; tile < tile_end; tile += tile_step) {
         i = tile * kForceBlock + threadIdx.x;
         bool active = i < n;
         const double4 pi = pi_n;
-        const int cnt_packed = cnt_n;
-        int cnt = total_of(cnt_n);
+        int cnt = cnt_n;
         uint32_t jj[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) jj[u] = jn[u];
@@ -1077,17 +1059,15 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 pi_n = pos[in];
                 cnt_n = nnbr[in];
 #pragma unroll
-                for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)((two_ended && cnt_n != 0x7fffffff) ? max(0, min(row_of(u, cnt_n), kcap - 1)) : u) * stride + in];
+                for (int u = 0; u < kUnroll; u++) jn[u] = nl[(int64_t)u * stride + in];
             }
         }
         // which list this particle walks: normally the grid-uniform choice; a particle whose inner list overflowed
         // keeps walking its outer list (exact either way)
         const uint32_t *__restrict__ mynl = nl;
         bool write_inner = refresh;
-        bool mapped = two_ended;
         if (active && !refresh && cnt > kcap) {
             mynl = lv.nl;
-            mapped = false;
             cnt = lv.nnbr[i];
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) jj[u] = mynl[(int64_t)u * stride + i];
@@ -1097,7 +1077,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         }
         if (!active) cnt = 0;
         double F[3] = {0.0, 0.0, 0.0};
-        int nq = 0, nin = 0, nhot = 0;
+        int nq = 0, nin = 0;
         // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
         bool wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
         if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
@@ -1128,7 +1108,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
             if (k0 + kUnroll < cnt) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++)
-                    jj[u] = (k0 + kUnroll + u < cnt) ? mynl[(int64_t)(mapped ? row_of(k0 + kUnroll + u, cnt_packed) : k0 + kUnroll + u) * stride + i] : (uint32_t)i;
+                    jj[u] = (k0 + kUnroll + u < cnt) ? mynl[(int64_t)(k0 + kUnroll + u) * stride + i] : (uint32_t)i;
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
@@ -1136,13 +1116,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                 double d2 = wrap ? separation_wrap<DIM, TRI ? 1 : 0>(g, pi, pj[u], dx, dy, dz) : separation_plain<DIM>(pi, pj[u], dx, dy, dz);
                 const bool valid = k0 + u < cnt;
                 if (write_inner && valid && d2 <= lv.rin2) {
-                    if (kHot) {
-                        const bool hot = d2 <= lv.rhot2;
-                        const int row = hot ? nhot : lv.kmax_in - 1 - (nin - nhot);
-                        if (nin < lv.kmax_in) lv.nl_in[(int64_t)row * stride + i] = jc[u];
-                        nhot += hot ? 1 : 0;
-                    } else if (nin < lv.kmax_in)
-                        lv.nl_in[(int64_t)nin * stride + i] = jc[u];
+                    if (nin < lv.kmax_in) lv.nl_in[(int64_t)nin * stride + i] = jc[u];
                     nin++;
                 }
                 if (valid && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
@@ -1158,7 +1132,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
             while (__any_sync(0xffffffffu, nq > 0)) drain_one();
         }
         if (write_inner && i < n) {
-            lv.nnbr_in[i] = active ? (kHot ? (nin | (nhot << 16)) : nin) : 0x7fffffff;  // outer-overflow particles never use the inner list
+            lv.nnbr_in[i] = active ? nin : 0x7fffffff;  // outer-overflow particles never use the inner list
             max_in = max(max_in, active ? nin : 0);
         }
         if (active) {
@@ -1188,6 +1162,248 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     }
     cta_epilogue(acc, out, blockIdx.x);
 }
+
+// ------------------------------------------------------------------------------------------------
+// K4 (TMA operands): k_force_list with the tile's OWN operands -- its 128 particle records, list counts and the first
+// index rows, all contiguous in slot order -- brought into shared memory by TMA bulk copies (cp.async.bulk + mbarrier,
+// SASS UBLKCP) two tiles ahead, through a three-stage ring filled by one elected thread.
+//   ncu on k_force_list (profiles/r02_force_kernel_ncu.md): besides the gathers themselves (29 % of all warp-stall
+//   samples), 9 % sit on STL instructions -- the compiler spills the next tile's prefetched operands, and a spill of a
+//   value that is still in flight waits for the load -- and 5 % on the first uses of those operands at the top of a
+//   tile.  Here the next tiles' operands never occupy registers: the copy engine writes them to shared memory, a thread
+//   reads its own element when the tile starts (one mbarrier wait per tile, normally long satisfied) and hands the
+//   stage back at once.  The neighbour gathers stay direct LDG.256s (staging scattered records cost more LSU wavefronts
+//   than it saved, k_force_list_staged below; staging whole neighbour rows costs as much as the whole kernel,
+//   tools/stage_probe.cu).  Arithmetic, candidate order and reduction order are those of k_force_list: bit-identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 3;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tMDBW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MDBD_%=;\n\tbra MDBW_%=;\n\tMDBD_%=:\n\t}" ::"r"(
+            smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"((unsigned long long)__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ double4 lds_rec(const double4 *p)
+{
+    double4 r;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%4];\n\tld.shared.v2.f64 {%2,%3}, [%4+16];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "r"(a) : "memory");
+    return r;
+}
+
+template <int DIM, class Pot, int KICK2, bool SLAB>
+__global__ void __launch_bounds__(kForceBlock, MDB_FORCE_MIN_CTAS)
+k_force_list_tma(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt,
+             ForceOut out, int guard)
+{
+    // guard: launched speculatively behind the rebuild decision (slab steps); a pending rebuild turns the launch into a no-op
+    if (guard && ctl->need_rebuild) return;
+    if (SLAB) g.gpos_m = ctl->gpos_m;
+    constexpr bool kPark = Pot::kSparseHits && (MDB_PARK != 0);  // park hits in a queue, or evaluate them where they are found
+    constexpr bool TRI = false;  // (general cells keep k_force_list)
+    constexpr int NS = kTmaStages;
+    __shared__ __align__(128) double4 s_pos[NS][kForceBlock];
+    __shared__ __align__(128) int32_t s_cnt[NS][kForceBlock];
+    __shared__ __align__(128) uint32_t s_idx[NS][kUnroll][kForceBlock];
+    __shared__ __align__(8) unsigned long long bar_full[NS], bar_empty[NS];
+    __shared__ uint32_t queue[kPark ? kQueue : 1][kForceBlock];
+    const StatePtrs s = ctl->st[ctl->cur];
+    const double4 *__restrict__ pos = s.pos;
+    double4 *__restrict__ pos_next = ctl->st[ctl->cur ^ 1].pos;  // KICK2 == 2 only
+    double vmax2 = 0.0, dref2 = 0.0;
+    const unsigned long long rng_step = ctl->rng_step;  // KICK2 == 3 only
+    const bool refresh = ctl->inner_refresh != 0;  // uniform over the grid
+    const uint32_t *__restrict__ nl = refresh ? lv.nl : lv.nl_in;
+    const int32_t *__restrict__ nnbr = refresh ? lv.nnbr : lv.nnbr_in;
+    const int kcap = refresh ? lv.kmax : lv.kmax_in;
+    const int64_t stride = lv.stride;
+    ThreadSums acc;
+    if (n < 0) n = ctl->n_own;
+    const int ntiles = (n + kForceBlock - 1) / kForceBlock;
+    int max_in = 0;
+    // operand ring: the elected thread posts the bulk copies of tile k+2 while tile k is evaluated
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < NS; q++) {
+            mbar_init(&bar_full[q], 1);
+            mbar_init(&bar_empty[q], kForceBlock / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int tile_end = ntiles;
+    const int tile_step = gridDim.x;
+    const int64_t cap = s.cap;
+    auto post = [&](int t, int st) {  // elected thread: own records, list counts and the first kUnroll index rows of tile t
+        const int base = t * kForceBlock;
+        const uint32_t lim = (uint32_t)min((int64_t)kForceBlock, cap - base);  // a multiple of 32 (cap is)
+        mbar_expect_tx(&bar_full[st], lim * (uint32_t)(sizeof(double4) + 4 + 4 * kUnroll));
+        bulk_g2s(&s_pos[st][0], pos + base, lim * (uint32_t)sizeof(double4), &bar_full[st]);
+        bulk_g2s(&s_cnt[st][0], nnbr + base, lim * 4u, &bar_full[st]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) bulk_g2s(&s_idx[st][u][0], nl + (int64_t)u * stride + base, lim * 4u, &bar_full[st]);
+    };
+    int tile = blockIdx.x;
+    int i = tile * kForceBlock + tid;
+    if (tid == 0) {
+        if (tile < tile_end) post(tile, 0);
+        if (tile + tile_step < tile_end) post(tile + tile_step, 1);
+    }
+    int kt = 0;  // ordinal of this CTA's tile
+    for (; tile < tile_end; tile += tile_step, kt++) {
+        i = tile * kForceBlock + tid;
+        bool active = i < n;
+        const int st = kt % NS;
+        if (tid == 0 && tile + 2 * tile_step < tile_end) {
+            const int st2 = (kt + 2) % NS;
+            if (kt + 2 >= NS) mbar_wait(&bar_empty[st2], (uint32_t)(((kt + 2) / NS - 1) & 1));  // every warp has let go of that stage
+            post(tile + 2 * tile_step, st2);
+        }
+        mbar_wait(&bar_full[st], (uint32_t)((kt / NS) & 1));
+        double4 pi = make_double4(0, 0, 0, 1);
+        int cnt = 0;
+        uint32_t jj[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) jj[u] = 0;
+        if (active) {
+            pi = lds_rec(&s_pos[st][tid]);
+            cnt = s_cnt[st][tid];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) jj[u] = s_idx[st][u][tid];
+        }
+        // the operands are in registers: hand the stage back (one arrival per warp)
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&bar_empty[st]);
+        // this tile's velocities (needed only by the epilogue) and the next tile's operands: in flight during the gathers
+        double vel[3] = {0.0, 0.0, 0.0};
+        if ((KICK2 == 1 || KICK2 == 2) && active) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) vel[k] = s.vel[k * s.cap + i];
+        }
+        // which list this particle walks: normally the grid-uniform choice; a particle whose inner list overflowed
+        // keeps walking its outer list (exact either way)
+        const uint32_t *__restrict__ mynl = nl;
+        bool write_inner = refresh;
+        if (active && !refresh && cnt > kcap) {
+            mynl = lv.nl;
+            cnt = lv.nnbr[i];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) jj[u] = mynl[(int64_t)u * stride + i];
+        }
+        if (active && cnt > lv.kmax) {  // outer list overflow: handled in full by k_force_overflow
+            active = false;
+        }
+        if (!active) cnt = 0;
+        double F[3] = {0.0, 0.0, 0.0};
+        int nq = 0, nin = 0;
+        // a listed neighbour can sit across a periodic face only if this particle is within rwrap of one
+        bool wrap = pi.x < rwrap || pi.x > g.L[0] - rwrap || pi.y < rwrap || pi.y > g.L[1] - rwrap;
+        if (DIM == 3) wrap = wrap || pi.z < rwrap || pi.z > g.L[2] - rwrap;
+        if (TRI) wrap = true;  // general cells: every listed pair goes through the fractional nearest image
+        const bool wrap_any = __any_sync(0xffffffffu, wrap);  // warp-uniform: the wrapped separation is exact for every pair
+        auto drain_one = [&]() {
+            if (nq > 0) {
+                int j = (int)queue[--nq][tid];
+                double4 pj = ldg_pos(SLAB ? nbr_ptr(g, pos, (uint32_t)j) : pos + j);
+                double dx, dy, dz, d2;
+                if (wrap_any) d2 = separation_wrap<DIM, TRI ? 1 : 0>(g, pi, pj, dx, dy, dz);
+                else d2 = separation_plain<DIM>(pi, pj, dx, dy, dz);
+                pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
+            }
+        };
+        for (int k0 = 0; k0 < cnt; k0 += kUnroll) {
+            double4 pj[kUnroll];
+            uint32_t jc[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                // slots past the end of this particle's list issue no load at all: the kernel is bound by L1 wavefronts
+                // (ncu: 74% of the LSU data pipe), and a dummy gather costs a sector per lane like a real one
+                jc[u] = jj[u];
+                pj[u] = make_double4(0.0, 0.0, 0.0, 1.0);
+                if (k0 + u < cnt) pj[u] = ldg_pos(SLAB ? nbr_ptr(g, pos, jc[u]) : pos + jc[u]);
+            }
+            // next index chunk travels while the gathers above are in flight
+            if (k0 + kUnroll < cnt) {
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++)
+                    jj[u] = (k0 + kUnroll + u < cnt) ? mynl[(int64_t)(k0 + kUnroll + u) * stride + i] : (uint32_t)i;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                double dx, dy, dz;
+                double d2 = wrap ? separation_wrap<DIM, TRI ? 1 : 0>(g, pi, pj[u], dx, dy, dz) : separation_plain<DIM>(pi, pj[u], dx, dy, dz);
+                const bool valid = k0 + u < cnt;
+                if (write_inner && valid && d2 <= lv.rin2) {
+                    if (nin < lv.kmax_in) lv.nl_in[(int64_t)nin * stride + i] = jc[u];
+                    nin++;
+                }
+                if (valid && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
+                    if (kPark) queue[nq++][tid] = jc[u];
+                    else pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj[u].w, F, acc.e, acc.w, acc.np);
+                }
+            }
+            if (kPark && nq > kQueue - kUnroll) {
+                while (nq > 0) drain_one();
+            }
+        }
+        if (kPark) {
+            while (__any_sync(0xffffffffu, nq > 0)) drain_one();
+        }
+        if (write_inner && i < n) {
+            lv.nnbr_in[i] = active ? nin : 0x7fffffff;  // outer-overflow particles never use the inner list
+            max_in = max(max_in, active ? nin : 0);
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) s.frc[k * s.cap + i] = F[k];
+            if (KICK2 == 1) {
+                double v2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; k++) {
+                    double v = vel[k];
+                    v += (F[k] * dt) * 0.5;
+                    s.vel[k * s.cap + i] = v;
+                    v2 = (k == 0) ? v * v : v2 + v * v;
+                }
+                acc.v2 += v2;
+            }
+            if (KICK2 == 2) leap_epilogue<DIM, TRI ? 1 : 0>(i, F, vel, pi, s, pos_next, g, dt, acc.v2, vmax2);
+            if (KICK2 == 3) brown_epilogue<DIM, TRI ? 1 : 0>(i, F, pi, s, pos_next, g, dt, ctl, rng_step, vmax2, dref2);
+        }
+    }
+    if (KICK2 == 2) leap_report<kForceBlock>(vmax2, dt, ctl);
+    if (KICK2 == 3) brown_report<kForceBlock>(vmax2, dref2, ctl);
+    if (refresh) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) max_in = max(max_in, __shfl_xor_sync(0xffffffffu, max_in, o));
+        if ((tid & 31) == 0 && max_in > 0) atomicMax(&ctl->max_nnbr_in, max_in);
+    }
+    cta_epilogue(acc, out, blockIdx.x);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // K4 (staged): the list-driven pair-force kernel with the NEIGHBOUR RECORDS STAGED IN SHARED MEMORY by asynchronous
@@ -1221,14 +1437,6 @@ __device__ __forceinline__ void cp_async_rec(double4 *smem_dst, const double4 *g
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ double4 lds_rec(const double4 *p)
-{
-    double4 r;
-    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%4];\n\tld.shared.v2.f64 {%2,%3}, [%4+16];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "r"(a) : "memory");
-    return r;
-}
-
 template <int DIM, class Pot, int KICK2, bool SLAB>
 __global__ void __launch_bounds__(kForceBlock, MDB_STAGED_MIN_CTAS)
 k_force_list_staged(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff2, double rwrap, Pot pot, PotParams pp, double dt,

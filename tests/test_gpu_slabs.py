@@ -325,3 +325,26 @@ def test_slab_frames_one_lammps_file_per_rank(md, orc, tr, tmp_path):
     got = np.array([rows[i] for i in range(n)])
     assert np.max(np.abs(got - fr0)) < 2e-6      # "%lf" keeps six decimals
     ring.close()
+
+
+@pytest.mark.parametrize("ensemble", ["nve", "nvt"])
+def test_peer_graph_batching_is_bit_identical(md, orc, monkeypatch, ensemble):
+    """MDB200_GRAPH_BATCH = B captures B consecutive slab steps (each with its own conditional rebuild node) into one
+    graph; any split of a run into batched launches, single steps and the fused run's plain last step gives the same bits"""
+    cfg, x, v, f, img = _cfg(md)
+    n = x.shape[0]
+    out = []
+    for batch in ("1", "4", "7"):
+        monkeypatch.setenv("MDB200_GRAPH_BATCH", batch)
+        ring = md.SlabRing.local(3, 3, n, cfg["box"], 1.5, 0, seed=31, slab_transport=2)
+        ring.upload(x, cfg["diam"], velocities=v, forces=f, images=img)
+        rows = []
+        for k in (1, 3, 64, 29):
+            rows.append(ring.run_nve(k, 1e-3) if ensemble == "nve" else ring.run_nvt(k, 1e-3, 1.4737, 0.1))
+        out.append((np.concatenate(rows), ring.download(), [s["rebuilds"] for s in ring.stats()]))
+        ring.close()
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0]) and out[0][2] == o[2]
+        for a, b in zip(out[0][1], o[1]):
+            assert np.array_equal(a, b)
+    assert min(out[0][2]) >= 2
