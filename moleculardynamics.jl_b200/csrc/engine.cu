@@ -80,6 +80,9 @@ struct mdb_engine_s {
     int64_t nl_stride = 0;
     double *part = nullptr;
     double *xref = nullptr;   // unwrapped positions at the last list build (exact displacement test, Brownian)
+    float4 *posf = nullptr;   // single-precision shadow of the re-sorted positions (k_build_list_f32), written by k_gather
+    bool build_f32 = false;   // list membership tested in FP32 against a padded radius (superset list)
+    float rl2f = 0.0f;
     uint32_t *ovf = nullptr;  // overflow particle list (MDB_MODE_LIST)
     int nsm = 148;
     int64_t alloc_ncell = -1, alloc_cap = -1;
@@ -226,8 +229,9 @@ static void free_state(Engine *e)
     }
     cudaFree(e->cell_of); cudaFree(e->slot_of); cudaFree(e->counts); cudaFree(e->start); cudaFree(e->order); cudaFree(e->tile_sums);
     cudaFree(e->nl); cudaFree(e->nnbr); cudaFree(e->ovf); cudaFree(e->nl_in); cudaFree(e->nnbr_in);
-    cudaFree(e->small_nl); cudaFree(e->small_nnbr); cudaFree(e->small_part); cudaFree(e->xref);
+    cudaFree(e->small_nl); cudaFree(e->small_nnbr); cudaFree(e->small_part); cudaFree(e->xref); cudaFree(e->posf);
     e->xref = nullptr;
+    e->posf = nullptr;
     e->small_part = nullptr;
     e->ovf = nullptr; e->nl_in = nullptr; e->nnbr_in = nullptr; e->small_nl = nullptr; e->small_nnbr = nullptr;
     e->small_nl_words = 0;
@@ -378,6 +382,17 @@ static int plan_neighbors(Engine *e)
         int ki = (int)std::ceil(expect_in * 1.6) + 6;
         ki = (ki + 3) & ~3;
         e->kmax_in = std::max(e->kmax_in, std::min(e->kmax, std::max(8, ki)));
+    }
+    // Verlet-list membership in single precision (k_build_list_f32): allowed while the worst-case rounding error of the
+    // float copies is small against the skin (the list is then a superset with a few extra candidates at its rim)
+    e->build_f32 = false;
+    if (e->mode == MDB_MODE_LIST && !e->brute && !e->tri && getenv("MDB200_BUILD_F64") == nullptr) {
+        const double Lmax = std::max(e->L[0], std::max(e->L[1], d == 3 ? e->L[2] : 0.0));
+        const double eps = 4.0 * Lmax * 5.9604644775390625e-08, rl = e->r_grid;
+        if (std::sqrt(3.0) * eps <= 0.02 * e->skin) {
+            e->build_f32 = true;
+            e->rl2f = (float)((rl * rl + 2.0 * std::sqrt(3.0) * rl * eps + 3.0 * eps * eps) * (1.0 + 1e-5));
+        }
     }
     // tiny systems: the step loop runs inside one persistent CTA (K0-small); the structures above still serve
     // mdb_compute_forces / mdb_count_pairs / mdb_fire_minimize
@@ -542,6 +557,7 @@ static int alloc_state(Engine *e, int64_t n)
     CU(cudaMalloc(&e->nnbr, sizeof(int32_t) * e->cap));
     CU(cudaMalloc(&e->ovf, sizeof(uint32_t) * e->cap));
     CU(cudaMalloc(&e->xref, sizeof(double) * 3 * e->cap));
+    CU(cudaMalloc(&e->posf, sizeof(float4) * e->cap));
     CU(cudaMalloc(&e->nnbr_in, sizeof(int32_t) * e->cap));
     CU(cudaMalloc(&e->small_nnbr, sizeof(int32_t) * e->cap));
     return MDB_OK;
@@ -563,13 +579,16 @@ static void enqueue_rebuild(Engine *e)
         k_scan_apply<<<e->ntiles, kStreamBlock, 0, s>>>(e->ncell, e->counts, e->tile_sums, e->start);
         k_fill<<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->ctl, e->cell_of, e->slot_of, e->start, e->order);
         k_cellsort<<<nblk(e->ncell, kStreamBlock), kStreamBlock, 0, s>>>(e->ncell, e->start, e->order, 0, e->ctl);
-        k_gather<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->order, e->ctl, nullptr);
+        k_gather<DIM><<<nblk(n, kStreamBlock), kStreamBlock, 0, s>>>(n, e->order, e->ctl, nullptr, e->build_f32 ? e->posf : nullptr);
         k_flip<<<1, 1, 0, s>>>(e->ctl, nullptr);
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
             if (e->tri)
                 k_build_list<DIM, true><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
                                                                                    e->nnbr, e->ovf, e->ctl, nullptr);
+            else if (e->build_f32)
+                k_build_list_f32<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, e->rl2f, e->posf, e->nl, e->nl_stride,
+                                                                                 e->kmax, e->nnbr, e->ovf, e->ctl, e->xref);
             else
                 k_build_list<DIM, false><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
                                                                                     e->nnbr, e->ovf, e->ctl, e->xref);
@@ -1236,7 +1255,7 @@ static int rebuild_part2(Group &G)
         PHASE(e, "fill");
         k_cellsort<<<nblk(e->ncell, kStreamBlock), kStreamBlock, 0, s>>>(e->ncell, e->start, e->order, 1, e->ctl);
         PHASE(e, "cellsort");
-        k_gather<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(-1, e->order, e->ctl, n_new);
+        k_gather<DIM><<<nblk(e->cap_own, kStreamBlock), kStreamBlock, 0, s>>>(-1, e->order, e->ctl, n_new, e->build_f32 ? e->posf : nullptr);
         PHASE(e, "gather");
         k_flip<<<1, 1, 0, s>>>(e->ctl, n_new);
         k_slab_rowcounts<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, s>>>(e->nrows, e->nxo, e->start, e->row_cnt[0], e->row_cnt[1]);
@@ -1276,8 +1295,12 @@ static int rebuild_part3(Group &G)
         PHASE(e, "ghost cells");
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
-            k_build_list<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
-                                                                                  e->nnbr, e->ovf, e->ctl, nullptr);
+            if (e->build_f32)
+                k_build_list_f32<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, e->rl2f, e->posf, e->nl,
+                                                                                          e->nl_stride, e->kmax, e->nnbr, e->ovf, e->ctl, nullptr);
+            else
+                k_build_list<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
+                                                                                      e->nnbr, e->ovf, e->ctl, nullptr);
             e->stats.kernel_launches += 1;
             PHASE(e, "build list");
         }

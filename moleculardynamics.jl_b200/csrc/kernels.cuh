@@ -504,16 +504,19 @@ __global__ void k_cellsort(int64_t ncell, const uint32_t *__restrict__ start, ui
     }
 }
 
+// posf (optional): single-precision shadow of the re-sorted positions, read by k_build_list_f32
 template <int DIM>
 __global__ void k_gather(int64_t n, const uint32_t *__restrict__ order, const DevCtl *__restrict__ ctl,
-                         const uint32_t *__restrict__ n_new)
+                         const uint32_t *__restrict__ n_new, float4 *__restrict__ posf = nullptr)
 {
     if (n < 0) n = *n_new;  // slab mode: the owned count after migration = start[number of owned cells]
     const StatePtrs src = ctl->st[ctl->cur], dst = ctl->st[ctl->cur ^ 1];
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= n) return;
     uint32_t s = order[p];
-    dst.pos[p] = src.pos[s];
+    const double4 rec = src.pos[s];
+    dst.pos[p] = rec;
+    if (posf) posf[p] = make_float4((float)rec.x, (float)rec.y, (float)rec.z, (float)rec.w);
 #pragma unroll
     for (int k = 0; k < DIM; k++) {
         dst.vel[k * dst.cap + p] = src.vel[k * src.cap + s];
@@ -902,6 +905,119 @@ k_build_list(int n, Grid g, const uint32_t *__restrict__ start, double rlist2,
                                                    slot += hit ? stride : 0;
                                                    cnt += hit ? 1 : 0;
                                                });
+        nnbr[i] = cnt;
+        if (cnt > kmax) ovf[atomicAdd(&ctl->n_overflow, 1)] = (uint32_t)i;
+    }
+    int m = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&ctl->max_nnbr, m);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->list_valid = 1;
+        ctl->disp = 0.0;
+        ctl->dref2_bits = 0ull;
+    }
+}
+
+// K4b (single-precision membership): the Verlet list only has to be a SUPERSET of the pairs within r_list -- every decision
+// that matters (inner-list membership, cutoff, potential range) is re-taken in FP64 by the force kernel -- so the build may
+// test membership on single-precision copies of the positions against a radius padded by the worst-case rounding error
+// (rl2f = (r_list^2 + 2*sqrt(3)*r_list*eps + 3*eps^2)(1 + 1e-5), eps = 4 L 2^-24; the engine falls back to k_build_list when
+// the pad is not small against the skin).  Why: ncu shows k_build_list bound by L1 wavefronts -- at every iteration the 32
+// lanes of a warp load 32 different 32-byte records spread over ~10 cache lines; 16-byte float4 records halve the lines
+// (and the FP64 pipe drops out of the loop).  Same traversal order as k_build_list, so list order -- and with it the order
+// of every force sum -- is unchanged; the list may hold a few extra candidates within ~1e-4 of r_list.
+template <int DIM>
+__global__ void __launch_bounds__(kForceBlock)
+k_build_list_f32(int n, Grid g, const uint32_t *__restrict__ start, float rl2f, const float4 *__restrict__ posf,
+                 uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, uint32_t *__restrict__ ovf, DevCtl *ctl,
+                 double *__restrict__ xref)
+{
+    const StatePtrs st = ctl->st[ctl->cur];
+    if (g.slab) g.gpos_m = ctl->gpos_m;
+    if (n < 0) n = ctl->n_own;
+    const int i = blockIdx.x * kForceBlock + threadIdx.x;
+    int cnt = 0;
+    if (i < n) {
+        const double4 pd = st.pos[i];
+        if (xref) {
+            const double pk[3] = {pd.x, pd.y, pd.z};
+#pragma unroll
+            for (int k = 0; k < DIM; k++) xref[k * st.cap + i] = pk[k] + g.L[k] * (double)st.img[k * st.cap + i];
+        }
+        int cx, cy, cz;
+        cell_of_point<DIM, 0>(g, pd, cx, cy, cz);
+        const float xi = (float)pd.x, yi = (float)pd.y, zi = (float)pd.z;
+        const float Lx = (float)g.L[0], Ly = (float)g.L[1], Lz = (float)g.L[2];
+        uint32_t *slot = nl + i;
+        const int nx = g.nxo, ny = g.nc[1], nz = g.nc[2];
+        const int lx = cx - g.c0;
+        for (int dz = (DIM == 3 ? -1 : 0); dz <= (DIM == 3 ? 1 : 0); dz++) {
+            int oz = cz + dz, kz = 0;
+            if (DIM == 3) {
+                if (oz < 0) { oz += nz; kz = -1; }
+                else if (oz >= nz) { oz -= nz; kz = 1; }
+            }
+            for (int dy = -1; dy <= 1; dy++) {
+                int oy = cy + dy, ky = 0;
+                if (oy < 0) { oy += ny; ky = -1; }
+                else if (oy >= ny) { oy -= ny; ky = 1; }
+                const uint32_t rowg = (uint32_t)oz * ny + oy;
+                const uint32_t row = rowg * nx;
+                uint32_t seg_b[2], seg_e[2];
+                int seg_k[2], nseg = 1;
+                bool seg_ghost[2] = {false, false};
+                if (!g.slab) {
+                    if (lx == 0) {
+                        seg_b[0] = start[row]; seg_e[0] = start[row + 2]; seg_k[0] = 0;
+                        seg_b[1] = start[row + nx - 1]; seg_e[1] = start[row + nx]; seg_k[1] = -1;
+                        nseg = 2;
+                    } else if (lx == nx - 1) {
+                        seg_b[0] = start[row + nx - 2]; seg_e[0] = start[row + nx]; seg_k[0] = 0;
+                        seg_b[1] = start[row]; seg_e[1] = start[row + 1]; seg_k[1] = 1;
+                        nseg = 2;
+                    } else {
+                        seg_b[0] = start[row + lx - 1]; seg_e[0] = start[row + lx + 2]; seg_k[0] = 0;
+                    }
+                } else {
+                    const int lo = lx > 0 ? lx - 1 : 0, hi = lx < nx - 1 ? lx + 1 : nx - 1;
+                    seg_b[0] = start[row + lo]; seg_e[0] = start[row + hi + 1]; seg_k[0] = 0;
+                    if (lx == 0) {
+                        seg_b[1] = g.gstart_l[rowg]; seg_e[1] = g.gstart_l[rowg + 1]; seg_k[1] = g.kx_left; seg_ghost[1] = true;
+                        nseg = 2;
+                    } else if (lx == nx - 1) {
+                        seg_b[1] = g.gstart_r[rowg]; seg_e[1] = g.gstart_r[rowg + 1]; seg_k[1] = g.kx_right; seg_ghost[1] = true;
+                        nseg = 2;
+                    }
+                }
+                for (int sgi = 0; sgi < nseg; sgi++) {
+                    const uint32_t jb = seg_b[sgi], je = seg_e[sgi];
+                    // the shifted own position: (xi - sx) - xj; the same two roundings whichever of the pair does the test
+                    const float sx = (float)seg_k[sgi] * Lx, sy = (float)ky * Ly, sz = (float)kz * Lz;
+                    const bool ghost = seg_ghost[sgi];
+                    for (uint32_t j = jb; j < je; j++) {
+                        float xj, yj, zj;
+                        if (!ghost) {
+                            const float4 pj = __ldg(&posf[j]);
+                            xj = pj.x; yj = pj.y; zj = pj.z;
+                        } else {  // ghost records live in the mailbox as FP64
+                            const double4 pj = ldg_pos(&g.gpos_m[j]);
+                            xj = (float)pj.x; yj = (float)pj.y; zj = (float)pj.z;
+                        }
+                        const float dx = (xi - xj) - sx, dy_ = (yi - yj) - sy;
+                        float d2 = dx * dx + dy_ * dy_;
+                        if (DIM == 3) {
+                            const float dz_ = (zi - zj) - sz;
+                            d2 += dz_ * dz_;
+                        }
+                        const bool hit = d2 <= rl2f && (int)j != i;
+                        if (hit && cnt < kmax) *slot = j;
+                        slot += hit ? stride : 0;
+                        cnt += hit ? 1 : 0;
+                    }
+                }
+            }
+        }
         nnbr[i] = cnt;
         if (cnt > kmax) ovf[atomicAdd(&ctl->n_overflow, 1)] = (uint32_t)i;
     }

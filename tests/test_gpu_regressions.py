@@ -125,3 +125,39 @@ def test_lammps_writer_survives_huge_coordinates(md, tmp_path):
     assert len(atoms) == n
     assert len(atoms[1].split()) == 9 and float(atoms[1].split()[2]) == 1e300 and float(atoms[2].split()[6]) == -1.7e308
     e.close()
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_f32_list_build_is_a_superset_with_identical_results(md, monkeypatch, dim):
+    """the Verlet list is built from single-precision copies of the positions against a padded radius (k_build_list_f32):
+    a superset of the FP64 list in the same order, so every force sum, thermo row and rebuild decision keeps its bits
+    (MDB200_BUILD_F64=1 restores the FP64 build)"""
+    from mdjl_b200 import workloads
+    if dim == 3:
+        n = 32768
+        cfg = workloads.phs_fluid(n)
+        tag, pp, dt, kt = md._capi.POT_PSEUDOHS, (), 1e-3, 1.4737
+    else:
+        n = 4900
+        cfg = workloads.poly2d(n)
+        tag, pp, dt, kt = md._capi.POT_POLY, (1.25, 0.2), 1e-3, 0.11
+    v0 = workloads.velocities(n, dim, kt)
+    out = []
+    for f64 in (True, False):
+        if f64:
+            monkeypatch.setenv("MDB200_BUILD_F64", "1")
+        else:
+            monkeypatch.delenv("MDB200_BUILD_F64", raising=False)
+        e = md.Engine(dim, n, cfg["box"], 1.5, tag, pp, seed=6, mode=md._capi.MODE_LIST)
+        e.upload(cfg["x"], cfg["diam"], velocities=v0)
+        if dim == 2:
+            e.fire_minimize(max_steps=200, tol=1e-3, dt_initial=1e-4, dt_max=5e-3)
+            e.set_velocities(v0)
+        t = np.vstack([e.run_nvt(150, dt, kt, 100 * dt), e.run_nve(150, dt)])
+        out.append((t, e.download(), e.stats()))
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    assert out[0][2]["rebuilds"] == out[1][2]["rebuilds"] >= 3
+    assert 0 <= out[1][2]["max_neighbors"] - out[0][2]["max_neighbors"] <= 2
