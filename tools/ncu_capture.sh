@@ -11,5 +11,13 @@ $B > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpur
 ncu --set full --clock-control none --import-source on -k regex:k_force_list -s 303 -c 6 -o /tmp/${tag} $B > gpurun_out/${tag}_ncu.log 2>&1
 ncu -i /tmp/${tag}.ncu-rep --page raw --csv > gpurun_out/${tag}_raw.csv 2>/dev/null
 ncu -i /tmp/${tag}.ncu-rep --page source --csv --launch-skip 0 --launch-count 1 > gpurun_out/${tag}_source.csv 2>/dev/null
+# identity of the build the capture belongs to (bench.py refuses ncu numbers of another build)
+python - > gpurun_out/${tag}_build.json <<'PY'
+import json, sys
+sys.path.insert(0, ".")
+import mdjl_b200 as md
+e = md.Engine(3, 4096, 20.0, 1.5, 0)
+print(json.dumps(e.force_kernel_info()))
+PY
 ls -la /tmp/${tag}.ncu-rep gpurun_out/${tag}_raw.csv gpurun_out/${tag}_source.csv
 rm -f /tmp/${tag}.ncu-rep
