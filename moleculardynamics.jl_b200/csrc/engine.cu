@@ -27,8 +27,11 @@
 using namespace mdb;
 
 #define MDB_EXPORT extern "C" __attribute__((visibility("default")))
+#ifndef MDB_DEFAULT_BUILD_WC
+#define MDB_DEFAULT_BUILD_WC 0  // warp-cooperative list build (k_build_list_wc): off until measured
+#endif
 #ifndef MDB_DEFAULT_GRAPH_BATCH
-#define MDB_DEFAULT_GRAPH_BATCH 1  // steps per launch of the captured peer-memory slab step
+#define MDB_DEFAULT_GRAPH_BATCH 8  // steps per launch of the captured peer-memory slab step (2 GPUs, 2^21 particles per rank: 0.2427 -> 0.2360 ms/step)
 #endif
 #ifndef MDB_DEFAULT_FORCE_VARIANT
 #define MDB_DEFAULT_FORCE_VARIANT 0  // see kernels.cuh "K4 (staged)" and profiles/r02_force_ab.md
@@ -82,6 +85,7 @@ struct mdb_engine_s {
     double *xref = nullptr;   // unwrapped positions at the last list build (exact displacement test, Brownian)
     float4 *posf = nullptr;   // single-precision shadow of the re-sorted positions (k_build_list_f32), written by k_gather
     bool build_f32 = false;   // list membership tested in FP32 against a padded radius (superset list)
+    bool build_wc = false;    // ... with the candidates of a warp staged once per neighbour row (k_build_list_wc; MDB200_BUILD_WC)
     float rl2f = 0.0f;
     uint32_t *ovf = nullptr;  // overflow particle list (MDB_MODE_LIST)
     int nsm = 148;
@@ -391,6 +395,10 @@ static int plan_neighbors(Engine *e)
         const double eps = 4.0 * Lmax * 5.9604644775390625e-08, rl = e->r_grid;
         if (std::sqrt(3.0) * eps <= 0.02 * e->skin) {
             e->build_f32 = true;
+            {
+                const char *wc = getenv("MDB200_BUILD_WC");
+                e->build_wc = wc ? atoi(wc) != 0 : (MDB_DEFAULT_BUILD_WC != 0);
+            }
             e->rl2f = (float)((rl * rl + 2.0 * std::sqrt(3.0) * rl * eps + 3.0 * eps * eps) * (1.0 + 1e-5));
         }
     }
@@ -586,6 +594,9 @@ static void enqueue_rebuild(Engine *e)
             if (e->tri)
                 k_build_list<DIM, true><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, rl2, e->nl, e->nl_stride, e->kmax,
                                                                                    e->nnbr, e->ovf, e->ctl, nullptr);
+            else if (e->build_f32 && e->build_wc)
+                k_build_list_wc<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, e->rl2f, e->posf, e->nl, e->nl_stride,
+                                                                                e->kmax, e->nnbr, e->ovf, e->ctl, e->xref);
             else if (e->build_f32)
                 k_build_list_f32<DIM><<<nblk(n, kForceBlock), kForceBlock, 0, s>>>(n, e->grid, e->start, e->rl2f, e->posf, e->nl, e->nl_stride,
                                                                                  e->kmax, e->nnbr, e->ovf, e->ctl, e->xref);
@@ -841,63 +852,58 @@ static void enqueue_step_tail(Engine *e, int ensemble, double dt, double tau, do
 static int step_fixed_kernels(const Engine *e, int ensemble) { return 3 + force_kernel_count(e) + (ensemble == MDB_BROWNIAN ? 0 : 0); }
 
 template <int DIM>
-static int build_one_graph(Engine *e, const GraphKey &key, int kind, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out);
+static int build_one_graph(Engine *e, const GraphKey &key, int kind, int batch, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out);
 template <int DIM>
 static int build_graph(Engine *e, const GraphKey &key)
 {
     drop_graph(e);
     int rc;
-    if (key.fused && key.ensemble == MDB_BROWNIAN) {
-        if ((rc = build_one_graph<DIM>(e, key, kStepBrownFused, &e->graph, &e->gexec))) return rc;
-    } else if (key.fused) {
-        if ((rc = build_one_graph<DIM>(e, key, kStepFused, &e->graph, &e->gexec))) return rc;
-        if ((rc = build_one_graph<DIM>(e, key, kStepLast, &e->graph_last, &e->gexec_last))) return rc;
-    } else if ((rc = build_one_graph<DIM>(e, key, kStepFull, &e->graph, &e->gexec)))
-        return rc;
+    // graph_batch > 1: that many consecutive steps as ONE graph (each with its own conditional rebuild node); the single-step
+    // graph serves the remainder of a run, gexec_last the plain last step of a fused NVE run
+    const int kind = (key.fused && key.ensemble == MDB_BROWNIAN) ? kStepBrownFused : (key.fused ? kStepFused : kStepFull);
+    if (e->graph_batch > 1 && (rc = build_one_graph<DIM>(e, key, kind, e->graph_batch, &e->graph_b, &e->gexec_b))) return rc;
+    if ((rc = build_one_graph<DIM>(e, key, kind, 1, &e->graph, &e->gexec))) return rc;
+    if (kind == kStepFused && (rc = build_one_graph<DIM>(e, key, kStepLast, 1, &e->graph_last, &e->gexec_last))) return rc;
     e->gkey = key;
     return MDB_OK;
 }
 template <int DIM>
-static int build_one_graph(Engine *e, const GraphKey &key, int kind, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out)
+static int build_one_graph(Engine *e, const GraphKey &key, int kind, int batch, cudaGraph_t *graph_out, cudaGraphExec_t *exec_out)
 {
     cudaStream_t s = e->stream;
     cudaGraph_t &graph = *graph_out;
     CU(cudaGraphCreate(&graph, 0));
     const bool conditional = (e->mode == MDB_MODE_LIST) && !e->brute;
-    cudaGraphConditionalHandle handle = 0;
-    if (conditional) CU(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
-    // head
     CU(cudaStreamBeginCaptureToGraph(s, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    enqueue_step_head<DIM>(e, key.ensemble, key.dt, handle, conditional ? 1 : 0, false, kind);
-    std::vector<cudaGraphNode_t> deps;
-    if (conditional) {
-        cudaStreamCaptureStatus status;
-        const cudaGraphNode_t *d = nullptr;
-        size_t nd = 0;
-        CU(cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &d, &nd));
-        deps.assign(d, d + nd);
-        cudaGraph_t g2 = nullptr;
-        CU(cudaStreamEndCapture(s, &g2));
-        cudaGraphNodeParams cp = {};
-        cp.type = cudaGraphNodeTypeConditional;
-        cp.conditional.handle = handle;
-        cp.conditional.type = cudaGraphCondTypeIf;
-        cp.conditional.size = 1;
-        cudaGraphNode_t cnode;
-        CU(cudaGraphAddNode(&cnode, graph, deps.data(), deps.size(), &cp));
-        cudaGraph_t body = cp.conditional.phGraph_out[0];
-        CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-        enqueue_rebuild<DIM>(e);
-        CU(cudaStreamEndCapture(s, &g2));
-        CU(cudaStreamBeginCaptureToGraph(s, graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t g2 = nullptr;
+    for (int step = 0; step < batch; step++) {
+        cudaGraphConditionalHandle handle = 0;
+        if (conditional) CU(cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault));
+        enqueue_step_head<DIM>(e, key.ensemble, key.dt, handle, conditional ? 1 : 0, false, kind);
+        if (conditional) {
+            cudaStreamCaptureStatus status;
+            const cudaGraphNode_t *d = nullptr;
+            size_t nd = 0;
+            CU(cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &d, &nd));
+            std::vector<cudaGraphNode_t> deps(d, d + nd);
+            CU(cudaStreamEndCapture(s, &g2));
+            cudaGraphNodeParams cp = {};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = handle;
+            cp.conditional.type = cudaGraphCondTypeIf;
+            cp.conditional.size = 1;
+            cudaGraphNode_t cnode;
+            CU(cudaGraphAddNode(&cnode, graph, deps.data(), deps.size(), &cp));
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            enqueue_rebuild<DIM>(e);
+            CU(cudaStreamEndCapture(s, &g2));
+            CU(cudaStreamBeginCaptureToGraph(s, graph, &cnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+        } else
+            enqueue_rebuild<DIM>(e);
         enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo, false, kind);
-        CU(cudaStreamEndCapture(s, &g2));
-    } else {
-        enqueue_rebuild<DIM>(e);
-        enqueue_step_tail<DIM>(e, key.ensemble, key.dt, key.tau, key.ktemp, key.thermo, false, kind);
-        cudaGraph_t g2 = nullptr;
-        CU(cudaStreamEndCapture(s, &g2));
     }
+    CU(cudaStreamEndCapture(s, &g2));
     CU(cudaGraphInstantiate(exec_out, graph, 0));
     return MDB_OK;
 }
@@ -1295,7 +1301,10 @@ static int rebuild_part3(Group &G)
         PHASE(e, "ghost cells");
         if (e->mode == MDB_MODE_LIST) {
             double rl2 = e->r_grid * e->r_grid;
-            if (e->build_f32)
+            if (e->build_f32 && e->build_wc)
+                k_build_list_wc<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, e->rl2f, e->posf, e->nl,
+                                                                                         e->nl_stride, e->kmax, e->nnbr, e->ovf, e->ctl, nullptr);
+            else if (e->build_f32)
                 k_build_list_f32<DIM><<<nblk(e->cap_own, kForceBlock), kForceBlock, 0, s>>>(-1, e->grid, e->start, e->rl2f, e->posf, e->nl,
                                                                                           e->nl_stride, e->kmax, e->nnbr, e->ovf, e->ctl, nullptr);
             else
@@ -1978,7 +1987,7 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
         if (ensemble == MDB_NVT)
             CU(cudaMemcpyAsync(e->d_ktemp, ktemp_per_step + done, sizeof(double) * m, cudaMemcpyHostToDevice, s));
         CU(cudaMemsetAsync(&e->ctl->step, 0, sizeof(unsigned long long), s));
-        for (int64_t q = 0; q < m; q++) {
+        for (int64_t q = 0; q < m;) {
             // fused NVE schedule: the run's only stand-alone kick-drift, then fused steps, then a plain last step
             int kind = kStepFull;
             if (fused && ensemble == MDB_BROWNIAN) kind = kStepBrownFused;
@@ -1990,7 +1999,15 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
                 }
             }
             if (e->cfg.use_graph) {
-                CU(cudaGraphLaunch(kind == kStepLast ? e->gexec_last : e->gexec, s));
+                // steps of this chunk that run the regular step (everything but the plain last step of a fused NVE run)
+                const int64_t regular_left = std::min(m, (fused && ensemble != MDB_BROWNIAN) ? (nsteps - 1 - done) : m) - q;
+                if (e->gexec_b && regular_left >= e->graph_batch) {
+                    CU(cudaGraphLaunch(e->gexec_b, s));
+                    q += e->graph_batch;
+                } else {
+                    CU(cudaGraphLaunch(kind == kStepLast ? e->gexec_last : e->gexec, s));
+                    q += 1;
+                }
             } else {
                 // eager mode doubles as the profiling mode: CUDA events around each kernel group, one sync per step
                 enqueue_step_head<DIM>(e, ensemble, dt, 0, 0, true, kind);
@@ -2015,6 +2032,7 @@ static int run_impl(Engine *e, int ensemble, int64_t nsteps, double dt, const do
                     e->stats.prof_rebuild_ms += t;
                 }
                 e->stats.prof_steps += 1;
+                q += 1;
             }
         }
         if (thermo) CU(cudaMemcpyAsync(thermo + 4 * done, e->d_thermo, sizeof(double) * 4 * m, cudaMemcpyDeviceToHost, s));

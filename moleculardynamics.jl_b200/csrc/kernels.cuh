@@ -1032,6 +1032,157 @@ k_build_list_f32(int n, Grid g, const uint32_t *__restrict__ start, float rl2f, 
     }
 }
 
+// K4b (warp-cooperative): k_build_list_f32 with the candidates of a warp staged ONCE per neighbour row.  The 32 particles of a
+// warp are consecutive slots, i.e. ~20 consecutive cells of one x-row; for each of the 9 neighbour rows their candidate
+// ranges overlap almost entirely (union ~34 records), yet k_build_list_f32 loads them lane by lane, 42 scattered 16-byte
+// loads per lane.  Here the warp loads the union window with one or two coalesced loads into its shared-memory buffer and
+// every lane walks its own [jb, je) out of shared memory.  Lanes of a warp that straddles two x-rows, periodic wrap
+// segments, ghost segments and windows larger than the buffer take the per-lane path of k_build_list_f32.  Same
+// traversal order, same tests: the list is identical to k_build_list_f32's.
+constexpr int kWcWindow = 96;
+template <int DIM>
+__global__ void __launch_bounds__(kForceBlock)
+k_build_list_wc(int n, Grid g, const uint32_t *__restrict__ start, float rl2f, const float4 *__restrict__ posf,
+                uint32_t *__restrict__ nl, int64_t stride, int kmax, int32_t *__restrict__ nnbr, uint32_t *__restrict__ ovf, DevCtl *ctl,
+                double *__restrict__ xref)
+{
+    __shared__ float4 win[kForceBlock / 32][kWcWindow];
+    const StatePtrs st = ctl->st[ctl->cur];
+    if (g.slab) g.gpos_m = ctl->gpos_m;
+    if (n < 0) n = ctl->n_own;
+    const int i = blockIdx.x * kForceBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool active = i < n;
+    int cnt = 0;
+    double4 pd = make_double4(0, 0, 0, 1);
+    int cx = 0, cy = 0, cz = 0;
+    if (active) {
+        pd = st.pos[i];
+        if (xref) {
+            const double pk[3] = {pd.x, pd.y, pd.z};
+#pragma unroll
+            for (int k = 0; k < DIM; k++) xref[k * st.cap + i] = pk[k] + g.L[k] * (double)st.img[k * st.cap + i];
+        }
+        cell_of_point<DIM, 0>(g, pd, cx, cy, cz);
+    }
+    const float xi = (float)pd.x, yi = (float)pd.y, zi = (float)pd.z;
+    const float Lx = (float)g.L[0], Ly = (float)g.L[1], Lz = (float)g.L[2];
+    uint32_t *slot = nl + i;
+    const int nx = g.nxo, ny = g.nc[1], nz = g.nc[2];
+    const int lx = cx - g.c0;
+    // the cooperative path needs every active lane in the same x-row (same cy, cz)
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    const int leader = act ? (__ffs(act) - 1) : 0;
+    const int cy0 = __shfl_sync(0xffffffffu, cy, leader), cz0 = __shfl_sync(0xffffffffu, cz, leader);
+    const bool same_row = __all_sync(0xffffffffu, !active || (cy == cy0 && cz == cz0));
+    auto test = [&](float xj, float yj, float zj, float sx, float sy, float sz, uint32_t j) {
+        const float dx = (xi - xj) - sx, dy_ = (yi - yj) - sy;
+        float d2 = dx * dx + dy_ * dy_;
+        if (DIM == 3) {
+            const float dz_ = (zi - zj) - sz;
+            d2 += dz_ * dz_;
+        }
+        const bool hit = d2 <= rl2f && (int)j != i;
+        if (hit && cnt < kmax) *slot = j;
+        slot += hit ? stride : 0;
+        cnt += hit ? 1 : 0;
+    };
+    for (int dz = (DIM == 3 ? -1 : 0); dz <= (DIM == 3 ? 1 : 0); dz++) {
+        int oz = cz + dz, kz = 0;
+        if (DIM == 3) {
+            if (oz < 0) { oz += nz; kz = -1; }
+            else if (oz >= nz) { oz -= nz; kz = 1; }
+        }
+        for (int dy = -1; dy <= 1; dy++) {
+            int oy = cy + dy, ky = 0;
+            if (oy < 0) { oy += ny; ky = -1; }
+            else if (oy >= ny) { oy -= ny; ky = 1; }
+            const uint32_t rowg = (uint32_t)oz * ny + oy;
+            const uint32_t row = rowg * nx;
+            uint32_t seg_b[2] = {0, 0}, seg_e[2] = {0, 0};
+            int seg_k[2] = {0, 0}, nseg = 0;
+            bool seg_ghost[2] = {false, false};
+            if (active) {
+                nseg = 1;
+                if (!g.slab) {
+                    if (lx == 0) {
+                        seg_b[0] = start[row]; seg_e[0] = start[row + 2]; seg_k[0] = 0;
+                        seg_b[1] = start[row + nx - 1]; seg_e[1] = start[row + nx]; seg_k[1] = -1;
+                        nseg = 2;
+                    } else if (lx == nx - 1) {
+                        seg_b[0] = start[row + nx - 2]; seg_e[0] = start[row + nx]; seg_k[0] = 0;
+                        seg_b[1] = start[row]; seg_e[1] = start[row + 1]; seg_k[1] = 1;
+                        nseg = 2;
+                    } else {
+                        seg_b[0] = start[row + lx - 1]; seg_e[0] = start[row + lx + 2]; seg_k[0] = 0;
+                    }
+                } else {
+                    const int lo = lx > 0 ? lx - 1 : 0, hi = lx < nx - 1 ? lx + 1 : nx - 1;
+                    seg_b[0] = start[row + lo]; seg_e[0] = start[row + hi + 1]; seg_k[0] = 0;
+                    if (lx == 0) {
+                        seg_b[1] = g.gstart_l[rowg]; seg_e[1] = g.gstart_l[rowg + 1]; seg_k[1] = g.kx_left; seg_ghost[1] = true;
+                        nseg = 2;
+                    } else if (lx == nx - 1) {
+                        seg_b[1] = g.gstart_r[rowg]; seg_e[1] = g.gstart_r[rowg + 1]; seg_k[1] = g.kx_right; seg_ghost[1] = true;
+                        nseg = 2;
+                    }
+                }
+            }
+            const float sy = (float)ky * Ly, sz = (float)kz * Lz;
+            // main segment (always unshifted in x): the warp's union window, staged once
+            uint32_t wb = active ? seg_b[0] : 0xffffffffu, we = active ? seg_e[0] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                wb = min(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+                we = max(we, __shfl_xor_sync(0xffffffffu, we, o));
+            }
+            const bool coop = same_row && we > wb && (we - wb) <= (uint32_t)kWcWindow;  // warp-uniform
+            if (coop) {
+                for (uint32_t q = wb + lane; q < we; q += 32) win[wid][q - wb] = __ldg(&posf[q]);
+                __syncwarp();
+                for (uint32_t j = seg_b[0]; j < seg_e[0]; j++) {
+                    const float4 pj = win[wid][j - wb];
+                    test(pj.x, pj.y, pj.z, 0.0f, sy, sz, j);
+                }
+                __syncwarp();
+            } else {
+                for (uint32_t j = seg_b[0]; j < seg_e[0]; j++) {
+                    const float4 pj = __ldg(&posf[j]);
+                    test(pj.x, pj.y, pj.z, 0.0f, sy, sz, j);
+                }
+            }
+            // second segment: periodic wrap piece or ghost column, per lane
+            if (nseg == 2) {
+                const float sx = (float)seg_k[1] * Lx;
+                for (uint32_t j = seg_b[1]; j < seg_e[1]; j++) {
+                    float xj, yj, zj;
+                    if (!seg_ghost[1]) {
+                        const float4 pj = __ldg(&posf[j]);
+                        xj = pj.x; yj = pj.y; zj = pj.z;
+                    } else {
+                        const double4 pj = ldg_pos(&g.gpos_m[j]);
+                        xj = (float)pj.x; yj = (float)pj.y; zj = (float)pj.z;
+                    }
+                    test(xj, yj, zj, sx, sy, sz, j);
+                }
+            }
+        }
+    }
+    if (active) {
+        nnbr[i] = cnt;
+        if (cnt > kmax) ovf[atomicAdd(&ctl->n_overflow, 1)] = (uint32_t)i;
+    }
+    int m = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0) atomicMax(&ctl->max_nnbr, m);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->list_valid = 1;
+        ctl->disp = 0.0;
+        ctl->dref2_bits = 0ull;
+    }
+}
+
 // minimum image of a listed pair: positions are re-wrapped every step, so the image is decided per evaluation,
 // dx = (xi - xj) - k*L with k = +-1 when |xi - xj| > L/2 (the oracle's nearbyint gives the same k for listed pairs)
 template <int DIM, int TRI = -1>
