@@ -301,7 +301,10 @@ static int plan_neighbors(Engine *e)
         if (!(e->r_search < 0.5 * e->L[k]))
             return fail(e, MDB_ERR_BOX_TOO_SMALL, "search radius must be < L/2 (half the perpendicular width of the cell) in every periodic direction");
     double rho = (double)e->N / e->volume;
-    double skin = e->cfg.skin > 0 ? e->cfg.skin : 0.25 * e->r_search;
+    // default skin: 0.3 r_search.  N = 2^24 PseudoHS, 200 NVE steps (profiles/r02_skin_sweep_and_nvt_breakdown.log):
+    // skin 0.20 / 0.255 / 0.32 / 0.40 -> 1.291 / 1.276 / 1.249 / 1.254 ms per step (15 / 12 / 9 / 7 rebuilds); the cheaper
+    // single-precision list build of round 2 moved the optimum up from round 1's 0.25 r_search
+    double skin = e->cfg.skin > 0 ? e->cfg.skin : 0.3 * e->r_search;
     auto cells_for = [&](double r, int nc[3]) {
         bool ok = true;
         nc[0] = nc[1] = nc[2] = 1;
