@@ -499,8 +499,15 @@ static int alloc_slab(Engine *e)
     double per_col = (double)e->N / std::max(1, e->grid.nc[0]);
     // a boundary column holds per_col particles (relative fluctuation ~ per_col^-1/2); leavers per rebuild are the
     // particles within skin/2 of a face, about 0.1 per_col.  Messages always travel at full capacity.
-    e->mig_cap = (int)std::max(2048.0, 0.3 * per_col + 1024.0);
-    e->ghost_cap = (int)std::max(2048.0, 1.3 * per_col + 1024.0);
+    // A LATTICE start is the hard case: a cell column of width w holds floor or ceil of w/a lattice planes, so a boundary
+    // column can hold up to ceil(w/a)/(w/a) times the mean (two planes where the mean is 1.28: 1.56x; the round-2 bench
+    // start overflowed a 1.3x buffer the moment the default skin moved the grid from 208 to 200 columns).  The peer-memory
+    // transport only moves the rows that exist, so generous capacities cost memory (tens of MB), not time.
+    double gf = 2.0, mf = 0.5;
+    if (const char *t = getenv("MDB200_GHOST_FACTOR")) gf = std::max(1.0, atof(t));
+    if (const char *t = getenv("MDB200_MIGRATION_FACTOR")) mf = std::max(0.05, atof(t));
+    e->mig_cap = (int)std::max(2048.0, mf * per_col + 1024.0);
+    e->ghost_cap = (int)std::max(2048.0, gf * per_col + 1024.0);
     size_t nr = (size_t)e->nrows + 1;
     // the mailbox (slab.cuh): header with the flags and reduction slots, ghost columns [2 parity][2 side], migration
     // records [2 side].  Every transport receives into it (the classic ones use parity 0 only); its layout depends on

@@ -180,6 +180,7 @@ struct DevCtl {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -1286,6 +1287,10 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
     if (n < 0) n = ctl->n_own;
     const int ntiles = (n + kForceBlock - 1) / kForceBlock;
     int max_in = 0;
+    // this thread's column of the parked-hit queue as a shared-window address, computed once: ncu's source view showed seven
+    // address instructions (S2R tid, S2UR cta id, ULEA, LEA, IMAD ...) in front of every queue access, ~7 % of all instructions
+    const uint32_t qaddr = smem_u32(&queue[0][threadIdx.x]);
+    constexpr uint32_t kQRow = kForceBlock * (uint32_t)sizeof(uint32_t);
     // prologue: first tile's operands
     // grid-strided tiles: CTAs that run at the same time work on adjacent tiles, so one SM's gathers are another's L2
     // hits (a contiguous range of tiles per CTA measured 24% slower)
@@ -1352,15 +1357,19 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
         const bool wrap_any = __any_sync(0xffffffffu, wrap);  // warp-uniform: the wrapped separation is exact for every pair
         auto drain_one = [&]() {
             if (nq > 0) {
-                int j = (int)queue[--nq][threadIdx.x];
-                double4 pj = ldg_pos(SLAB ? nbr_ptr(g, pos, (uint32_t)j) : pos + j);
+                uint32_t j;
+                --nq;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(j) : "r"(qaddr + (uint32_t)nq * kQRow) : "memory");
+                double4 pj = ldg_pos(SLAB ? nbr_ptr(g, pos, j) : pos + j);
                 double dx, dy, dz, d2;
                 if (wrap_any) d2 = separation_wrap<DIM, TRI ? 1 : 0>(g, pi, pj, dx, dy, dz);
                 else d2 = separation_plain<DIM>(pi, pj, dx, dy, dz);
                 pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, acc.e, acc.w, acc.np);
             }
         };
-        for (int k0 = 0; k0 < cnt; k0 += kUnroll) {
+        // row k0 + kUnroll of this particle's list column: a running pointer instead of a 64-bit multiply per index load
+        const uint32_t *__restrict__ prow = mynl + (int64_t)kUnroll * stride + i;
+        for (int k0 = 0; k0 < cnt; k0 += kUnroll, prow += (int64_t)kUnroll * stride) {
             double4 pj[kUnroll];
             uint32_t jc[kUnroll];
 #pragma unroll
@@ -1375,7 +1384,7 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
             if (k0 + kUnroll < cnt) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++)
-                    jj[u] = (k0 + kUnroll + u < cnt) ? mynl[(int64_t)(k0 + kUnroll + u) * stride + i] : (uint32_t)i;
+                    jj[u] = (k0 + kUnroll + u < cnt) ? prow[(int64_t)u * stride] : (uint32_t)i;
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
@@ -1387,8 +1396,11 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
                     nin++;
                 }
                 if (valid && d2 <= cutoff2 && pot.may_interact(pp, d2, pi.w, pj[u].w)) {
-                    if (kPark) queue[nq++][threadIdx.x] = jc[u];
-                    else pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj[u].w, F, acc.e, acc.w, acc.np);
+                    if (kPark) {
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qaddr + (uint32_t)nq * kQRow), "r"(jc[u]) : "memory");
+                        nq++;
+                    } else
+                        pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj[u].w, F, acc.e, acc.w, acc.np);
                 }
             }
             if (kPark && nq > kQueue - kUnroll) {
@@ -1444,7 +1456,6 @@ k_force_list(int n, DevCtl *__restrict__ ctl, Grid g, ListView lv, double cutoff
 //   tools/stage_probe.cu).  Arithmetic, candidate order and reduction order are those of k_force_list: bit-identical.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTmaStages = 3;
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -348,3 +348,29 @@ def test_peer_graph_batching_is_bit_identical(md, orc, monkeypatch, ensemble):
         for a, b in zip(out[0][1], o[1]):
             assert np.array_equal(a, b)
     assert min(out[0][2]) >= 2
+
+
+def test_lattice_start_fits_the_ghost_buffers(md, tr):
+    """a lattice start puts whole lattice planes into single cell columns: a boundary column can hold ceil(w/a) planes where
+    the mean is w/a (here 2 vs 1.33), which overflowed ghost buffers sized at 1.3x the mean column (round-2 finding: the
+    N = 2^24 bench start failed on 2 GPUs the moment the default skin moved the grid)"""
+    from mdjl_b200 import slabs
+    m, a = 64, 1.0367
+    n, L = m ** 3, m * a
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) * a
+    rng = np.random.default_rng(3)
+    x = (g + 0.5 + rng.uniform(-0.015, 0.015, g.shape)) % L     # offset: two whole planes inside the boundary column at x ~ 16-17
+    box = np.array([L, L, L])
+    ring = md.SlabRing.local(4, 3, n, box, 1.5, 0, seed=1, slab_transport=tr)
+    ring.upload(x, np.ones(n), velocities=rng.normal(0, 1.2, (n, 3)))
+    st = ring.lead.stats()
+    pl = slabs.plan(box, 3, st["r_search"], 0.3 * st["r_search"], 4)   # the engine's own grid (default skin)
+    assert pl["nc"][0] == st["ncell"][0]
+    col = slabs.column_of(x[:, 0], pl)
+    pop = np.bincount(col, minlength=pl["nc"][0])
+    boundary = sorted({c for lo, hi in pl["columns"] for c in (lo, hi - 1)})
+    assert pop[boundary].max() > 1.3 * n / pl["nc"][0] + 1024      # the case that used to overflow is really present
+    E, W, npairs = ring.compute_forces()
+    t = ring.run_nve(30, 1e-3)
+    assert np.all(np.isfinite(t)) and sum(s["n_owned"] for s in ring.stats()) == n
+    ring.close()
