@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -195,6 +196,11 @@ static inline int force_grid(const Engine *e) { return std::max(1, std::min(nblk
 static inline int stream_grid(const Engine *e) { return std::max(1, std::min(nblk(grid_particles(e), kStreamBlock), e->nsm * e->stream_cta_per_sm)); }
 static inline int kick_grid(const Engine *e) { return std::max(1, std::min(nblk(grid_particles(e), kStreamBlock), e->nsm * e->kick_cta_per_sm)); }
 constexpr int kOverflowGrid = 8;
+
+// the alternative list-mode force kernels (variants 1 and 2) are instantiated for the headline potential
+// only: they are A/B partners, not the default, and every instantiation costs build time
+template <class Pot>
+static constexpr bool has_force_variants() { return std::is_same<Pot, PotPHS>::value; }
 
 template <class F>
 static bool dispatch_pot(int tag, F &&f)
@@ -677,13 +683,15 @@ static void enqueue_force(Engine *e, double dt)
             if (e->tri)
                 k_force_list<DIM, Pot, KICK2, false, true><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
                                                                                      e->r_grid + e->skin, pot, e->pp, dt, out, 0);
-            else if (e->force_variant == 1)
-                k_force_list_staged<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
-                                                                                      e->r_grid + e->skin, pot, e->pp, dt, out, 0);
-            else if (e->force_variant == 2)
-                k_force_list_tma<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
-                                                                                   e->r_grid + e->skin, pot, e->pp, dt, out, 0);
-            else
+            else if (has_force_variants<Pot>() && e->force_variant == 1) {
+                if constexpr (has_force_variants<Pot>())
+                    k_force_list_staged<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                          e->r_grid + e->skin, pot, e->pp, dt, out, 0);
+            } else if (has_force_variants<Pot>() && e->force_variant == 2) {
+                if constexpr (has_force_variants<Pot>())
+                    k_force_list_tma<DIM, Pot, KICK2, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                       e->r_grid + e->skin, pot, e->pp, dt, out, 0);
+            } else
                 k_force_list<DIM, Pot, KICK2, false, false><<<blocks, kForceBlock, 0, s>>>(n, e->ctl, e->grid, list_view(e), e->cutoff2,
                                                                                       e->r_grid + e->skin, pot, e->pp, dt, out, 0);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,
@@ -711,35 +719,22 @@ static void query_occupancy(Engine *e)
         if (e->brute) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_force_brute<DIM, Pot, true>, kForceBlock, 0);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_force_brute<DIM, Pot, false>, kForceBlock, 0);
-        } else if (e->mode == MDB_MODE_LIST && e->force_variant == 2 && !e->tri) {
-            // TMA-operand kernel: the operand ring's shared memory counts
+        } else if (e->mode == MDB_MODE_LIST && has_force_variants<Pot>() && (e->force_variant == 1 || e->force_variant == 2) && !e->tri) {
+            // alternative kernels: their shared memory (staging slots / operand ring) bounds the residency
             int q[4] = {0, 0, 0, 0};
-            if (e->slab) {
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_tma<DIM, Pot, 0, true>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_tma<DIM, Pot, 1, true>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_tma<DIM, Pot, 2, true>, kForceBlock, 0);
-                q[3] = q[2];
-            } else {
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_tma<DIM, Pot, 0, false>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_tma<DIM, Pot, 1, false>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_tma<DIM, Pot, 2, false>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[3], k_force_list_tma<DIM, Pot, 3, false>, kForceBlock, 0);
-            }
-            a = std::min(std::min(q[0], q[1]), std::min(q[2], q[3]));
-            b = a;
-        } else if (e->mode == MDB_MODE_LIST && e->force_variant == 1 && !e->tri) {
-            // the staged kernel: its shared-memory slots bound the residency
-            int q[4] = {0, 0, 0, 0};
-            if (e->slab) {
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_staged<DIM, Pot, 0, true>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_staged<DIM, Pot, 1, true>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_staged<DIM, Pot, 2, true>, kForceBlock, 0);
-                q[3] = q[2];
-            } else {
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[0], k_force_list_staged<DIM, Pot, 0, false>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[1], k_force_list_staged<DIM, Pot, 1, false>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[2], k_force_list_staged<DIM, Pot, 2, false>, kForceBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q[3], k_force_list_staged<DIM, Pot, 3, false>, kForceBlock, 0);
+            if constexpr (has_force_variants<Pot>()) {
+                auto occ = [&](auto kern) {
+                    int v = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, kForceBlock, 0);
+                    return v;
+                };
+                if (e->force_variant == 1) {
+                    if (e->slab) { q[0] = occ(k_force_list_staged<DIM, Pot, 0, true>); q[1] = occ(k_force_list_staged<DIM, Pot, 1, true>); q[2] = occ(k_force_list_staged<DIM, Pot, 2, true>); q[3] = q[2]; }
+                    else { q[0] = occ(k_force_list_staged<DIM, Pot, 0, false>); q[1] = occ(k_force_list_staged<DIM, Pot, 1, false>); q[2] = occ(k_force_list_staged<DIM, Pot, 2, false>); q[3] = occ(k_force_list_staged<DIM, Pot, 3, false>); }
+                } else {
+                    if (e->slab) { q[0] = occ(k_force_list_tma<DIM, Pot, 0, true>); q[1] = occ(k_force_list_tma<DIM, Pot, 1, true>); q[2] = occ(k_force_list_tma<DIM, Pot, 2, true>); q[3] = q[2]; }
+                    else { q[0] = occ(k_force_list_tma<DIM, Pot, 0, false>); q[1] = occ(k_force_list_tma<DIM, Pot, 1, false>); q[2] = occ(k_force_list_tma<DIM, Pot, 2, false>); q[3] = occ(k_force_list_tma<DIM, Pot, 3, false>); }
+                }
             }
             a = std::min(std::min(q[0], q[1]), std::min(q[2], q[3]));
             b = a;
@@ -1341,13 +1336,15 @@ static void enqueue_force_slab(Engine *e, double dt, int guard = 0)
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
         if (e->mode == MDB_MODE_LIST) {
-            if (e->force_variant == 1)
-                k_force_list_staged<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2,
-                                                                                     e->r_grid + e->skin, pot, e->pp, dt, out, guard);
-            else if (e->force_variant == 2)
-                k_force_list_tma<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2,
-                                                                                  e->r_grid + e->skin, pot, e->pp, dt, out, guard);
-            else
+            if (has_force_variants<Pot>() && e->force_variant == 1) {
+                if constexpr (has_force_variants<Pot>())
+                    k_force_list_staged<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                         e->r_grid + e->skin, pot, e->pp, dt, out, guard);
+            } else if (has_force_variants<Pot>() && e->force_variant == 2) {
+                if constexpr (has_force_variants<Pot>())
+                    k_force_list_tma<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2,
+                                                                                      e->r_grid + e->skin, pot, e->pp, dt, out, guard);
+            } else
             k_force_list<DIM, Pot, KICK2, true><<<blocks, kForceBlock, 0, s>>>(-1, e->ctl, e->grid, list_view(e), e->cutoff2, e->r_grid + e->skin,
                                                                        pot, e->pp, dt, out, guard);
             k_force_overflow<DIM, Pot, KICK2><<<kOverflowGrid, kForceBlock, 0, s>>>(e->ctl, e->grid, e->start, e->ovf, e->cutoff2, pot,

@@ -576,15 +576,22 @@ MDB_EXPORT int mdb_force_kernel_info(mdb_handle e, int32_t info[6])
     cudaFuncAttributes a;
     memset(&a, 0, sizeof(a));
     cudaError_t ce = cudaErrorInvalidValue;
-    const int var = e->tri ? 0 : e->force_variant;
+    int var = 0;
     dispatch_pot(e->cfg.potential, [&](auto pot) {
         typedef decltype(pot) Pot;
-        if (e->dim == 3)
-            ce = var == 1 ? cudaFuncGetAttributes(&a, k_force_list_staged<3, Pot, 2, false>)
-               : var == 2 ? cudaFuncGetAttributes(&a, k_force_list_tma<3, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<3, Pot, 2, false, false>);
-        else
-            ce = var == 1 ? cudaFuncGetAttributes(&a, k_force_list_staged<2, Pot, 2, false>)
-               : var == 2 ? cudaFuncGetAttributes(&a, k_force_list_tma<2, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list<2, Pot, 2, false, false>);
+        var = (e->tri || !has_force_variants<Pot>()) ? 0 : e->force_variant;
+        if constexpr (has_force_variants<Pot>()) {
+            if (var == 1) {
+                ce = e->dim == 3 ? cudaFuncGetAttributes(&a, k_force_list_staged<3, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list_staged<2, Pot, 2, false>);
+                return;
+            }
+            if (var == 2) {
+                ce = e->dim == 3 ? cudaFuncGetAttributes(&a, k_force_list_tma<3, Pot, 2, false>) : cudaFuncGetAttributes(&a, k_force_list_tma<2, Pot, 2, false>);
+                return;
+            }
+        }
+        var = 0;
+        ce = e->dim == 3 ? cudaFuncGetAttributes(&a, k_force_list<3, Pot, 2, false, false>) : cudaFuncGetAttributes(&a, k_force_list<2, Pot, 2, false, false>);
     });
     if (ce != cudaSuccess) return fail(e, MDB_ERR_CUDA, std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(ce));
     info[0] = a.numRegs;
