@@ -469,32 +469,50 @@ def main_slabs(args, rank, world, local_rank):
             return th, k
 
         ok, th, k_in, k_out, t_e2e = 1, None, 0, 0, 0.0
+        trips = []
         try:
             k_in = down(A)
             A["diam"][:k_in] = cfg["diam"][A["ids"][:k_in]]
             th, k_mid = round_trip(A, k_in, B)           # untimed warm-up of exactly the timed call (buffers, first touch)
             B["diam"][:k_mid] = cfg["diam"][B["ids"][:k_mid]]
-            sync()
-            t0 = time.perf_counter()
-            th, k_out = round_trip(B, k_mid, A)
-            torch.cuda.synchronize()
-            t_e2e = time.perf_counter() - t0
-            k_in = k_mid
         except Exception as exc:   # the bench line must still be printed; the end-to-end figure is then absent
             print("slab e2e failed on rank %d: %s" % (rank, exc), file=sys.stderr)
             ok = 0
+        # three timed round trips, each behind a barrier every rank reaches whatever happened before, MAX over ranks per
+        # trip, MEDIAN over the trips: one trip is a single shot of ~50 ms through shared host memory, and one late rank
+        # (a page fault, a descheduled process) shows as a 4x outlier in one trip out of a few
+        src, k_src, dst = B, (k_mid if ok else 0), A
+        for _ in range(3):
+            sync()
+            if not ok:
+                continue
+            try:
+                t0 = time.perf_counter()
+                th, k_dst = round_trip(src, k_src, dst)
+                torch.cuda.synchronize()
+                trips.append(time.perf_counter() - t0)
+                if os.environ.get("MDB200_BENCH_E2E_TRACE"):
+                    print("e2e trip rank %d: %.4f s %s" % (rank, trips[-1], {k: round(v, 4) for k, v in parts.items()}),
+                          file=sys.stderr)
+                k_in, k_out = k_src, k_dst
+                dst["diam"][:k_dst] = cfg["diam"][dst["ids"][:k_dst]]
+                src, k_src, dst = dst, k_dst, src
+            except Exception as exc:
+                print("slab e2e failed on rank %d: %s" % (rank, exc), file=sys.stderr)
+                ok = 0
+        # collectives only out here, where every rank arrives whatever happened above
         sync()
-        tt = torch.tensor([t_e2e, float(ok)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt[:1], op=dist.ReduceOp.MAX)
-        dist.all_reduce(tt[1:], op=dist.ReduceOp.MIN)
-        t_e2e = float(tt[0].item())
-        if tt[1].item() > 0.5:
+        tt = torch.tensor((trips + [0.0, 0.0, 0.0])[:3] + [-float(ok)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        trips = [float(v) for v in tt[:3].tolist()]
+        t_e2e = sorted(trips)[1]
+        if tt[3].item() < -0.5:
             e2e = {"value": n * args.steps / t_e2e, "unit": "particle-steps/s",
                    "h2d_bytes_per_step": k_in * (3 * 24 + 8 + 12 + 4) / args.steps,
                    "d2h_bytes_per_step": (k_out * (3 * 24 + 12 + 4) + th.nbytes) / args.steps, "seconds": t_e2e,
-                   "breakdown_s_rank0": parts,
+                   "breakdown_s_rank0": parts, "trips_s": trips,
                    "what": "per rank (max over ranks): mdb_upload_owned(own rows, pinned host) + %d steps + mdb_download_owned "
-                           "into pinned host buffers; one untimed warm-up round trip before" % args.steps}
+                           "into pinned host buffers; one untimed warm-up round trip, then the median of 3 timed ones" % args.steps}
 
     nf = 3 * (n - 1.0)
     E = t_thermo[:, 0] + t_thermo[:, 2]
@@ -681,14 +699,17 @@ def main():
             parts.update(upload_s=tb - ta, run_s=tc - tb, download_s=time.perf_counter() - tc)
             return th
         e2e_call()  # warm-up: allocations, graph capture
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        th = e2e_call()
-        t_e2e = time.perf_counter() - t0
+        trips = []
+        for _ in range(3):   # median of three round trips (a single shot through host memory is noisy)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            th = e2e_call()
+            trips.append(time.perf_counter() - t0)
+        t_e2e = sorted(trips)[1]
         h2d = sum(a[1].nbytes for a in (hx, hv, hf, hi, hd))
         d2h = sum(a[1].nbytes for a in (ox, ov, of_, oi)) + th.nbytes
         e2e = {"value": n * args.steps / t_e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e, "breakdown_s": parts,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": t_e2e, "breakdown_s": parts, "trips_s": trips,
                "what": "mdb_upload(pinned host) + mdb_run_%s(%d steps) + mdb_download + thermo rows" % (args.ensemble, args.steps)}
         e3.close()
 
