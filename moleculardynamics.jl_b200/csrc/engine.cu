@@ -163,7 +163,12 @@ struct mdb_engine_s {
     // ---- K0-small: persistent single-CTA step loop for n <= kSmallMaxN ------------------------------
     bool small = false;
     uint32_t *small_nl = nullptr;
+    double *small_rng = nullptr;   // cluster version of K0-small, NVT: the thermostat's draws of a chunk of steps
     size_t small_nl_words = 0;  // allocated size of small_nl (small_kmax * n can grow on a re-upload)
+    bool small_cluster_allowed = true;  // MDB200_SMALL_CLUSTER=0 keeps the cooperative-grid version (A/B, fallback)
+    int small_cluster = -1;     // K0-small as one thread-block cluster: -1 undecided, 0 no (cooperative grid), > 0 the cluster size in use
+    int small_block = 0;        // MDB200_SMALL_BLOCK: threads per CTA of the cluster version (0 = by particle count)
+    int small_lpp = 0;          // MDB200_SMALL_LPP: upper bound on the lanes per particle of the cluster version (0 = by particle count)
     int32_t *small_nnbr = nullptr;
     double *small_part = nullptr;
     int small_kmax = 0;
@@ -239,10 +244,11 @@ static void free_state(Engine *e)
     }
     cudaFree(e->cell_of); cudaFree(e->slot_of); cudaFree(e->counts); cudaFree(e->start); cudaFree(e->order); cudaFree(e->tile_sums);
     cudaFree(e->nl); cudaFree(e->nnbr); cudaFree(e->ovf); cudaFree(e->nl_in); cudaFree(e->nnbr_in);
-    cudaFree(e->small_nl); cudaFree(e->small_nnbr); cudaFree(e->small_part); cudaFree(e->xref); cudaFree(e->posf);
+    cudaFree(e->small_nl); cudaFree(e->small_nnbr); cudaFree(e->small_part); cudaFree(e->small_rng); cudaFree(e->xref); cudaFree(e->posf);
     e->xref = nullptr;
     e->posf = nullptr;
     e->small_part = nullptr;
+    e->small_rng = nullptr;
     e->ovf = nullptr; e->nl_in = nullptr; e->nnbr_in = nullptr; e->small_nl = nullptr; e->small_nnbr = nullptr;
     e->small_nl_words = 0;
     e->cell_of = e->slot_of = e->counts = e->start = e->order = e->tile_sums = nullptr;
@@ -417,6 +423,7 @@ static int plan_neighbors(Engine *e)
     // the graph-replayed multi-kernel step, so MDB_MODE_AUTO switches over at 2048 particles
     e->small = !e->slab && !e->tri && e->cfg.potential != MDB_POT_USER &&
                ((want == MDB_MODE_AUTO && e->N <= 2048) || (want == MDB_MODE_SMALL && e->N <= kSmallMaxN));
+    e->small_cluster = e->small_cluster_allowed ? -1 : 0;   // decided again at the next run (the particle count may have changed)
     if (e->small) {
         e->small_skin = std::max(e->cfg.skin > 0 ? e->cfg.skin : 0.0, 0.4 * e->r_search);
         double rl = e->r_search + e->small_skin;
@@ -1882,7 +1889,8 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
 {
     cudaStream_t s = e->stream;
     {
-        const size_t need = (size_t)e->small_kmax * (size_t)std::max(e->n, 1);
+        // the cluster version keeps one sub-list per lane of a particle: at most 8 lanes, at most 4096 threads
+        const size_t need = (size_t)e->small_kmax * (size_t)std::max(std::max(e->n, 1), std::min(8 * std::max(e->n, 1), 4096));
         if (!e->small_nl || e->small_nl_words < need) {
             cudaFree(e->small_nl);
             e->small_nl = nullptr;
@@ -1903,6 +1911,8 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
     a.nl = e->small_nl; a.kmax = e->small_kmax;
     if (!e->small_part) CU(cudaMalloc(&e->small_part, sizeof(double) * 3 * kSmallMaxGrid * 5));
     a.gpart = e->small_part;
+    if (!e->small_rng) CU(cudaMalloc(&e->small_rng, sizeof(double) * 2 * e->chunk));
+    a.rng_pre = e->small_rng;
     a.skin = e->small_skin;
     double rl = e->r_search + e->small_skin;
     const double rlist2 = rl * rl;
@@ -1922,11 +1932,51 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
         cudaError_t le = cudaSuccess;
         dispatch_pot(e->cfg.potential, [&](auto pot) {
             typedef decltype(pot) Pot;
-            auto kern = k_small_run<DIM, Pot>;
-            le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             DevCtl *ctl = e->ctl;
             Grid g = e->grid;
             PotParams pp = e->pp;
+            if (e->small_cluster != 0 && (e->n <= 2048 || e->small_lpp > 0)) {   // measured: 16 SMs lose to the 64-CTA grid at N = 4096
+                // one thread-block cluster: hardware cluster barriers, positions pushed through distributed shared memory,
+                // LPP lanes per particle (as many as fit 16 CTAs x 256 threads)
+                int lpp = e->n <= 512 ? 8 : (e->n <= 1024 ? 4 : (e->n <= 2048 ? 2 : 1));
+                if (e->small_lpp == 1 || e->small_lpp == 2 || e->small_lpp == 4 || e->small_lpp == 8) lpp = std::min(lpp, e->small_lpp);
+                const int threads = std::max(e->n, 1) * lpp;
+                int block = threads > 2048 ? 256 : (threads > 1024 ? 128 : 64);
+                if (e->small_block == 64 || e->small_block == 128 || e->small_block == 256) block = e->small_block;
+                int need = nblk(threads, block), csize = 1;
+                while (csize < need) csize <<= 1;
+                cudaLaunchConfig_t lc = {};
+                lc.gridDim = dim3(csize);
+                lc.blockDim = dim3(block);
+                lc.dynamicSmemBytes = smem;
+                lc.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at;
+                lc.numAttrs = 1;
+                auto go = [&](auto ck) {
+                    int fits = 0;
+                    if (e->small_cluster == csize) fits = 1;             // decided by an earlier launch on this handle
+                    else if (csize <= 16 &&
+                             cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                             cudaFuncSetAttribute(ck, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                             cudaOccupancyMaxActiveClusters(&fits, ck, &lc) == cudaSuccess && fits > 0)
+                        fits = 1;
+                    else fits = 0;
+                    (void)cudaGetLastError();
+                    if (!fits) return false;
+                    e->small_cluster = csize;
+                    le = cudaLaunchKernelEx(&lc, ck, ctl, g, a, pot, pp);
+                    return true;
+                };
+                bool launched = lpp == 8 ? go(k_small_cluster<DIM, Pot, 8>) : lpp == 4 ? go(k_small_cluster<DIM, Pot, 4>)
+                              : lpp == 2 ? go(k_small_cluster<DIM, Pot, 2>) : go(k_small_cluster<DIM, Pot, 1>);
+                if (launched) return;
+                e->small_cluster = 0;   // this device / size cannot host the cluster: cooperative grid from here on
+            }
+            auto kern = k_small_run<DIM, Pot>;
+            le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             void *args[] = {&ctl, &g, &a, &pot, &pp};
             // cooperative launch: all CTAs are co-resident (at most 64 CTAs of 64 threads) and meet at grid-wide barriers
             if (le == cudaSuccess)
@@ -2151,6 +2201,12 @@ MDB_EXPORT int mdb_create(const mdb_config *cfg, mdb_handle *out)
         e->force_variant = fv ? atoi(fv) : MDB_DEFAULT_FORCE_VARIANT;
         const char *gb = getenv("MDB200_GRAPH_BATCH");
         e->graph_batch = gb ? std::max(1, std::min(64, atoi(gb))) : MDB_DEFAULT_GRAPH_BATCH;
+        const char *sc = getenv("MDB200_SMALL_CLUSTER");
+        e->small_cluster_allowed = !(sc && atoi(sc) == 0);
+        const char *sb = getenv("MDB200_SMALL_BLOCK");
+        e->small_block = sb ? atoi(sb) : 0;
+        const char *sl = getenv("MDB200_SMALL_LPP");
+        e->small_lpp = sl ? atoi(sl) : 0;
     }
     memset(&e->stats, 0, sizeof(e->stats));
     memset(&e->grid, 0, sizeof(e->grid));

@@ -36,6 +36,7 @@ struct SmallArgs {
     unsigned long long seed;
     double *gpart;           // [3][kSmallMaxGrid][5] per-CTA partials: phase 0 = {vmax2}, phase 1 = {e, w, np, ke2, dmax2},
                              // phase 1 double-buffered by step parity (see the step loop)
+    double *rng_pre;         // cluster version, NVT: [nsteps][2] the thermostat's Gaussian and chi-square draws of every step
 };
 
 template <int DIM, class Pot>
@@ -285,6 +286,287 @@ k_small_run(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParams pp
         ctl->dmax2_bits = 0ull;
         ctl->disp = 0.0;
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K0-small, thread-block-cluster version: the same step loop with the CTAs of ONE cluster (<= 16 CTAs on the SMs of one GPC)
+// instead of a cooperative grid, and LPP lanes of a warp per particle.
+//   * the grid-wide barriers become hardware cluster barriers (barrier.cluster arrive/wait, ~0.2 us against ~2 us for a
+//     cooperative grid.sync through global memory);
+//   * nothing is staged from L2: the lanes of a particle PUSH its new position into the position table of every CTA of the
+//     cluster through distributed shared memory before the barrier, so after the barrier the neighbour gathers and the
+//     all-pairs list rebuild read local shared memory only;
+//   * a step of a small system is one dependent chain per thread (ncu: half of the step is the pair loop at ~14 iterations
+//     per warp, most of them entering the interaction branch for a few lanes).  The LPP lanes of a particle hold the same
+//     state (they repeat the cheap kick / drift / move arithmetic, bit for bit), split the candidates j = q, q + LPP, ...
+//     between them -- list rebuild and pair loop -- and add their partial forces with a fixed butterfly, so every lane of
+//     the group ends with the same force bits.  LPP = 1 is the cooperative kernel's arithmetic statement by statement;
+//   * reductions: the lanes of every warp push the warp's partial sums to every CTA; after the barrier every warp folds the
+//     per-warp partials itself in one fixed order (lane l takes warps l, l+32, ... in sequence, then a fixed butterfly) --
+//     deterministic for a given (block, LPP) shape, and no block-level barrier on the way;
+//   * Brownian steps take a second cluster barrier (cheap here) instead of ping-ponging the tables: "everyone has finished
+//     reading the positions" before the moved positions are pushed.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallMaxWarps = kSmallMaxN / 32;
+constexpr int kSmallClusterMaxBlock = 256;
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+template <int DIM, class Pot, int LPP>
+__global__ void __launch_bounds__(kSmallClusterMaxBlock, 1)
+k_small_cluster(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParams pp)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double4 spos[];                 // [n] positions of ALL particles, pushed by their owners
+    __shared__ double part0[kSmallMaxWarps];          // per-warp max |v|^2 (pushed by every warp of the cluster)
+    __shared__ double part1[kSmallMaxWarps][5];       // per-warp {e, w, np, ke2, dmax2}
+    const StatePtrs s = ctl->st[ctl->cur];
+    const int n = a.n, tid = threadIdx.x, lane = tid & 31;
+    const int C = (int)gridDim.x;                     // the grid is one cluster
+    const int t = blockIdx.x * blockDim.x + tid;      // thread number in the cluster
+    const int i = t / LPP, q = t % LPP;               // particle and the lane's place among the particle's lanes
+    const int gw = t >> 5, NW = (C * (int)blockDim.x) >> 5;
+    const bool active = i < n;
+    uint32_t *const nl = a.nl + ((size_t)(active ? i : 0) * LPP + q);   // [k][i][q]: a warp's entries of one k are contiguous
+    const size_t nl_stride = (size_t)n * LPP;
+
+    double x[3] = {0, 0, 0}, v[3] = {0, 0, 0}, f[3] = {0, 0, 0}, sig = 1.0;
+    int32_t im[3] = {0, 0, 0};
+    uint32_t pid = 0;
+    if (active) {
+        double4 p = s.pos[i];
+        x[0] = p.x; x[1] = p.y; x[2] = p.z; sig = p.w;
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            v[k] = s.vel[k * s.cap + i];
+            f[k] = s.frc[k * s.cap + i];
+            im[k] = s.img[k * s.cap + i];
+        }
+        pid = (uint32_t)s.id[i];
+    }
+    int cnt = 0;
+    double alpha = 1.0, disp = 0.0;
+    bool rebuild = true;          // the list of a previous call is never trusted
+    double dmax2_prev = 0.0;      // Brownian: displacement bound of the previous step's move (cluster-wide)
+    unsigned long long rng_step = ctl->rng_step;
+    const double sigma_bd = sqrt(2.0 * a.dt);
+
+    auto push_position = [&]() {
+        if (active) {
+            const double4 p = make_double4(x[0], x[1], x[2], sig);
+            for (int r = q; r < C; r += LPP) cluster.map_shared_rank(spos, r)[i] = p;   // the particle's lanes share the fan-out
+        }
+    };
+    push_position();              // Brownian dynamics evaluates forces before it moves anything
+    if (a.ensemble == 1) {
+        // the thermostat's random numbers depend on (seed, step) only: a serial chain of ~2.4 us per step when one thread
+        // draws them between the barriers -- here every thread of the cluster draws the pair of a few steps up front
+        const int T = C * (int)blockDim.x;
+        for (long long st = t; st < a.nsteps; st += T) {
+            ThermoRng rng;
+            rng.init(a.seed, rng_step + (unsigned long long)st);
+            double r1 = rng.normal();
+            double r2 = rng.sum_noises(a.nf - 1.0);
+            a.rng_pre[2 * st] = r1;
+            a.rng_pre[2 * st + 1] = r2;
+        }
+    }
+    cluster_sync_all();           // release / acquire at cluster scope: the table above is read through L2 below
+
+    for (long long step = 0; step < a.nsteps; step++) {
+        double dmax2;
+        double2 rr = make_double2(0.0, 0.0);
+        double kt_step = 0.0;
+        if (a.ensemble == 1) {   // needed after barrier B: on their way from L2 during the whole step
+            rr = __ldcg(reinterpret_cast<const double2 *>(a.rng_pre) + step);
+            kt_step = a.ktemp_per_step[step];
+        }
+        if (a.ensemble != 2) {
+            // ---- first half kick + drift + wrap (src/integrate.jl:8-21, src/boundary.jl:7-17); Bussi scale of the previous step
+            double v2 = 0.0;
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < DIM; k++) {
+                    double vk = v[k] * alpha;
+                    vk += (f[k] * a.dt) * 0.5;
+                    v[k] = vk;
+                    v2 = (k == 0) ? vk * vk : v2 + vk * vk;
+                    double xv = x[k] + vk * a.dt;
+                    double frac = g.invL[k] * xv;
+                    double ncr = floor(frac);
+                    if (ncr != 0.0) im[k] += (int32_t)ncr;
+                    x[k] = g.L[k] * (frac - ncr);
+                }
+            }
+            push_position();
+            v2 = warp_max(v2);
+            for (int r = lane; r < C; r += 32) cluster.map_shared_rank(part0, r)[gw] = v2;
+            cluster_sync_all();   // barrier A: new positions and the per-warp maxima are in every CTA's shared memory
+            dmax2 = 0.0;
+            for (int w = lane; w < NW; w += 32) dmax2 = fmax(dmax2, part0[w]);
+            dmax2 = warp_max(dmax2) * (a.dt * a.dt);
+        } else {
+            dmax2 = dmax2_prev;
+        }
+        {
+            double d = disp + sqrt(dmax2);
+            rebuild = rebuild || !(2.0 * d <= a.skin);
+            disp = rebuild ? 0.0 : d;
+        }
+        const double4 pi = make_double4(x[0], x[1], x[2], sig);
+        // ---- Verlet list rebuild: all pairs from shared memory, FP32 membership with margin (superset); lane q keeps the
+        // neighbours j = q (mod LPP) in ascending order
+        if (rebuild) {
+            if (active) {
+                const float xi = (float)pi.x, yi = (float)pi.y, zi = (float)pi.z;
+                const float Lx = (float)g.L[0], Ly = (float)g.L[1], Lz = (float)g.L[2];
+                const float hx = 0.5f * Lx, hy = 0.5f * Ly, hz = 0.5f * Lz;
+                cnt = 0;
+                for (int j = q; j < n; j += LPP) {
+                    const double4 pj = spos[j];
+                    float dx = xi - (float)pj.x, dy = yi - (float)pj.y;
+                    dx = dx > hx ? dx - Lx : (dx < -hx ? dx + Lx : dx);
+                    dy = dy > hy ? dy - Ly : (dy < -hy ? dy + Ly : dy);
+                    float d2 = dx * dx + dy * dy;
+                    if (DIM == 3) {
+                        float dz = zi - (float)pj.z;
+                        dz = dz > hz ? dz - Lz : (dz < -hz ? dz + Lz : dz);
+                        d2 += dz * dz;
+                    }
+                    if (d2 <= a.rlist2_f && j != i) {
+                        if (cnt < a.kmax) nl[(size_t)cnt * nl_stride] = (uint32_t)j;
+                        cnt++;
+                    }
+                }
+            }
+            if (t == 0) ctl->rebuilds += 1;
+            rebuild = false;
+        }
+        // ---- pair forces (src/pairwise.jl:26-39)
+        double e = 0.0, w = 0.0, np = 0.0, ke2 = 0.0, bd2 = 0.0;
+        double F[3] = {0.0, 0.0, 0.0};
+        if (active) {
+            auto candidate = [&](int j) {
+                const double4 pj = spos[j];
+                double dx, dy, dz;
+                double d2 = separation_wrap<DIM>(g, pi, pj, dx, dy, dz);
+                if (d2 <= a.cutoff2 && pot.may_interact(pp, d2, pi.w, pj.w)) pair_accumulate<DIM>(pot, pp, dx, dy, dz, d2, pi.w, pj.w, F, e, w, np);
+            };
+            if (cnt <= a.kmax) {
+                uint32_t jn = cnt > 0 ? nl[0] : 0u;
+                for (int k = 0; k < cnt; k++) {
+                    const uint32_t j = jn;
+                    if (k + 1 < cnt) jn = nl[(size_t)(k + 1) * nl_stride];   // the next index is on its way while this pair is evaluated
+                    candidate((int)j);
+                }
+            } else {
+                for (int j = q; j < n; j += LPP)
+                    if (j != i) candidate(j);  // list overflow: exact scan of this lane's share
+            }
+        }
+        if (LPP > 1) {
+            // the particle's lanes add their shares with a fixed butterfly: every lane ends with the same bits
+#pragma unroll
+            for (int o = LPP / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < DIM; k++) F[k] += __shfl_xor_sync(0xffffffffu, F[k], o);
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < DIM; k++) f[k] = F[k];
+            if (a.ensemble != 2) {
+                // ---- second half kick (src/integrate.jl:28-38)
+#pragma unroll
+                for (int k = 0; k < DIM; k++) {
+                    v[k] += (F[k] * a.dt) * 0.5;
+                    ke2 = (k == 0) ? v[k] * v[k] : ke2 + v[k] * v[k];
+                }
+            } else {
+                // ---- Brownian move (src/integrate.jl:66-82, intended semantics)
+                double noise[3];
+                brownian_noise<DIM>(a.seed, rng_step, pid, noise);
+#pragma unroll
+                for (int k = 0; k < DIM; k++) {
+                    double xv = x[k] + (F[k] * a.dt / a.ktemp) + (noise[k] * sigma_bd);
+                    double del = xv - x[k];
+                    bd2 = (k == 0) ? del * del : bd2 + del * del;
+                    double frac = g.invL[k] * xv;
+                    double ncr = floor(frac);
+                    if (ncr != 0.0) im[k] += (int32_t)ncr;
+                    x[k] = g.L[k] * (frac - ncr);
+                }
+            }
+        }
+        if (a.ensemble == 2) {
+            cluster_sync_all();   // every CTA has finished reading this step's positions (and last step's partials)
+            push_position();
+        }
+        {
+            // e, w, np are per-lane shares (their warp sum is the sum over the warp's particles); the kinetic term is the
+            // same in all lanes of a particle and is counted once
+            double vals[5] = {warp_sum(e), warp_sum(w), warp_sum(np), warp_sum(q == 0 ? ke2 : 0.0), warp_max(bd2)};
+            for (int r = lane; r < C; r += 32) {
+                double *dst = cluster.map_shared_rank(&part1[0][0], r) + gw * 5;
+#pragma unroll
+                for (int c = 0; c < 5; c++) dst[c] = vals[c];
+            }
+        }
+        cluster_sync_all();       // barrier B: per-warp sums (and Brownian positions) are in every CTA's shared memory
+        // ---- thermo scalars and thermostat (src/thermostat.jl:20-67, src/simulation.jl:118-131): every warp folds the same
+        // numbers in the same order
+        double r[4] = {0.0, 0.0, 0.0, 0.0}, dm = 0.0;
+        for (int wq = lane; wq < NW; wq += 32) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] += part1[wq][c];
+            dm = fmax(dm, part1[wq][4]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+            dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        }
+        dmax2_prev = dm;
+        if (a.ensemble == 1) {
+            // every thread evaluates the scale from the same numbers (no block barrier, no broadcast)
+            alpha = bussi_scale(r[3] / 2.0, kt_step, a.nf, a.dt, a.tau, rr.x, rr.y);
+        }
+        if (t == 0) {
+            double U = 0.5 * r[0], W = 0.5 * r[1], NP = 0.5 * r[2], KE = r[3] / 2.0;
+            if (a.ensemble == 1) KE = (alpha * alpha) * KE;
+            if (a.ensemble == 2) KE = 0.0;
+            ctl->last[0] = U; ctl->last[1] = W; ctl->last[2] = KE; ctl->last[3] = NP;
+            if (!(isfinite(U) && isfinite(KE))) ctl->nonfinite = 1;
+            if (a.thermo) {
+                a.thermo[4 * step + 0] = U; a.thermo[4 * step + 1] = W; a.thermo[4 * step + 2] = KE; a.thermo[4 * step + 3] = NP;
+            }
+        }
+        rng_step++;
+    }
+    // ---- leave the resident state as the step loop would: pending Bussi scale applied, everything back in global memory
+    if (active && q == 0) {
+        s.pos[i] = make_double4(x[0], x[1], x[2], sig);
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            s.vel[k * s.cap + i] = (a.ensemble == 1) ? v[k] * alpha : v[k];
+            s.frc[k * s.cap + i] = f[k];
+            s.img[k * s.cap + i] = im[k];
+        }
+    }
+    if (t == 0) {
+        ctl->rng_step = rng_step;
+        ctl->list_valid = 0;  // the large-system neighbour structures no longer match the positions
+        ctl->dmax2_bits = 0ull;
+        ctl->disp = 0.0;
+    }
+    cluster_sync_all();           // no CTA may exit while peers can still address its shared memory
 }
 
 }  // namespace mdb

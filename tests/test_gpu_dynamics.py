@@ -256,6 +256,53 @@ def test_small_system_persistent_kernel_matches_oracle(md, orc, ensemble):
     e.close()
 
 
+@pytest.mark.parametrize("n,lpp", [(300, 1), (1024, 1), (1200, 1), (2500, 1), (300, 8), (1024, 4), (1200, 2), (777, 4), (2048, 2)])
+def test_small_system_cluster_kernel_equals_cooperative_kernel(md, monkeypatch, n, lpp):
+    """K0-small as one thread-block cluster (cluster barriers, positions pushed through distributed shared memory, lpp lanes
+    per particle) against the cooperative-grid version of the same loop.  With one lane per particle the per-particle
+    arithmetic is the same statement by statement, so NVE and Brownian trajectories are bit-identical (only sums that
+    never feed back are folded in another order: thermo rows to 1e-13); NVT feeds the kinetic-energy sum back through
+    the thermostat: a few ulps per step.  With several lanes per particle the partial forces are added in another order:
+    pair counts stay exact, everything else agrees to rounding error carried through the run."""
+    from mdjl_b200 import workloads
+    cfg = workloads.phs_fluid(n)
+    v0 = workloads.velocities(n, 3, 1.4737)
+    out = {}
+    for name, flag in (("cluster", "1"), ("grid", "0")):
+        monkeypatch.setenv("MDB200_SMALL_CLUSTER", flag)
+        monkeypatch.setenv("MDB200_SMALL_LPP", str(lpp))
+        e = md.Engine(3, n, cfg["box"], 1.5, 0, seed=5, mode=md._capi.MODE_SMALL)
+        e.upload(cfg["x"], cfg["diam"], velocities=v0)
+        assert e.stats()["mode"] == md._capi.MODE_SMALL
+        t1 = e.run_nve(400, 1e-3)
+        s1 = e.download()
+        t2 = e.run_brownian(150, 1e-5, 1.4737)
+        s2 = e.download()
+        t3 = e.run_nvt(60, 1e-3, 1.4737, 0.1)
+        s3 = e.download()
+        out[name] = (t1, s1, t2, s2, t3, s3, e.stats()["rebuilds"])
+        e.close()
+    a, b = out["cluster"], out["grid"]
+    assert a[6] == b[6] and a[6] >= 2
+    for k in (0, 2, 4):
+        assert np.array_equal(a[k][:, 3], b[k][:, 3])                      # pair counts, every step
+    if lpp == 1:
+        for k in (1, 3):
+            for u, w in zip(a[k], b[k]):
+                assert np.array_equal(u, w)
+        for k in (0, 2):
+            assert np.allclose(a[k][:, :3], b[k][:, :3], rtol=1e-13, atol=1e-13)
+    else:
+        for k in (1, 3):
+            assert np.array_equal(a[k][3], b[k][3])                        # image counters
+            assert np.max(np.abs(a[k][0] - b[k][0])) < 1e-10 and np.max(np.abs(a[k][1] - b[k][1])) < 1e-9
+            assert np.max(np.abs(a[k][2] - b[k][2])) < 1e-8 * max(1.0, np.max(np.abs(b[k][2])))
+        for k in (0, 2):
+            assert np.allclose(a[k][:, :3], b[k][:, :3], rtol=1e-10, atol=1e-12)
+    assert np.allclose(a[4][:, :3], b[4][:, :3], rtol=1e-10)
+    assert np.max(np.abs(a[5][0] - b[5][0])) < 1e-10 and np.max(np.abs(a[5][1] - b[5][1])) < 1e-9
+
+
 def test_small_system_2d_polydisperse(md, orc):
     from mdjl_b200 import workloads
     p = workloads.poly2d(1200)
