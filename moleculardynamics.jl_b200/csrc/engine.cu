@@ -419,8 +419,9 @@ static int plan_neighbors(Engine *e)
     }
     // tiny systems: the step loop runs inside one persistent CTA (K0-small); the structures above still serve
     // mdb_compute_forces / mdb_count_pairs / mdb_fire_minimize
-    // measured on B200 (tools/small_probe.py): 15 / 20 / 41 us per step at N = 256 / 1024 / 4096 against 30 / 31 / 32 us for
-    // the graph-replayed multi-kernel step, so MDB_MODE_AUTO switches over at 2048 particles
+    // measured on B200 (tools/small_probe.py): 4.2 / 8.3 us per step at N = 256 / 1024 (thread-block cluster version), 29 us at
+    // N = 4096 (cooperative grid) against 30 / 31 / 32 us for the graph-replayed multi-kernel step, so MDB_MODE_AUTO
+    // switches over at 2048 particles
     e->small = !e->slab && !e->tri && e->cfg.potential != MDB_POT_USER &&
                ((want == MDB_MODE_AUTO && e->N <= 2048) || (want == MDB_MODE_SMALL && e->N <= kSmallMaxN));
     e->small_cluster = e->small_cluster_allowed ? -1 : 0;   // decided again at the next run (the particle count may have changed)
@@ -1882,7 +1883,7 @@ static int slab_group(Engine *e, Group &storage, Group **out)
     return MDB_OK;
 }
 
-// K0-small: one persistent CTA runs a whole chunk of steps per launch
+// K0-small: one persistent kernel (a thread-block cluster, or a cooperative grid) runs a whole chunk of steps per launch
 template <int DIM>
 static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const double *ktemp_per_step, double tau, double ktemp,
                      double *thermo)
@@ -1935,20 +1936,22 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
             DevCtl *ctl = e->ctl;
             Grid g = e->grid;
             PotParams pp = e->pp;
-            if (e->small_cluster != 0 && (e->n <= 2048 || e->small_lpp > 0)) {   // measured: 16 SMs lose to the 64-CTA grid at N = 4096
-                // one thread-block cluster: hardware cluster barriers, positions pushed through distributed shared memory,
-                // LPP lanes per particle (as many as fit 16 CTAs x 256 threads)
-                int lpp = e->n <= 512 ? 8 : (e->n <= 1024 ? 4 : (e->n <= 2048 ? 2 : 1));
+            if (e->small_cluster != 0 && e->n <= kSmallClusterMaxN) {   // measured: 16 SMs lose to the 64-CTA grid at N = 4096
+                // one thread-block cluster: positions pushed through distributed shared memory, several lanes per particle
+                // as many lanes per particle as fit 16 CTAs x kSmallClusterMaxBlock threads
+                int lpp = 8;
+                while (lpp > 1 && (int64_t)std::max(e->n, 1) * lpp > 16 * kSmallClusterMaxBlock) lpp >>= 1;
                 if (e->small_lpp == 1 || e->small_lpp == 2 || e->small_lpp == 4 || e->small_lpp == 8) lpp = std::min(lpp, e->small_lpp);
                 const int threads = std::max(e->n, 1) * lpp;
-                int block = threads > 2048 ? 256 : (threads > 1024 ? 128 : 64);
-                if (e->small_block == 64 || e->small_block == 128 || e->small_block == 256) block = e->small_block;
+                int block = std::max(64, ((threads + 15) / 16 + 31) & ~31);
+                if (e->small_block >= 64 && e->small_block <= kSmallClusterMaxBlock && e->small_block % 32 == 0) block = e->small_block;
                 int need = nblk(threads, block), csize = 1;
                 while (csize < need) csize <<= 1;
                 cudaLaunchConfig_t lc = {};
                 lc.gridDim = dim3(csize);
                 lc.blockDim = dim3(block);
-                lc.dynamicSmemBytes = smem;
+                const size_t csmem = 2 * smem;   // two position tables (alternating by step)
+                lc.dynamicSmemBytes = csmem;
                 lc.stream = s;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1959,7 +1962,7 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
                     int fits = 0;
                     if (e->small_cluster == csize) fits = 1;             // decided by an earlier launch on this handle
                     else if (csize <= 16 &&
-                             cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                             cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem) == cudaSuccess &&
                              cudaFuncSetAttribute(ck, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                              cudaOccupancyMaxActiveClusters(&fits, ck, &lc) == cudaSuccess && fits > 0)
                         fits = 1;

@@ -1,4 +1,6 @@
-// small.cuh -- K0-small: the whole step loop of src/simulation.jl:88-108 / :231-250 as ONE persistent cooperative
+// small.cuh -- K0-small: the whole step loop of src/simulation.jl:88-108 / :231-250 as ONE persistent kernel for systems
+// of a few thousand particles.  Two versions: k_small_run (cooperative grid, below; N up to 4096, fallback) and k_small_cluster
+// (one thread-block cluster, further down; default for N <= 2048).  k_small_run: a cooperative
 // kernel for systems of a few thousand particles (BASELINE configs 1 and 2: N = 1024 / 1200), where a step is a few
 // microseconds of work and per-kernel launch latency would dominate ("K0-small").
 //   * one thread per particle, 64-thread CTAs spread over as many SMs as there are CTAs (N = 1024 -> 16 SMs); the
@@ -290,31 +292,62 @@ k_small_run(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParams pp
 
 
 // ------------------------------------------------------------------------------------------------
-// K0-small, thread-block-cluster version: the same step loop with the CTAs of ONE cluster (<= 16 CTAs on the SMs of one GPC)
-// instead of a cooperative grid, and LPP lanes of a warp per particle.
-//   * the grid-wide barriers become hardware cluster barriers (barrier.cluster arrive/wait, ~0.2 us against ~2 us for a
-//     cooperative grid.sync through global memory);
+// K0-small, thread-block-cluster version (default for N <= 2048): the same step loop with the CTAs of ONE cluster (<= 16
+// CTAs on the SMs of one GPC) instead of a cooperative grid, LPP lanes of a warp per particle, and no barrier in the step.
 //   * nothing is staged from L2: the lanes of a particle PUSH its new position into the position table of every CTA of the
-//     cluster through distributed shared memory before the barrier, so after the barrier the neighbour gathers and the
-//     all-pairs list rebuild read local shared memory only;
-//   * a step of a small system is one dependent chain per thread (ncu: half of the step is the pair loop at ~14 iterations
+//     cluster through distributed shared memory (st.async ... mbarrier::complete_tx::bytes, SASS STAS), so the neighbour
+//     gathers and the all-pairs list rebuild read local shared memory only;
+//   * each CTA waits on its OWN byte-counting mbarrier for an exchange to be complete: "A" (velocity Verlet) = the drifted
+//     positions + the per-warp velocity maxima, "B" = the per-warp partial sums (+ the moved positions, Brownian dynamics).
+//     Thread 0 re-arms a barrier (arrive.expect_tx) right after its wait; bytes that land before that are counted against
+//     the new phase, which cannot complete without thread 0's arrival;
+//   * position tables, maxima and partial sums alternate between two buffers by step parity, and the two exchanges of a step
+//     order each other, so nothing is overwritten while it is still read and no phase is overrun:
+//       - a peer pushes positions(s+1) only after its B(s) wait, i.e. after it received THIS CTA's sums of step s, which this
+//         CTA sends after its pair loop of step s -- the last reader of the table positions(s+1) replaces (the one of s-1);
+//       - a peer pushes sums(s) only after its A(s) wait, i.e. after it received this CTA's positions(s), which this CTA
+//         sends after folding sums(s-1) -- and sums(s-2), the previous content of that buffer, before that;
+//       - Brownian dynamics has exchange B only: a peer pushes sums(s) and positions(s+1) after its B(s-1) wait, i.e. after
+//         it received this CTA's sums(s-1), sent after this CTA's pair loop of step s-1 and its fold of sums(s-2);
+//       - every warp of the cluster contributes bytes to every phase, so no warp can fall a whole phase behind
+//         (mbarrier.try_wait.parity tells the current phase from the previous one only);
+//     the barrier.cluster version of this loop spent 21 % of its samples in ERRBAR / barrier wait (ncu);
+//   * a step of a small system is one dependent chain per thread (ncu: half of the step was the pair loop at ~14 iterations
 //     per warp, most of them entering the interaction branch for a few lanes).  The LPP lanes of a particle hold the same
 //     state (they repeat the cheap kick / drift / move arithmetic, bit for bit), split the candidates j = q, q + LPP, ...
 //     between them -- list rebuild and pair loop -- and add their partial forces with a fixed butterfly, so every lane of
 //     the group ends with the same force bits.  LPP = 1 is the cooperative kernel's arithmetic statement by statement;
-//   * reductions: the lanes of every warp push the warp's partial sums to every CTA; after the barrier every warp folds the
-//     per-warp partials itself in one fixed order (lane l takes warps l, l+32, ... in sequence, then a fixed butterfly) --
-//     deterministic for a given (block, LPP) shape, and no block-level barrier on the way;
-//   * Brownian steps take a second cluster barrier (cheap here) instead of ping-ponging the tables: "everyone has finished
-//     reading the positions" before the moved positions are pushed.
+//   * reductions: every warp folds the per-warp partials itself in one fixed order (lane l takes warps l, l+32, ... in
+//     sequence, then a fixed butterfly) -- deterministic for a given (block, LPP) shape, no block-level barrier;
+//   * NVT: the thermostat's Gaussian and chi-square draws depend on (seed, step) only; all threads draw them for the whole
+//     chunk up front, and every thread evaluates the Bussi scale from the same numbers.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSmallMaxWarps = kSmallMaxN / 32;
-constexpr int kSmallClusterMaxBlock = 256;
+constexpr int kSmallClusterMaxN = 2048;           // two position tables of 32 B per particle in shared memory
+constexpr int kSmallClusterMaxBlock = 320;        // 204 registers per thread available (the 3-D kernels use ~180)
+constexpr int kSmallMaxWarps = 16 * kSmallClusterMaxBlock / 32;
 
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// address of `local` (a shared-memory address of this CTA) in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+// 16 bytes into a peer CTA's shared memory; the peer's mbarrier counts the bytes as they land (no fence, no cluster barrier)
+__device__ __forceinline__ void st_async_f64x2(uint32_t remote, double lo, double hi, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote), "d"(lo), "d"(hi),
+                 "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote, double val, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote), "d"(val), "r"(remote_bar) : "memory");
 }
 
 template <int DIM, class Pot, int LPP>
@@ -323,9 +356,10 @@ k_small_cluster(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParam
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ double4 spos[];                 // [n] positions of ALL particles, pushed by their owners
-    __shared__ double part0[kSmallMaxWarps];          // per-warp max |v|^2 (pushed by every warp of the cluster)
-    __shared__ double part1[kSmallMaxWarps][5];       // per-warp {e, w, np, ke2, dmax2}
+    extern __shared__ __align__(32) double4 spos_all[];             // [2][n] positions of ALL particles, pushed by their owners
+    __shared__ __align__(16) double part0[2][kSmallMaxWarps];       // per-warp max |v|^2 (pushed by every warp of the cluster)
+    __shared__ __align__(16) double part1[2][kSmallMaxWarps][6];    // per-warp {e, w, np, ke2, dmax2, 0}
+    __shared__ __align__(8) unsigned long long barA, barB;          // byte-counting barriers of the two exchanges of a step
     const StatePtrs s = ctl->st[ctl->cur];
     const int n = a.n, tid = threadIdx.x, lane = tid & 31;
     const int C = (int)gridDim.x;                     // the grid is one cluster
@@ -335,6 +369,11 @@ k_small_cluster(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParam
     const bool active = i < n;
     uint32_t *const nl = a.nl + ((size_t)(active ? i : 0) * LPP + q);   // [k][i][q]: a warp's entries of one k are contiguous
     const size_t nl_stride = (size_t)n * LPP;
+    const uint32_t barA_u = smem_u32(&barA), barB_u = smem_u32(&barB);
+    // bytes every CTA receives per exchange.  A (velocity Verlet): the drifted positions and the per-warp velocity maxima;
+    // B: the per-warp sums (and, Brownian dynamics, the moved positions)
+    const uint32_t bytesA = (uint32_t)n * 32u + (uint32_t)NW * 8u;
+    const uint32_t bytesB = (uint32_t)NW * 48u + (a.ensemble == 2 ? (uint32_t)n * 32u : 0u);
 
     double x[3] = {0, 0, 0}, v[3] = {0, 0, 0}, f[3] = {0, 0, 0}, sig = 1.0;
     int32_t im[3] = {0, 0, 0};
@@ -357,16 +396,29 @@ k_small_cluster(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParam
     unsigned long long rng_step = ctl->rng_step;
     const double sigma_bd = sqrt(2.0 * a.dt);
 
-    auto push_position = [&]() {
+    // the particle's lanes share the fan-out; table `buf`, counted by the peers' barrier `bar`
+    auto push_position = [&](int buf, uint32_t bar) {
         if (active) {
-            const double4 p = make_double4(x[0], x[1], x[2], sig);
-            for (int r = q; r < C; r += LPP) cluster.map_shared_rank(spos, r)[i] = p;   // the particle's lanes share the fan-out
+            const uint32_t slot = smem_u32(spos_all + (size_t)buf * n + i);
+            for (int r = q; r < C; r += LPP) {
+                const uint32_t dst = dsmem_addr(slot, (uint32_t)r), rb = dsmem_addr(bar, (uint32_t)r);
+                st_async_f64x2(dst, x[0], x[1], rb);
+                st_async_f64x2(dst + 16, x[2], sig, rb);
+            }
         }
     };
-    push_position();              // Brownian dynamics evaluates forces before it moves anything
+    if (tid == 0) {
+        mbar_init(&barA, 1);
+        mbar_init(&barB, 1);
+        mbar_fence_init();
+        if (a.ensemble != 2) mbar_expect_tx(&barA, bytesA);
+        mbar_expect_tx(&barB, bytesB);
+    }
+    if (active)           // Brownian dynamics evaluates forces before it moves anything: table 0, plain remote stores
+        for (int r = q; r < C; r += LPP) cluster.map_shared_rank(spos_all, r)[i] = make_double4(x[0], x[1], x[2], sig);
     if (a.ensemble == 1) {
         // the thermostat's random numbers depend on (seed, step) only: a serial chain of ~2.4 us per step when one thread
-        // draws them between the barriers -- here every thread of the cluster draws the pair of a few steps up front
+        // draws them between the exchanges -- here every thread of the cluster draws the pair of a few steps up front
         const int T = C * (int)blockDim.x;
         for (long long st = t; st < a.nsteps; st += T) {
             ThermoRng rng;
@@ -377,13 +429,17 @@ k_small_cluster(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParam
             a.rng_pre[2 * st + 1] = r2;
         }
     }
-    cluster_sync_all();           // release / acquire at cluster scope: the table above is read through L2 below
+    // the only cluster barrier before the end: barriers initialised and armed, table 0 filled, the draws visible (release /
+    // acquire at cluster scope; the table is read through L2 below)
+    cluster_sync_all();
 
     for (long long step = 0; step < a.nsteps; step++) {
+        const int par = (int)(step & 1);
+        const double4 *spos = spos_all + (size_t)par * n;    // this step's positions
         double dmax2;
         double2 rr = make_double2(0.0, 0.0);
         double kt_step = 0.0;
-        if (a.ensemble == 1) {   // needed after barrier B: on their way from L2 during the whole step
+        if (a.ensemble == 1) {   // needed after exchange B: on their way from L2 during the whole step
             rr = __ldcg(reinterpret_cast<const double2 *>(a.rng_pre) + step);
             kt_step = a.ktemp_per_step[step];
         }
@@ -404,12 +460,17 @@ k_small_cluster(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParam
                     x[k] = g.L[k] * (frac - ncr);
                 }
             }
-            push_position();
+            // ---- exchange A: positions into table `par` and the per-warp maxima, counted by every peer's barrier A
+            push_position(par, barA_u);
             v2 = warp_max(v2);
-            for (int r = lane; r < C; r += 32) cluster.map_shared_rank(part0, r)[gw] = v2;
-            cluster_sync_all();   // barrier A: new positions and the per-warp maxima are in every CTA's shared memory
+            {
+                const uint32_t slot = smem_u32(&part0[par][gw]);
+                for (int r = lane; r < C; r += 32) st_async_f64(dsmem_addr(slot, (uint32_t)r), v2, dsmem_addr(barA_u, (uint32_t)r));
+            }
+            mbar_wait(&barA, (uint32_t)par);
+            if (tid == 0) mbar_expect_tx(&barA, bytesA);     // arm the next phase (bytes that land early are counted against it)
             dmax2 = 0.0;
-            for (int w = lane; w < NW; w += 32) dmax2 = fmax(dmax2, part0[w]);
+            for (int wq = lane; wq < NW; wq += 32) dmax2 = fmax(dmax2, part0[par][wq]);
             dmax2 = warp_max(dmax2) * (a.dt * a.dt);
         } else {
             dmax2 = dmax2_prev;
@@ -504,28 +565,30 @@ k_small_cluster(DevCtl *__restrict__ ctl, Grid g, SmallArgs a, Pot pot, PotParam
                 }
             }
         }
-        if (a.ensemble == 2) {
-            cluster_sync_all();   // every CTA has finished reading this step's positions (and last step's partials)
-            push_position();
-        }
+        // ---- exchange B: the per-warp sums (Brownian dynamics: and the moved positions, into the OTHER table -- peers may
+        // still be reading this step's), counted by every peer's barrier B
+        if (a.ensemble == 2) push_position(par ^ 1, barB_u);
         {
             // e, w, np are per-lane shares (their warp sum is the sum over the warp's particles); the kinetic term is the
             // same in all lanes of a particle and is counted once
-            double vals[5] = {warp_sum(e), warp_sum(w), warp_sum(np), warp_sum(q == 0 ? ke2 : 0.0), warp_max(bd2)};
+            const double s0 = warp_sum(e), s1 = warp_sum(w), s2 = warp_sum(np), s3 = warp_sum(q == 0 ? ke2 : 0.0), s4 = warp_max(bd2);
+            const uint32_t slot = smem_u32(&part1[par][gw][0]);
             for (int r = lane; r < C; r += 32) {
-                double *dst = cluster.map_shared_rank(&part1[0][0], r) + gw * 5;
-#pragma unroll
-                for (int c = 0; c < 5; c++) dst[c] = vals[c];
+                const uint32_t dst = dsmem_addr(slot, (uint32_t)r), rb = dsmem_addr(barB_u, (uint32_t)r);
+                st_async_f64x2(dst, s0, s1, rb);
+                st_async_f64x2(dst + 16, s2, s3, rb);
+                st_async_f64x2(dst + 32, s4, 0.0, rb);
             }
         }
-        cluster_sync_all();       // barrier B: per-warp sums (and Brownian positions) are in every CTA's shared memory
+        mbar_wait(&barB, (uint32_t)par);
+        if (tid == 0) mbar_expect_tx(&barB, bytesB);
         // ---- thermo scalars and thermostat (src/thermostat.jl:20-67, src/simulation.jl:118-131): every warp folds the same
         // numbers in the same order
         double r[4] = {0.0, 0.0, 0.0, 0.0}, dm = 0.0;
         for (int wq = lane; wq < NW; wq += 32) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) r[c] += part1[wq][c];
-            dm = fmax(dm, part1[wq][4]);
+            for (int c = 0; c < 4; c++) r[c] += part1[par][wq][c];
+            dm = fmax(dm, part1[par][wq][4]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -256,7 +256,7 @@ def test_small_system_persistent_kernel_matches_oracle(md, orc, ensemble):
     e.close()
 
 
-@pytest.mark.parametrize("n,lpp", [(300, 1), (1024, 1), (1200, 1), (2500, 1), (300, 8), (1024, 4), (1200, 2), (777, 4), (2048, 2)])
+@pytest.mark.parametrize("n,lpp", [(300, 1), (1024, 1), (1200, 1), (2000, 1), (300, 8), (1024, 4), (1200, 2), (1200, 4), (640, 8), (777, 4), (2048, 2)])
 def test_small_system_cluster_kernel_equals_cooperative_kernel(md, monkeypatch, n, lpp):
     """K0-small as one thread-block cluster (cluster barriers, positions pushed through distributed shared memory, lpp lanes
     per particle) against the cooperative-grid version of the same loop.  With one lane per particle the per-particle
