@@ -432,6 +432,27 @@ def main_slabs(args, rank, world, local_rank):
     value = n * args.steps / (ms * 1e-3)
     hbm, peak_src = peaks()
 
+    # where a slab step spends its time: a SEPARATE pass of the same number of steps after the timed region, launched eagerly with
+    # CUDA events around the phases and one host sync per phase (MDB200_SLAB_PROF; the timed region above replays a graph and
+    # cannot be instrumented).  Shares of the eager step, not of the timed one.
+    phases = None
+    if not args.no_profile:
+        os.environ["MDB200_SLAB_PROF"] = "1"
+        try:
+            run(args.steps)
+            torch.cuda.synchronize()
+            st2 = ring.lead.stats()
+            if st2["prof_steps"]:
+                k = st2["prof_steps"]
+                phases = {"head_pack_flags_wait_decision": st2["prof_kick_ms"] / k, "tail_forces_thermo": st2["prof_force_ms"] / k,
+                          "rebuild_per_step": st2["prof_rebuild_ms"] / k, "eager_ms_per_step": st2["last_run_ms"] / args.steps, "steps": int(k),
+                          "how": "separate eager pass after the timed region, CUDA events per phase, one host sync per phase (rank 0)"}
+        except Exception as exc:
+            print("slab phase pass failed on rank %d: %s" % (rank, exc), file=sys.stderr)
+        finally:
+            os.environ.pop("MDB200_SLAB_PROF", None)
+        sync()
+
     e2e = None
     if not args.no_e2e:
         # steady-state round trip of a rank: hand back the rows it owns (mdb_upload_owned), step, read them again
@@ -537,9 +558,10 @@ def main_slabs(args, rank, world, local_rank):
                           "algorithmic_bytes_per_particle_step": BYTES_STEP_3D},
         "cpu_baseline": None,
         "owned_per_rank": int(st1["n_owned"]),
-        "slab_phases_ms": ({"head_kick_pack_exchange_allreduce": st1["prof_kick_ms"] / max(st1["prof_steps"], 1),
-                            "tail_forces_thermo": st1["prof_force_ms"] / max(st1["prof_steps"], 1),
-                            "rebuild_per_step": st1["prof_rebuild_ms"] / max(st1["prof_steps"], 1)} if st1["prof_steps"] else None),
+        "slab_phases_ms": phases if phases is not None else (
+            {"head_pack_flags_wait_decision": st1["prof_kick_ms"] / max(st1["prof_steps"], 1),
+             "tail_forces_thermo": st1["prof_force_ms"] / max(st1["prof_steps"], 1),
+             "rebuild_per_step": st1["prof_rebuild_ms"] / max(st1["prof_steps"], 1)} if st1["prof_steps"] else None),
         "rebuilds_in_timed_region": int(st1["rebuilds"] - st0["rebuilds"]),
         "physics": {"T_mean": float(np.mean(2 * t_thermo[:, 2] / nf)), "U_per_particle": float(np.mean(t_thermo[:, 0]) / n),
                     "E_drift_rel": float((E.max() - E.min()) / abs(E[0])) if args.ensemble == "nve" else None,

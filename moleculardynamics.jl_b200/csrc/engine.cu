@@ -1453,7 +1453,8 @@ static int group_force_phase(Group &G, int ensemble, double dt, double tau, doub
     // speculatively behind the decision, guarded on the device (a pending rebuild turns its kernels into no-ops).  In
     // the common case (no rebuild) the host returns from the read-back with the forces already running and goes on to
     // enqueue the next step; otherwise it rebuilds and enqueues the tail again, unguarded.
-    static const bool slab_prof_env = getenv("MDB200_SLAB_PROF") != nullptr;  // per-phase CUDA-event totals, one sync per phase
+    const bool slab_prof_env = getenv("MDB200_SLAB_PROF") != nullptr;  // per-phase CUDA-event totals, one sync per phase (read per call:
+                                                                         // bench.py switches it on for a separate pass after the timed region)
     const bool slab_prof = slab_prof_env && lead->prof_step_open;                // (only inside a run step: evp[5] marks its start)
     const bool speculate = !debug_sync() && !slab_prof;
     Engine *e = lead;
@@ -1727,7 +1728,7 @@ static int run_group(Group &G, int ensemble, int64_t nsteps, double dt, const do
     lead->stats.prof_kick_ms = lead->stats.prof_force_ms = lead->stats.prof_rebuild_ms = 0.0;
     lead->stats.prof_steps = 0;
     if ((rc = ensure_peer(G))) return rc;
-    static const bool slab_prof_run = getenv("MDB200_SLAB_PROF") != nullptr;
+    const bool slab_prof_run = getenv("MDB200_SLAB_PROF") != nullptr;
     // Peer-memory transport: the step is all kernels and replays as a CUDA graph (fused NVE schedule included): no host
     // round trip inside the run.  cfg.use_graph = 0, MDB200_DEBUG_SYNC and MDB200_SLAB_PROF keep the eager, host-driven
     // loop (same kernels; the rebuild decision is read back every step).
