@@ -129,6 +129,7 @@ struct mdb_engine_s {
     MigRec *mig_send[2] = {nullptr, nullptr}, *mig_recv[2] = {nullptr, nullptr};  // [0] left, [1] right
     double4 *gh_send[2] = {nullptr, nullptr};
     double4 *gpos_raw = nullptr;           // [hdr][left ghosts x ghost_cap][hdr][right ghosts x ghost_cap]
+    uint32_t *gsrc[2] = {nullptr, nullptr};   // source slot of every record of the first / last owned column (tabulated at rebuilds)
     uint32_t *row_cnt[2] = {nullptr, nullptr}, *rowoff[2] = {nullptr, nullptr}, *gcnt[2] = {nullptr, nullptr},
              *gstart[2] = {nullptr, nullptr};
     int transport = 0;                     // 0 none, 1 in-process ring (tests / one-GPU emulation), 2 NCCL
@@ -493,7 +494,8 @@ static void free_slab(Engine *e)
     peer_disconnect(e);
     for (int d = 0; d < 2; d++) {
         cudaFree(e->mig_send[d]); cudaFree(e->gh_send[d]);
-        cudaFree(e->row_cnt[d]); cudaFree(e->rowoff[d]); cudaFree(e->gcnt[d]); cudaFree(e->gstart[d]);
+        cudaFree(e->row_cnt[d]); cudaFree(e->rowoff[d]); cudaFree(e->gcnt[d]); cudaFree(e->gstart[d]); cudaFree(e->gsrc[d]);
+        e->gsrc[d] = nullptr;
         e->mig_send[d] = e->mig_recv[d] = nullptr;  // mig_recv and gpos_raw live inside the mailbox
         e->gh_send[d] = nullptr;
         e->row_cnt[d] = e->rowoff[d] = e->gcnt[d] = e->gstart[d] = nullptr;
@@ -545,6 +547,8 @@ static int alloc_slab(Engine *e)
         CU(cudaMalloc(&e->rowoff[d], sizeof(uint32_t) * nr));
         CU(cudaMalloc(&e->gcnt[d], sizeof(uint32_t) * nr));
         CU(cudaMalloc(&e->gstart[d], sizeof(uint32_t) * nr));
+        CU(cudaMalloc(&e->gsrc[d], sizeof(uint32_t) * (size_t)std::max(e->ghost_cap, 1)));
+        CU(cudaMemset(e->gsrc[d], 0, sizeof(uint32_t) * (size_t)std::max(e->ghost_cap, 1)));
         CU(cudaMemset(e->rowoff[d], 0, sizeof(uint32_t) * nr));
         CU(cudaMemset(e->gstart[d], 0, sizeof(uint32_t) * nr));
     }
@@ -1279,13 +1283,15 @@ static int rebuild_part2(Group &G)
         k_flip<<<1, 1, 0, s>>>(e->ctl, n_new);
         k_slab_rowcounts<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, s>>>(e->nrows, e->nxo, e->start, e->row_cnt[0], e->row_cnt[1]);
         k_slab_rowscan<<<1, 1024, 0, s>>>(e->nrows, e->row_cnt[0], e->rowoff[0], 0u, e->row_cnt[1], e->rowoff[1], 0u);
-        e->stats.kernel_launches += 10;
+        k_slab_ghost_src<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, s>>>(e->nrows, e->nxo, e->start, e->rowoff[0], e->rowoff[1], e->gsrc[0],
+                                                                             e->gsrc[1], e->ghost_cap);
+        e->stats.kernel_launches += 11;
         PHASE(e, "rowscan");
     }
     if (G[0]->peer) {
         for (Engine *e : G) {
-            k_peer_pack_ghost<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->nxo, e->start, e->rowoff[0],
-                                                                                          e->rowoff[1], e->links, 1, e->peer_done);
+            k_peer_pack_ghost<<<nblk(e->ghost_cap, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->rowoff[0], e->rowoff[1],
+                                                                                              e->gsrc[0], e->gsrc[1], e->links, 1, e->peer_done);
             e->stats.kernel_launches += 1;
         }
     } else
@@ -1375,8 +1381,8 @@ static int slab_head(Group &G, CondHandles hs)
         const char *mute = getenv("MDB200_PEER_TEST_MUTE_RANK");  // fault injection for the time-out test: this rank stays silent
         for (Engine *e : G) {
             if (mute && atoi(mute) == e->rank) continue;
-            k_peer_pack_ghost<<<nblk(e->nrows, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->nxo, e->start, e->rowoff[0],
-                                                                                          e->rowoff[1], e->links, 0, e->peer_done);
+            k_peer_pack_ghost<<<nblk(e->ghost_cap, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->rowoff[0], e->rowoff[1],
+                                                                                              e->gsrc[0], e->gsrc[1], e->links, 0, e->peer_done);
             e->stats.kernel_launches += 1;
         }
         for (Engine *e : G) {

@@ -258,6 +258,13 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsign
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// flag store behind an explicit __threadfence_system(): fence + relaxed store is a release, and ONE fence covers every flag
+// that follows it.  A st.release.sys per flag carries a system-scope fence each: P + 2 of them in a row made the publishing
+// thread of the per-step pack kernel the longest part of a slab step's head (ncu: 21 us per launch with 2 ranks)
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -287,52 +294,78 @@ __device__ __forceinline__ double4 *peer_ghost(const PeerView &v, int parity, in
 }
 
 // Boundary columns -> the NEIGHBOURS' ghost buffers (same row-by-row order as k_slab_pack_ghost), then the flags.
+// rebuild: source slot of every record of the two boundary columns, in the order the ghost buffers keep (row by row, slot
+// order inside a cell): gsrc_l[rowoff_l[row] + k] = start[row * nxo] + k, likewise for the last column
+__global__ void k_slab_ghost_src(int nrows, int nxo, const uint32_t *__restrict__ start, const uint32_t *__restrict__ rowoff_l,
+                                 const uint32_t *__restrict__ rowoff_r, uint32_t *__restrict__ gsrc_l, uint32_t *__restrict__ gsrc_r, int ghost_cap)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const uint32_t cap = (uint32_t)ghost_cap;
+    uint32_t b = (uint32_t)row * nxo;
+    uint32_t o = rowoff_l[row];
+    for (uint32_t j = start[b]; j < start[b + 1]; j++, o++)
+        if (o < cap) gsrc_l[o] = j;
+    o = rowoff_r[row];
+    for (uint32_t j = start[b + nxo - 1]; j < start[b + nxo]; j++, o++)
+        if (o < cap) gsrc_r[o] = j;
+}
+
 // kind 0: head of a force evaluation (epoch E = ctl->epoch + 1): per-step ghost flag + this rank's displacement bound
 //         into every rank's reduction slot;  kind 1: rebuild (E = ctl->epoch, already advanced): rebuild ghost flag.
 // `done` is a zeroed counter used to find the last CTA (it re-zeroes it).
 __global__ void __launch_bounds__(kStreamBlock)
-k_peer_pack_ghost(DevCtl *ctl, int nrows, int nxo, const uint32_t *__restrict__ start, const uint32_t *__restrict__ rowoff_l,
-                  const uint32_t *__restrict__ rowoff_r, PeerLinks lk, int kind, unsigned int *done)
+k_peer_pack_ghost(DevCtl *ctl, int nrows, const uint32_t *__restrict__ rowoff_l, const uint32_t *__restrict__ rowoff_r,
+                  const uint32_t *__restrict__ gsrc_l, const uint32_t *__restrict__ gsrc_r, PeerLinks lk, int kind, unsigned int *done)
 {
+    // one thread per ghost RECORD (source slots tabulated at the rebuild by k_slab_ghost_src): index -> record -> remote store,
+    // two independent chains per thread.  The first version walked one cell row per thread (row offsets -> cell ranges -> a serial
+    // loop per column): 26 us per launch at 16 000 rows, the bulk of a slab step's head (ncu, tools/peer_head_probe.py)
     const double4 *__restrict__ pos = ctl->st[ctl->cur].pos;
     const unsigned long long E = ctl->epoch + (kind == 0 ? 1ull : 0ull);
     const int par = (int)(E & 1ull);
     double4 *out_l = peer_ghost(lk.left, par, 1, lk.ghost_cap);   // my first column is the left neighbour's RIGHT ghost column
     double4 *out_r = peer_ghost(lk.right, par, 0, lk.ghost_cap);
     const uint32_t cap = (uint32_t)lk.ghost_cap;
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row == 0) {
-        uint32_t tl = rowoff_l[nrows], tr = rowoff_r[nrows];
+    const uint32_t tl = rowoff_l[nrows], tr = rowoff_r[nrows];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
         if (tl > cap || tr > cap) atomicOr(&ctl->error, kErrGhostOverflow);
         out_l[0] = make_double4((double)min(tl, cap), 0, 0, 0);
         out_r[0] = make_double4((double)min(tr, cap), 0, 0, 0);
     }
-    if (row < nrows) {
-        uint32_t b = (uint32_t)row * nxo;
-        uint32_t o = rowoff_l[row];
-        for (uint32_t j = start[b]; j < start[b + 1]; j++, o++)
-            if (o < cap) out_l[1 + o] = pos[j];
-        o = rowoff_r[row];
-        for (uint32_t j = start[b + nxo - 1]; j < start[b + nxo]; j++, o++)
-            if (o < cap) out_r[1 + o] = pos[j];
-    }
-    __threadfence_system();  // this thread's remote stores are visible system-wide before the CTA reports
+    const bool hl = t < min(tl, cap), hr = t < min(tr, cap);
+    uint32_t jl = 0, jr = 0;
+    if (hl) jl = gsrc_l[t];
+    if (hr) jr = gsrc_r[t];
+    double4 pl = make_double4(0, 0, 0, 0), pr = pl;
+    if (hl) pl = ld_pos(pos + jl);
+    if (hr) pr = ld_pos(pos + jr);
+    if (hl) st_pos(out_l + 1 + t, pl);
+    if (hr) st_pos(out_r + 1 + t, pr);
+    // CTA barrier, then ONE system-scope fence by the reporting thread: the barrier orders every thread's stores before it and
+    // the fence is cumulative (the pattern of a cooperative-groups multi-device barrier).  A fence per thread measured 20 us per
+    // launch for 66 000 records -- MEMBAR.SYS, not the copies, was the cost of this kernel
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int k = atomicAdd(done, 1u);
         if (k == gridDim.x - 1) {  // last CTA: everybody's stores are out
             *done = 0u;
-            __threadfence_system();
             if (kind == 0) {
                 const unsigned long long bits = ctl->dmax2_bits;
                 for (int r = 0; r < lk.nranks; r++) lk.all[r]->red_val[par][lk.me] = bits;
-                __threadfence_system();
-                for (int r = 0; r < lk.nranks; r++) st_release_sys_u64(&lk.all[r]->red_tag[par][lk.me], E);
-                st_release_sys_u64(&lk.left.hdr->ghost_flag[1], E);
-                st_release_sys_u64(&lk.right.hdr->ghost_flag[0], E);
+            }
+            // one fence: every CTA's records (each CTA fenced before it reported to `done`; fence - atomic - atomic - fence
+            // synchronises) and the bound above are visible system-wide before any of the flags below
+            __threadfence_system();
+            if (kind == 0) {
+                for (int r = 0; r < lk.nranks; r++) st_relaxed_sys_u64(&lk.all[r]->red_tag[par][lk.me], E);
+                st_relaxed_sys_u64(&lk.left.hdr->ghost_flag[1], E);
+                st_relaxed_sys_u64(&lk.right.hdr->ghost_flag[0], E);
             } else {
-                st_release_sys_u64(&lk.left.hdr->rghost_flag[1], E);
-                st_release_sys_u64(&lk.right.hdr->rghost_flag[0], E);
+                st_relaxed_sys_u64(&lk.left.hdr->rghost_flag[1], E);
+                st_relaxed_sys_u64(&lk.right.hdr->rghost_flag[0], E);
             }
         }
     }
@@ -398,8 +431,8 @@ __global__ void k_peer_mig_publish(DevCtl *ctl, PeerLinks lk)
     out_l[0].p.x = (double)min(ctl->mig_count[0], lk.mig_cap);
     out_r[0].p.x = (double)min(ctl->mig_count[1], lk.mig_cap);
     __threadfence_system();
-    st_release_sys_u64(&lk.left.hdr->mig_flag[1], E);
-    st_release_sys_u64(&lk.right.hdr->mig_flag[0], E);
+    st_relaxed_sys_u64(&lk.left.hdr->mig_flag[1], E);
+    st_relaxed_sys_u64(&lk.right.hdr->mig_flag[0], E);
 }
 // which: 0 migration flags, 1 rebuild-ghost flags (both sides), epoch = ctl->epoch
 __global__ void k_peer_wait(PeerLinks lk, int which, DevCtl *ctl)
@@ -421,7 +454,7 @@ __global__ void k_peer_sum_publish(DevCtl *ctl, PeerLinks lk, int guard)
     for (int r = 0; r < lk.nranks; r++)
         for (int c = 0; c < 4; c++) lk.all[r]->sum_val[par][lk.me][c] = ctl->red[c];
     __threadfence_system();
-    for (int r = 0; r < lk.nranks; r++) st_release_sys_u64(&lk.all[r]->sum_tag[par][lk.me], E);
+    for (int r = 0; r < lk.nranks; r++) st_relaxed_sys_u64(&lk.all[r]->sum_tag[par][lk.me], E);
 }
 // ... and the global sums, added in rank order (the same bits on every rank), back into ctl->red for k_finalize stage 2
 __global__ void k_peer_sum_wait(DevCtl *ctl, PeerLinks lk, int guard)
