@@ -1290,7 +1290,7 @@ static int rebuild_part2(Group &G)
     }
     if (G[0]->peer) {
         for (Engine *e : G) {
-            k_peer_pack_ghost<<<nblk(e->ghost_cap, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->rowoff[0], e->rowoff[1],
+            k_peer_pack_ghost<<<nblk(e->ghost_cap, kPackBlock), kPackBlock, 0, e->stream>>>(e->ctl, e->nrows, e->rowoff[0], e->rowoff[1],
                                                                                               e->gsrc[0], e->gsrc[1], e->links, 1, e->peer_done);
             e->stats.kernel_launches += 1;
         }
@@ -1381,7 +1381,7 @@ static int slab_head(Group &G, CondHandles hs)
         const char *mute = getenv("MDB200_PEER_TEST_MUTE_RANK");  // fault injection for the time-out test: this rank stays silent
         for (Engine *e : G) {
             if (mute && atoi(mute) == e->rank) continue;
-            k_peer_pack_ghost<<<nblk(e->ghost_cap, kStreamBlock), kStreamBlock, 0, e->stream>>>(e->ctl, e->nrows, e->rowoff[0], e->rowoff[1],
+            k_peer_pack_ghost<<<nblk(e->ghost_cap, kPackBlock), kPackBlock, 0, e->stream>>>(e->ctl, e->nrows, e->rowoff[0], e->rowoff[1],
                                                                                               e->gsrc[0], e->gsrc[1], e->links, 0, e->peer_done);
             e->stats.kernel_launches += 1;
         }

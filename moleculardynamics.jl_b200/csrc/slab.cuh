@@ -314,7 +314,8 @@ __global__ void k_slab_ghost_src(int nrows, int nxo, const uint32_t *__restrict_
 // kind 0: head of a force evaluation (epoch E = ctl->epoch + 1): per-step ghost flag + this rank's displacement bound
 //         into every rank's reduction slot;  kind 1: rebuild (E = ctl->epoch, already advanced): rebuild ghost flag.
 // `done` is a zeroed counter used to find the last CTA (it re-zeroes it).
-__global__ void __launch_bounds__(kStreamBlock)
+constexpr int kPackBlock = 1024;   // one system-scope fence per CTA: few, large CTAs
+__global__ void __launch_bounds__(kPackBlock)
 k_peer_pack_ghost(DevCtl *ctl, int nrows, const uint32_t *__restrict__ rowoff_l, const uint32_t *__restrict__ rowoff_r,
                   const uint32_t *__restrict__ gsrc_l, const uint32_t *__restrict__ gsrc_r, PeerLinks lk, int kind, unsigned int *done)
 {
