@@ -1976,8 +1976,12 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
                     else fits = 0;
                     (void)cudaGetLastError();
                     if (!fits) return false;
+                    const cudaError_t ce = cudaLaunchKernelEx(&lc, ck, ctl, g, a, pot, pp);
+                    if (ce != cudaSuccess) {   // refused at launch (nothing ran): fall back to the cooperative grid
+                        (void)cudaGetLastError();
+                        return false;
+                    }
                     e->small_cluster = csize;
-                    le = cudaLaunchKernelEx(&lc, ck, ctl, g, a, pot, pp);
                     return true;
                 };
                 bool launched = lpp == 8 ? go(k_small_cluster<DIM, Pot, 8>) : lpp == 4 ? go(k_small_cluster<DIM, Pot, 4>)
