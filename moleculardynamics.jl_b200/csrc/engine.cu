@@ -1897,8 +1897,9 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
 {
     cudaStream_t s = e->stream;
     {
-        // the cluster version keeps one sub-list per lane of a particle: at most 8 lanes, at most 4096 threads
-        const size_t need = (size_t)e->small_kmax * (size_t)std::max(std::max(e->n, 1), std::min(8 * std::max(e->n, 1), 4096));
+        // the cluster version keeps one sub-list of capacity kmax per lane of a particle: at most 8 lanes per particle and at most
+        // 16 CTAs x kSmallClusterMaxBlock threads in all (the launch below picks the lanes by the same bound)
+        const size_t need = (size_t)e->small_kmax * (size_t)std::max(std::max(e->n, 1), std::min(8 * std::max(e->n, 1), 16 * kSmallClusterMaxBlock));
         if (!e->small_nl || e->small_nl_words < need) {
             cudaFree(e->small_nl);
             e->small_nl = nullptr;
