@@ -1968,12 +1968,13 @@ static int run_small(Engine *e, int ensemble, int64_t nsteps, double dt, const d
                 lc.numAttrs = 1;
                 auto go = [&](auto ck) {
                     int fits = 0;
-                    if (e->small_cluster == csize) fits = 1;             // decided by an earlier launch on this handle
-                    else if (csize <= 16 &&
-                             cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem) == cudaSuccess &&
-                             cudaFuncSetAttribute(ck, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                             cudaOccupancyMaxActiveClusters(&fits, ck, &lc) == cudaSuccess && fits > 0)
-                        fits = 1;
+                    // the attributes belong to the FUNCTION (shared by every handle of the process): set them before every
+                    // launch; only the occupancy answer is remembered per handle
+                    const bool attrs = csize <= 16 &&
+                                       cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem) == cudaSuccess &&
+                                       cudaFuncSetAttribute(ck, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+                    if (attrs && e->small_cluster == csize) fits = 1;    // decided by an earlier launch on this handle
+                    else if (attrs && cudaOccupancyMaxActiveClusters(&fits, ck, &lc) == cudaSuccess && fits > 0) fits = 1;
                     else fits = 0;
                     (void)cudaGetLastError();
                     if (!fits) return false;
